@@ -1,0 +1,691 @@
+// engine.cu — C ABI (include/vpmb200.h) of the B200-native rVPM particle-field engine.
+//
+// One engine = one CUDA device + one stream + a device-resident SoA particle field.  Every entry point mirrors a
+// call FLOWUnsteady makes on FLOWVPM's ParticleField (citations in include/vpmb200.h).  No CPU fallback exists:
+// creation fails without an sm_100 device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/vpmb200.h"
+#include "estr_direct.cuh"
+#include "field_kernels.cuh"
+#include "uj_direct.cuh"
+#include "uj_direct_f32.cuh"
+
+using namespace vpm;
+
+struct vpmb200_engine {
+    int device = 0;
+    int float_bits = 64;
+    cudaStream_t stream = nullptr;
+    int64_t maxp = 0, ld = 0, np = 0;
+    double* state = nullptr;    // NFIELDS x ld
+    double* rec = nullptr;      // source records (UJ or E_str pass)
+    double* aos = nullptr;      // AoS staging, maxp x NFIELDS
+    double* gh_table = nullptr; // Gaussian-erf G/H table
+    double* z_table = nullptr;  // Gaussian-erf zeta table
+    float* gh_table_f32 = nullptr;
+    double* probe = nullptr;    // probe scratch: 3 (X) + 3 (U) + 9 (J) rows of probe_ld, + AoS staging
+    int64_t probe_cap = 0;
+    unsigned long long* counter = nullptr;
+    double t = 0.0;
+    int64_t nt = 0;
+    vpmb200_schemes sch;
+    std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int32_t fail(vpmb200_engine* e, int32_t code, const std::string& msg) {
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(e, call)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t _st = (call);                                                                         \
+        if (_st != cudaSuccess)                                                                           \
+            return fail((e), VPMB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_st));         \
+    } while (0)
+
+#define CHECK_HANDLE(h) \
+    if (!(h)) return VPMB200_EINVAL
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline unsigned blocks_for(int64_t n, int bt) { return (unsigned)((n + bt - 1) / bt); }
+
+double zeta0_of(int kernel) {
+    switch (kernel) {
+    case K_GAUSSIANERF: return CONST1;
+    case K_WINCKELMANS: return CONST4 * 7.5;
+    case K_GAUSSIAN: return 3 * CONST4;
+    default: return 1.0;
+    }
+}
+
+template <int K>
+cudaError_t launch_uj(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty,
+                      const double* tz, int64_t nt, double* U, double* J, int64_t ldo, int accumulate) {
+    if (nt <= 0) return cudaSuccess;
+    if (e->float_bits == 32) {
+        auto kfn = uj_direct_f32_kernel<K>;
+        size_t smem = uj_f32_smem_bytes(K);
+        cudaError_t st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (st != cudaSuccess) return st;
+        kfn<<<blocks_for(nt, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate,
+                                                             e->gh_table_f32);
+        return cudaGetLastError();
+    }
+    auto kfn = uj_direct_f64_kernel<K>;
+    size_t smem = uj_smem_bytes(K);
+    cudaError_t st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return st;
+    kfn<<<blocks_for(nt, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate,
+                                                         e->gh_table);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_uj(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty,
+                        const double* tz, int64_t nt, double* U, double* J, int64_t ldo, int accumulate) {
+    switch (e->sch.kernel) {
+    case K_GAUSSIANERF: return launch_uj<K_GAUSSIANERF>(e, rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate);
+    case K_WINCKELMANS: return launch_uj<K_WINCKELMANS>(e, rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate);
+    case K_GAUSSIAN: return launch_uj<K_GAUSSIAN>(e, rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate);
+    default: return launch_uj<K_SINGULAR>(e, rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate);
+    }
+}
+
+template <int K>
+cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
+    if (e->np <= 0) return cudaSuccess;
+    auto kfn = estr_direct_f64_kernel<K>;
+    size_t smem = estr_smem_bytes(K);
+    cudaError_t st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st != cudaSuccess) return st;
+    const double* S = e->state;
+    const int64_t ld = e->ld;
+    kfn<<<blocks_for(e->np, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld,
+                                                            S + (size_t)(F_X + 2) * ld, e->np, S + (size_t)F_J * ld, ld,
+                                                            e->sch.transposed, e->state + (size_t)F_SFS * ld, ld,
+                                                            e->z_table);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
+    switch (e->sch.kernel) {
+    case K_GAUSSIANERF: return launch_estr<K_GAUSSIANERF>(e, rec, ntiles);
+    case K_WINCKELMANS: return launch_estr<K_WINCKELMANS>(e, rec, ntiles);
+    case K_GAUSSIAN: return launch_estr<K_GAUSSIAN>(e, rec, ntiles);
+    default: return launch_estr<K_SINGULAR>(e, rec, ntiles);
+    }
+}
+
+int32_t zero_rows(vpmb200_engine* e, int first, int count) {
+    if (e->np <= 0) return VPMB200_OK;
+    zero_rows_kernel<<<blocks_for(e->np, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, first, count);
+    CU_TRY(e, cudaGetLastError());
+    return VPMB200_OK;
+}
+
+int32_t do_reset(vpmb200_engine* e) {
+    int32_t rc = zero_rows(e, F_U, 3);
+    if (rc) return rc;
+    rc = zero_rows(e, F_J, 9);
+    if (rc) return rc;
+    return zero_rows(e, F_PSE, 3);
+}
+
+int32_t pack_uj(vpmb200_engine* e, double* dst) {
+    int64_t ntot = round_up(e->np, TILE_SRC);
+    if (ntot == 0) return VPMB200_OK;
+    pack_uj_records_kernel<<<blocks_for(ntot, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, ntot, dst);
+    CU_TRY(e, cudaGetLastError());
+    return VPMB200_OK;
+}
+
+int32_t pack_estr(vpmb200_engine* e, double* dst) {
+    int64_t ntot = round_up(e->np, TILE_SRC);
+    if (ntot == 0) return VPMB200_OK;
+    pack_estr_records_kernel<<<blocks_for(ntot, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, ntot,
+                                                                             e->sch.transposed, zeta0_of(e->sch.kernel), dst);
+    CU_TRY(e, cudaGetLastError());
+    return VPMB200_OK;
+}
+
+int32_t uj_local_from(vpmb200_engine* e, const double* rec, int64_t nsrc, int accumulate) {
+    double* S = e->state;
+    const int64_t ld = e->ld;
+    int ntiles = (int)(round_up(nsrc, TILE_SRC) / TILE_SRC);
+    CU_TRY(e, dispatch_uj(e, rec, ntiles, S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld, S + (size_t)(F_X + 2) * ld,
+                          e->np, S + (size_t)F_U * ld, S + (size_t)F_J * ld, ld, accumulate));
+    return VPMB200_OK;
+}
+
+// pfield.UJ(pfield; reset, reset_sfs, sfs) on the direct path
+int32_t do_uj(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
+    if (e->sch.uj != VPMB200_UJ_DIRECT) return fail(e, VPMB200_ENOTSUP, "UJ_fmm is not built in this round; use uj = direct");
+    int32_t rc;
+    if (reset && (rc = zero_rows(e, F_PSE, 3))) return rc;
+    if (reset_sfs && (rc = zero_rows(e, F_SFS, 3))) return rc;
+    if (e->np <= 0) return VPMB200_OK;
+    if ((rc = pack_uj(e, e->rec))) return rc;
+    if ((rc = uj_local_from(e, e->rec, e->np, reset ? 0 : 1))) return rc;
+    if (sfs) {
+        if ((rc = pack_estr(e, e->rec))) return rc;
+        int ntiles = (int)(round_up(e->np, TILE_SRC) / TILE_SRC);
+        CU_TRY(e, dispatch_estr(e, e->rec, ntiles));
+    }
+    return VPMB200_OK;
+}
+
+int32_t do_stage(vpmb200_engine* e, int stage, double a, double b, double dt, const double* Uinf, int relax_inline) {
+    if (e->np <= 0) return VPMB200_OK;
+    const vpmb200_schemes& s = e->sch;
+    const unsigned nb = blocks_for(e->np, PK_BT);
+    const double zeta0 = zeta0_of(s.kernel);
+    switch (stage) {
+    case VPMB200_STAGE_SCALE_SIGMA_TEST:
+        scale_sigma_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.alpha, 0);
+        break;
+    case VPMB200_STAGE_STORE_TEST:
+        dyn_store_test_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.transposed);
+        break;
+    case VPMB200_STAGE_SCALE_SIGMA_DOMAIN:
+        scale_sigma_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.alpha, 1);
+        break;
+    case VPMB200_STAGE_DYNAMIC_COEFF:
+        dyn_coeff_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.transposed, s.alpha, s.sfs_rlxf, s.minC,
+                                                    s.maxC, s.force_positive, zeta0);
+        break;
+    case VPMB200_STAGE_CONSTANT_COEFF:
+        const_coeff_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.Cs);
+        break;
+    case VPMB200_STAGE_CLIP_CONTROL:
+        if (s.clippings || s.controls)
+            clip_control_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.clippings, s.controls, s.f, zeta0,
+                                                           e->t, e->nt);
+        break;
+    case VPMB200_STAGE_ZERO_M:
+        zero_m_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np);
+        break;
+    case VPMB200_STAGE_UPDATE: {
+        if (!Uinf) return fail(e, VPMB200_EINVAL, "stage UPDATE needs Uinf");
+        UpdateParams p;
+        p.a = a; p.b = b; p.dt = dt;
+        p.Uinf0 = Uinf[0]; p.Uinf1 = Uinf[1]; p.Uinf2 = Uinf[2];
+        p.f = s.f; p.g = s.g; p.zeta0 = zeta0; p.nu = s.nu; p.rlxf = s.rlxf;
+        p.transposed = s.transposed; p.viscous = s.viscous; p.relaxation = s.relaxation;
+        p.euler = (s.integration == VPMB200_INTEGRATION_EULER);
+        p.relax_inline = relax_inline;
+        update_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, p);
+        break;
+    }
+    case VPMB200_STAGE_RELAX:
+        if (s.relaxation != VPMB200_RELAX_NONE)
+            relax_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.relaxation, s.rlxf);
+        break;
+    default:
+        return fail(e, VPMB200_EINVAL, "unknown stage id");
+    }
+    CU_TRY(e, cudaGetLastError());
+    return VPMB200_OK;
+}
+
+// pfield.SFS(pfield; a, b)   (oracle: vpmo_field_sfs)
+int32_t do_sfs(vpmb200_engine* e, double a, double b) {
+    (void)b;
+    const vpmb200_schemes& s = e->sch;
+    const bool first = (a == 1.0 || a == 0.0);
+    int32_t rc;
+    switch (s.sfs) {
+    case VPMB200_SFS_NONE:
+        return do_uj(e, 1, 0, 0);
+    case VPMB200_SFS_CONSTANT:
+        if ((rc = do_uj(e, 1, 1, 1))) return rc;
+        if (first) {
+            if ((rc = do_stage(e, VPMB200_STAGE_CONSTANT_COEFF, 0, 0, 0, nullptr, 0))) return rc;
+            if ((rc = do_stage(e, VPMB200_STAGE_CLIP_CONTROL, 0, 0, 0, nullptr, 0))) return rc;
+        }
+        return VPMB200_OK;
+    case VPMB200_SFS_DYNAMIC:
+        if (!first) return do_uj(e, 1, 1, 1);
+        if ((rc = do_stage(e, VPMB200_STAGE_SCALE_SIGMA_TEST, 0, 0, 0, nullptr, 0))) return rc;
+        if ((rc = do_uj(e, 1, 1, 1))) return rc;
+        if ((rc = do_stage(e, VPMB200_STAGE_STORE_TEST, 0, 0, 0, nullptr, 0))) return rc;
+        if ((rc = do_stage(e, VPMB200_STAGE_SCALE_SIGMA_DOMAIN, 0, 0, 0, nullptr, 0))) return rc;
+        if ((rc = do_uj(e, 1, 1, 1))) return rc;
+        if ((rc = do_stage(e, VPMB200_STAGE_DYNAMIC_COEFF, 0, 0, 0, nullptr, 0))) return rc;
+        return do_stage(e, VPMB200_STAGE_CLIP_CONTROL, 0, 0, 0, nullptr, 0);
+    default:
+        return fail(e, VPMB200_EINVAL, "unknown SFS scheme id");
+    }
+}
+
+int32_t check_schemes(vpmb200_engine* e, const vpmb200_schemes* s) {
+    if (s->kernel < 0 || s->kernel > 3) return fail(e, VPMB200_EINVAL, "kernel id out of range");
+    if (s->relaxation < 0 || s->relaxation > 2) return fail(e, VPMB200_EINVAL, "relaxation id out of range");
+    if (s->sfs < 0 || s->sfs > 2) return fail(e, VPMB200_EINVAL, "SFS id out of range");
+    if (s->viscous < 0 || s->viscous > 1) return fail(e, VPMB200_EINVAL, "viscous id out of range");
+    if (s->integration < 0 || s->integration > 1) return fail(e, VPMB200_EINVAL, "integration id out of range");
+    if (s->uj < 0 || s->uj > 1) return fail(e, VPMB200_EINVAL, "UJ id out of range");
+    if (s->sfs == VPMB200_SFS_DYNAMIC && (s->minC < 0 || s->maxC < s->minC))
+        return fail(e, VPMB200_EINVAL, "DynamicSFS needs 0 <= minC <= maxC");
+    if (s->sfs == VPMB200_SFS_DYNAMIC && !(s->alpha > 0)) return fail(e, VPMB200_EINVAL, "DynamicSFS needs alpha > 0");
+    if (s->controls & ~(VPMB200_CTRL_DIRECTIONAL | VPMB200_CTRL_MAGNITUDE))
+        return fail(e, VPMB200_ENOTSUP, "control_sigmasensor is not implemented (upstream form unverified)");
+    if (s->viscous == VPMB200_VISCOUS_CORESPREADING && s->kernel != VPMB200_KERNEL_GAUSSIANERF)
+        return fail(e, VPMB200_EINVAL, "CoreSpreading requires the gaussianerf kernel (vpm._kernel_compatibility)");
+    return VPMB200_OK;
+}
+
+int32_t ensure_probe(vpmb200_engine* e, int64_t m) {
+    if (m <= e->probe_cap) return VPMB200_OK;
+    if (e->probe) cudaFree(e->probe);
+    e->probe = nullptr;
+    e->probe_cap = 0;
+    int64_t cap = round_up(m, 1024);
+    // rows: 3 X + 3 U + 9 J (SoA, ld = cap) followed by AoS staging of 12 * cap
+    CU_TRY(e, cudaMalloc(&e->probe, sizeof(double) * (size_t)cap * (15 + 12)));
+    e->probe_cap = cap;
+    return VPMB200_OK;
+}
+
+// AoS [n][nc] <-> SoA rows of length ld (small helper kernels for probes)
+__global__ void split_rows_kernel(const double* __restrict__ aos, int nc, int64_t n, double* __restrict__ soa, int64_t ld) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < nc; ++c) soa[(size_t)c * ld + i] = aos[i * nc + c];
+}
+__global__ void join_rows_kernel(const double* __restrict__ soa, int64_t ld, int nc, int64_t n, double* __restrict__ aos) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < nc; ++c) aos[i * nc + c] = soa[(size_t)c * ld + i];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vpmb200_version(void) { return "vpmb200 0.1 (sm_100a)"; }
+
+int32_t vpmb200_default_schemes(vpmb200_schemes* s) {
+    if (!s) return VPMB200_EINVAL;
+    std::memset(s, 0, sizeof(*s));
+    s->kernel = VPMB200_KERNEL_GAUSSIANERF;
+    s->f = 0.0;
+    s->g = 1.0 / 5.0;
+    s->transposed = 1;
+    s->relaxation = VPMB200_RELAX_PEDRIZZETTI;
+    s->rlxf = 0.3;
+    s->sfs = VPMB200_SFS_NONE;
+    s->alpha = 0.999;
+    s->sfs_rlxf = 0.005;
+    s->minC = 0.0;
+    s->maxC = 1.0;
+    s->Cs = 1.0;
+    s->viscous = VPMB200_VISCOUS_INVISCID;
+    s->integration = VPMB200_INTEGRATION_RK3;
+    s->uj = VPMB200_UJ_DIRECT;
+    s->fmm_p = 4;
+    s->fmm_ncrit = 50;
+    s->fmm_theta = 0.4;
+    s->fmm_nonzero_sigma = 0;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_create(int64_t max_particles, int32_t nfields, int32_t float_bits, int32_t device, vpmb200_handle* out) {
+    if (!out) return VPMB200_EINVAL;
+    *out = nullptr;
+    if (max_particles <= 0) return fail(nullptr, VPMB200_EINVAL, "max_particles must be positive");
+    if (nfields != NFIELDS) return fail(nullptr, VPMB200_EINVAL, "nfields must be 43");
+    if (float_bits != 64 && float_bits != 32) return fail(nullptr, VPMB200_EINVAL, "float_bits must be 64 or 32");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(nullptr, VPMB200_ENODEVICE, "no CUDA device: the engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, VPMB200_EINVAL, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, VPMB200_ENODEVICE, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+    vpmb200_engine* e = new (std::nothrow) vpmb200_engine();
+    if (!e) return VPMB200_EINVAL;
+    e->device = device;
+    e->float_bits = float_bits;
+    e->maxp = max_particles;
+    e->ld = round_up(max_particles, 256);
+    vpmb200_default_schemes(&e->sch);
+#define CREATE_TRY(call)                                                                         \
+    do {                                                                                         \
+        cudaError_t _st = (call);                                                                \
+        if (_st != cudaSuccess) {                                                                \
+            g_create_error = std::string(#call) + ": " + cudaGetErrorString(_st);                \
+            vpmb200_destroy(e);                                                                  \
+            return VPMB200_ECUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaMalloc(&e->state, sizeof(double) * (size_t)NFIELDS * e->ld));
+    CREATE_TRY(cudaMemsetAsync(e->state, 0, sizeof(double) * (size_t)NFIELDS * e->ld, e->stream));
+    CREATE_TRY(cudaMalloc(&e->rec, sizeof(double) * (size_t)vpmb200_record_doubles(e->maxp)));
+    CREATE_TRY(cudaMalloc(&e->aos, sizeof(double) * (size_t)NFIELDS * e->maxp));
+    CREATE_TRY(cudaMalloc(&e->gh_table, sizeof(vpm_gt_GH)));
+    CREATE_TRY(cudaMalloc(&e->z_table, sizeof(vpm_gt_Z)));
+    CREATE_TRY(cudaMalloc(&e->gh_table_f32, sizeof(vpm_gt32_GH)));
+    CREATE_TRY(cudaMalloc(&e->counter, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemcpyAsync(e->gh_table, vpm_gt_GH, sizeof(vpm_gt_GH), cudaMemcpyHostToDevice, e->stream));
+    CREATE_TRY(cudaMemcpyAsync(e->z_table, vpm_gt_Z, sizeof(vpm_gt_Z), cudaMemcpyHostToDevice, e->stream));
+    CREATE_TRY(cudaMemcpyAsync(e->gh_table_f32, vpm_gt32_GH, sizeof(vpm_gt32_GH), cudaMemcpyHostToDevice, e->stream));
+    CREATE_TRY(cudaStreamSynchronize(e->stream));
+#undef CREATE_TRY
+    *out = e;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_destroy(vpmb200_handle e) {
+    CHECK_HANDLE(e);
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->state);
+    cudaFree(e->rec);
+    cudaFree(e->aos);
+    cudaFree(e->gh_table);
+    cudaFree(e->z_table);
+    cudaFree(e->gh_table_f32);
+    cudaFree(e->probe);
+    cudaFree(e->counter);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return VPMB200_OK;
+}
+
+const char* vpmb200_last_error(vpmb200_handle e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int32_t vpmb200_set_schemes(vpmb200_handle e, const vpmb200_schemes* s) {
+    CHECK_HANDLE(e);
+    if (!s) return fail(e, VPMB200_EINVAL, "schemes is NULL");
+    int32_t rc = check_schemes(e, s);
+    if (rc) return rc;
+    e->sch = *s;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_get_schemes(vpmb200_handle e, vpmb200_schemes* s) {
+    CHECK_HANDLE(e);
+    if (!s) return fail(e, VPMB200_EINVAL, "schemes is NULL");
+    *s = e->sch;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_set_time(vpmb200_handle e, double t, int64_t nt) {
+    CHECK_HANDLE(e);
+    e->t = t;
+    e->nt = nt;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_get_time(vpmb200_handle e, double* t, int64_t* nt) {
+    CHECK_HANDLE(e);
+    if (t) *t = e->t;
+    if (nt) *nt = e->nt;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_get_np(vpmb200_handle e, int64_t* np) {
+    CHECK_HANDLE(e);
+    if (!np) return fail(e, VPMB200_EINVAL, "np is NULL");
+    *np = e->np;
+    return VPMB200_OK;
+}
+
+static int32_t upload_block(vpmb200_engine* e, const double* particles, int64_t ld, int64_t n, int64_t dst0, uint32_t mask) {
+    if (n <= 0) return VPMB200_OK;
+    if (ld < NFIELDS) return fail(e, VPMB200_EINVAL, "ld < 43");
+    CU_TRY(e, cudaSetDevice(e->device));
+    // host (ld per particle) -> device AoS staging (NFIELDS per particle)
+    CU_TRY(e, cudaMemcpy2DAsync(e->aos, sizeof(double) * NFIELDS, particles, sizeof(double) * ld, sizeof(double) * NFIELDS,
+                                (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    dim3 grid(blocks_for(n, 32), (NFIELDS + 31) / 32), block(32, 8);
+    aos_to_soa_kernel<<<grid, block, 0, e->stream>>>(e->aos, NFIELDS, n, e->state, e->ld, dst0, mask);
+    CU_TRY(e, cudaGetLastError());
+    // the borrowed host pointer must not be read after return
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_upload(vpmb200_handle e, const double* particles, int64_t ld, int64_t np, uint32_t field_mask) {
+    CHECK_HANDLE(e);
+    if (np < 0) return fail(e, VPMB200_EINVAL, "np < 0");
+    if (np > e->maxp) return fail(e, VPMB200_ECAPACITY, "np exceeds max_particles");
+    if (np > 0 && !particles) return fail(e, VPMB200_EINVAL, "particles is NULL");
+    int32_t rc = upload_block(e, particles, ld, np, 0, field_mask);
+    if (rc) return rc;
+    e->np = np;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_download(vpmb200_handle e, double* particles, int64_t ld, int64_t np, uint32_t field_mask) {
+    CHECK_HANDLE(e);
+    if (np < 0 || np > e->np) return fail(e, VPMB200_EINVAL, "np out of range");
+    if (np == 0) return VPMB200_OK;
+    if (!particles) return fail(e, VPMB200_EINVAL, "particles is NULL");
+    if (ld < NFIELDS) return fail(e, VPMB200_EINVAL, "ld < 43");
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (field_mask != VPMB200_FM_ALL) {
+        // rows not selected must keep the host's values: stage the host block first
+        CU_TRY(e, cudaMemcpy2DAsync(e->aos, sizeof(double) * NFIELDS, particles, sizeof(double) * ld,
+                                    sizeof(double) * NFIELDS, (size_t)np, cudaMemcpyHostToDevice, e->stream));
+    }
+    dim3 grid(blocks_for(np, 32), (NFIELDS + 31) / 32), block(32, 8);
+    soa_to_aos_kernel<<<grid, block, 0, e->stream>>>(e->state, e->ld, np, e->aos, NFIELDS, field_mask);
+    CU_TRY(e, cudaGetLastError());
+    CU_TRY(e, cudaMemcpy2DAsync(particles, sizeof(double) * ld, e->aos, sizeof(double) * NFIELDS, sizeof(double) * NFIELDS,
+                                (size_t)np, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_add_particles(vpmb200_handle e, const double* cols, int64_t ld, int64_t n) {
+    CHECK_HANDLE(e);
+    if (n < 0) return fail(e, VPMB200_EINVAL, "n < 0");
+    if (e->np + n > e->maxp) return fail(e, VPMB200_ECAPACITY, "adding particles would exceed max_particles");
+    if (n > 0 && !cols) return fail(e, VPMB200_EINVAL, "cols is NULL");
+    int32_t rc = upload_block(e, cols, ld, n, e->np, VPMB200_FM_ALL);
+    if (rc) return rc;
+    e->np += n;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_remove_particle(vpmb200_handle e, int64_t i) {
+    CHECK_HANDLE(e);
+    if (i < 0 || i >= e->np) return fail(e, VPMB200_EINVAL, "particle index out of range");
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (i != e->np - 1) {
+        move_column_kernel<<<1, 64, 0, e->stream>>>(e->state, e->ld, i, e->np - 1);
+        CU_TRY(e, cudaGetLastError());
+    }
+    e->np -= 1;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_reset_particles(vpmb200_handle e) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    return do_reset(e);
+}
+
+int32_t vpmb200_reset_particles_sfs(vpmb200_handle e) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    return zero_rows(e, F_SFS, 3);
+}
+
+int32_t vpmb200_uj(vpmb200_handle e, int32_t reset, int32_t reset_sfs, int32_t sfs) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    return do_uj(e, reset, reset_sfs, sfs);
+}
+
+int32_t vpmb200_uj_probe(vpmb200_handle e, const double* X, int64_t m, double* U, double* J) {
+    CHECK_HANDLE(e);
+    if (m < 0) return fail(e, VPMB200_EINVAL, "m < 0");
+    if (m == 0) return VPMB200_OK;
+    if (!X || !U) return fail(e, VPMB200_EINVAL, "X or U is NULL");
+    if (e->sch.uj != VPMB200_UJ_DIRECT) return fail(e, VPMB200_ENOTSUP, "UJ_fmm is not built in this round");
+    CU_TRY(e, cudaSetDevice(e->device));
+    int32_t rc = ensure_probe(e, m);
+    if (rc) return rc;
+    const int64_t pl = e->probe_cap;
+    double* soaX = e->probe;
+    double* soaU = e->probe + 3 * pl;
+    double* soaJ = e->probe + 6 * pl;
+    double* stage = e->probe + 15 * pl;
+    CU_TRY(e, cudaMemcpyAsync(stage, X, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice, e->stream));
+    split_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(stage, 3, m, soaX, pl);
+    CU_TRY(e, cudaGetLastError());
+    if ((rc = pack_uj(e, e->rec))) return rc;
+    int ntiles = (int)(round_up(e->np, TILE_SRC) / TILE_SRC);
+    CU_TRY(e, dispatch_uj(e, e->rec, ntiles, soaX, soaX + pl, soaX + 2 * pl, m, soaU, soaJ, pl, 0));
+    join_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(soaU, pl, 3, m, stage);
+    CU_TRY(e, cudaGetLastError());
+    CU_TRY(e, cudaMemcpyAsync(U, stage, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, e->stream));
+    if (J) {
+        double* stageJ = stage + 3 * pl;
+        join_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(soaJ, pl, 9, m, stageJ);
+        CU_TRY(e, cudaGetLastError());
+        CU_TRY(e, cudaMemcpyAsync(J, stageJ, sizeof(double) * 9 * (size_t)m, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_sfs(vpmb200_handle e, double a, double b) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    return do_sfs(e, a, b);
+}
+
+int32_t vpmb200_nextstep(vpmb200_handle e, double dt, const double* Uinf, int32_t relax) {
+    CHECK_HANDLE(e);
+    if (!Uinf) return fail(e, VPMB200_EINVAL, "Uinf is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    int32_t rc;
+    if (e->np > 0) {
+        if (e->sch.integration == VPMB200_INTEGRATION_EULER) {
+            if ((rc = do_sfs(e, 1.0, 1.0))) return rc;
+            if ((rc = do_stage(e, VPMB200_STAGE_UPDATE, 0.0, 1.0, dt, Uinf, relax ? 1 : 0))) return rc;
+        } else {
+            static const double AB[3][2] = {{0.0, 1.0 / 3.0}, {-5.0 / 9.0, 15.0 / 16.0}, {-153.0 / 128.0, 8.0 / 15.0}};
+            if ((rc = do_stage(e, VPMB200_STAGE_ZERO_M, 0, 0, 0, nullptr, 0))) return rc;
+            for (int st = 0; st < 3; ++st) {
+                if ((rc = do_sfs(e, AB[st][0], AB[st][1]))) return rc;
+                if ((rc = do_stage(e, VPMB200_STAGE_UPDATE, AB[st][0], AB[st][1], dt, Uinf, 0))) return rc;
+            }
+            if (relax && e->sch.relaxation != VPMB200_RELAX_NONE) {
+                if ((rc = do_uj(e, 1, 0, 0))) return rc;
+                if ((rc = do_stage(e, VPMB200_STAGE_RELAX, 0, 0, 0, nullptr, 0))) return rc;
+            }
+        }
+    }
+    e->t += dt;
+    e->nt += 1;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_count_nonfinite(vpmb200_handle e, int64_t* count) {
+    CHECK_HANDLE(e);
+    if (!count) return fail(e, VPMB200_EINVAL, "count is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    if (e->np > 0) {
+        count_nonfinite_kernel<<<blocks_for(e->np, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, e->counter);
+        CU_TRY(e, cudaGetLastError());
+    }
+    unsigned long long c = 0;
+    CU_TRY(e, cudaMemcpyAsync(&c, e->counter, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    *count = (int64_t)c;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_device_field(vpmb200_handle e, int32_t field, double** ptr, int64_t* ld) {
+    CHECK_HANDLE(e);
+    if (field < 0 || field >= NFIELDS || !ptr) return fail(e, VPMB200_EINVAL, "bad field index");
+    *ptr = e->state + (size_t)field * e->ld;
+    if (ld) *ld = e->ld;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_stream(vpmb200_handle e, void** stream) {
+    CHECK_HANDLE(e);
+    if (!stream) return fail(e, VPMB200_EINVAL, "stream is NULL");
+    *stream = (void*)e->stream;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_synchronize(vpmb200_handle e) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    return VPMB200_OK;
+}
+
+int64_t vpmb200_record_doubles(int64_t nparticles) {
+    if (nparticles < 0) return 0;
+    return round_up(nparticles, TILE_SRC) * REC_REALS;
+}
+
+int32_t vpmb200_pack_uj_records(vpmb200_handle e, double* dst) {
+    CHECK_HANDLE(e);
+    if (!dst) return fail(e, VPMB200_EINVAL, "dst is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    return pack_uj(e, dst);
+}
+
+int32_t vpmb200_pack_estr_records(vpmb200_handle e, double* dst) {
+    CHECK_HANDLE(e);
+    if (!dst) return fail(e, VPMB200_EINVAL, "dst is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    return pack_estr(e, dst);
+}
+
+int32_t vpmb200_uj_from_records(vpmb200_handle e, const double* records, int64_t nsrc, int32_t accumulate) {
+    CHECK_HANDLE(e);
+    if (nsrc < 0 || (nsrc > 0 && !records)) return fail(e, VPMB200_EINVAL, "bad records");
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (e->np <= 0) return VPMB200_OK;
+    if (nsrc == 0) {
+        if (!accumulate) {
+            int32_t rc = zero_rows(e, F_U, 3);
+            if (rc) return rc;
+            return zero_rows(e, F_J, 9);
+        }
+        return VPMB200_OK;
+    }
+    return uj_local_from(e, records, nsrc, accumulate);
+}
+
+int32_t vpmb200_estr_from_records(vpmb200_handle e, const double* records, int64_t nsrc) {
+    CHECK_HANDLE(e);
+    if (nsrc < 0 || (nsrc > 0 && !records)) return fail(e, VPMB200_EINVAL, "bad records");
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (e->np <= 0 || nsrc == 0) return VPMB200_OK;
+    int ntiles = (int)(round_up(nsrc, TILE_SRC) / TILE_SRC);
+    CU_TRY(e, dispatch_estr(e, records, ntiles));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_stage(vpmb200_handle e, int32_t stage, double a, double b, double dt, const double* Uinf) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (stage == VPMB200_STAGE_UPDATE_EULER_RELAX) return do_stage(e, VPMB200_STAGE_UPDATE, a, b, dt, Uinf, 1);
+    return do_stage(e, stage, a, b, dt, Uinf, 0);
+}
+
+}  // extern "C"

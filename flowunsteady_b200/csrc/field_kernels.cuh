@@ -1,0 +1,411 @@
+// field_kernels.cuh — O(N) per-particle kernels of the hot path (all HBM-bound, coalesced SoA rows):
+//   K6  AoS (43 x np column-major, the reference's matrix) <-> SoA import/export, source-record packing
+//   K4  dynamic SFS coefficient (pseudo3level), clippings and controls          SURVEY.md A.5
+//   K5  euler / rungekutta3 substep with the rVPM closure, core spreading        SURVEY.md A.6, A.8
+//       and Pedrizzetti relaxation                                               SURVEY.md A.7
+// Equations: /root/reference/docs/src/theory/rvpm.md:107-235 (governing equations), :264-296 (C_d), :363-367.
+// Arithmetic is kept in the same operation order as oracle/vpm_oracle.c so the per-particle stages agree to
+// round-off (FMA contraction is disabled for this translation unit's update kernels via explicit intrinsics).
+#pragma once
+
+#include "../../include/vpmb200.h"
+#include "common.cuh"
+
+namespace vpm {
+
+constexpr int PK_BT = 256;
+
+// field-group table: first row and row count of each VPMB200_FM_* bit
+__constant__ int c_group_first[13] = {F_X, F_GAMMA, F_SIGMA, F_VOL, F_CIRC, F_U, F_W, F_J, F_PSE, F_M, F_C, F_SFS, F_STATIC};
+__constant__ int c_group_count[13] = {3, 3, 1, 1, 1, 3, 3, 9, 3, 9, 3, 3, 1};
+
+__device__ __forceinline__ bool row_selected(int row, uint32_t mask) {
+#pragma unroll
+    for (int g = 0; g < 13; ++g)
+        if ((mask >> g) & 1u)
+            if (row >= c_group_first[g] && row < c_group_first[g] + c_group_count[g]) return true;
+    return false;
+}
+
+// AoS -> SoA through a 32 x 33 shared tile so both sides are coalesced.  aos: particle-major, lda doubles per
+// particle; particles [p0, p0 + n) of the AoS block land at SoA columns [dst0, dst0 + n).
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, int64_t lda, int64_t n, double* __restrict__ soa,
+                                  int64_t ld, int64_t dst0, uint32_t mask) {
+    __shared__ double tile[32][33];
+    const int64_t pbase = (int64_t)blockIdx.x * 32;
+    const int fbase = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // r: particle within tile, threadIdx.x: field
+        int64_t p = pbase + r;
+        int f = fbase + threadIdx.x;
+        tile[r][threadIdx.x] = (p < n && f < NFIELDS) ? aos[p * lda + f] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // r: field within tile, threadIdx.x: particle
+        int f = fbase + r;
+        int64_t p = pbase + threadIdx.x;
+        if (p < n && f < NFIELDS && row_selected(f, mask)) soa[(size_t)f * ld + dst0 + p] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void soa_to_aos_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, double* __restrict__ aos,
+                                  int64_t lda, uint32_t mask) {
+    __shared__ double tile[32][33];
+    const int64_t pbase = (int64_t)blockIdx.x * 32;
+    const int fbase = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // r: field, threadIdx.x: particle
+        int f = fbase + r;
+        int64_t p = pbase + threadIdx.x;
+        tile[r][threadIdx.x] = (p < n && f < NFIELDS) ? soa[(size_t)f * ld + p] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // r: particle, threadIdx.x: field
+        int64_t p = pbase + r;
+        int f = fbase + threadIdx.x;
+        if (p < n && f < NFIELDS && row_selected(f, mask)) aos[p * lda + f] = tile[threadIdx.x][r];
+    }
+}
+
+// rows [first, first + count) of particles [0, n) <- 0
+__global__ void zero_rows_kernel(double* __restrict__ soa, int64_t ld, int64_t n, int first, int count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int f = first; f < first + count; ++f) soa[(size_t)f * ld + i] = 0.0;
+}
+
+// swap-remove: column `last` -> column `i`
+__global__ void move_column_kernel(double* __restrict__ soa, int64_t ld, int64_t dst, int64_t src) {
+    int f = threadIdx.x;
+    if (f < NFIELDS) soa[(size_t)f * ld + dst] = soa[(size_t)f * ld + src];
+}
+
+// UJ source records (common.cuh): i in [0, ntiles * TILE_SRC); i >= n writes a null record.
+__global__ void pack_uj_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, int64_t ntot,
+                                       double* __restrict__ rec) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntot) return;
+    double2* r = reinterpret_cast<double2*>(rec + (size_t)i * REC_REALS);
+    if (i < n) {
+        double x = soa[(size_t)(F_X + 0) * ld + i], y = soa[(size_t)(F_X + 1) * ld + i], z = soa[(size_t)(F_X + 2) * ld + i];
+        double gx = soa[(size_t)(F_GAMMA + 0) * ld + i], gy = soa[(size_t)(F_GAMMA + 1) * ld + i],
+               gz = soa[(size_t)(F_GAMMA + 2) * ld + i];
+        double sg = soa[(size_t)F_SIGMA * ld + i];
+        double si = 1.0 / sg, si2 = si * si, si3 = si2 * si;
+        r[0] = make_double2(x, y);
+        r[1] = make_double2(z, si2);
+        r[2] = make_double2(-CONST4 * gx, -CONST4 * gy);
+        r[3] = make_double2(-CONST4 * gz, si3);
+        r[4] = make_double2(si3 * si2, sg);
+    } else {
+        r[0] = make_double2(0.0, 0.0);
+        r[1] = make_double2(0.0, 1.0);
+        r[2] = make_double2(0.0, 0.0);
+        r[3] = make_double2(0.0, 0.0);
+        r[4] = make_double2(0.0, 1.0);
+    }
+}
+
+// E_str source records: c = zeta_norm / sigma^3, v = J^T Gamma (transposed) or J Gamma.
+__global__ void pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, int64_t ntot,
+                                         int transposed, double zeta_norm, double* __restrict__ rec) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntot) return;
+    double2* r = reinterpret_cast<double2*>(rec + (size_t)i * REC_REALS);
+    if (i < n) {
+        double x = soa[(size_t)(F_X + 0) * ld + i], y = soa[(size_t)(F_X + 1) * ld + i], z = soa[(size_t)(F_X + 2) * ld + i];
+        double g0 = soa[(size_t)(F_GAMMA + 0) * ld + i], g1 = soa[(size_t)(F_GAMMA + 1) * ld + i],
+               g2 = soa[(size_t)(F_GAMMA + 2) * ld + i];
+        double sg = soa[(size_t)F_SIGMA * ld + i];
+        double Jq[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) Jq[c] = soa[(size_t)(F_J + c) * ld + i];
+        double v0, v1, v2;
+        if (transposed) {
+            v0 = Jq[0] * g0 + Jq[1] * g1 + Jq[2] * g2;
+            v1 = Jq[3] * g0 + Jq[4] * g1 + Jq[5] * g2;
+            v2 = Jq[6] * g0 + Jq[7] * g1 + Jq[8] * g2;
+        } else {
+            v0 = Jq[0] * g0 + Jq[3] * g1 + Jq[6] * g2;
+            v1 = Jq[1] * g0 + Jq[4] * g1 + Jq[7] * g2;
+            v2 = Jq[2] * g0 + Jq[5] * g1 + Jq[8] * g2;
+        }
+        double si = 1.0 / sg, si2 = si * si;
+        double c = zeta_norm * (si2 * si);
+        r[0] = make_double2(x, y);
+        r[1] = make_double2(z, si2);
+        r[2] = make_double2(c * g0, c * g1);
+        r[3] = make_double2(c * g2, c * v0);
+        r[4] = make_double2(c * v1, c * v2);
+    } else {
+        r[0] = make_double2(0.0, 0.0);
+        r[1] = make_double2(0.0, 1.0);
+        r[2] = make_double2(0.0, 0.0);
+        r[3] = make_double2(0.0, 0.0);
+        r[4] = make_double2(0.0, 0.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-particle stages.  `P(f)` addresses row f of this thread's particle.
+// ------------------------------------------------------------------------------------------------------------
+#define VPM_P(f) soa[(size_t)(f) * ld + i]
+
+__device__ __forceinline__ void stretching(const double* __restrict__ soa, int64_t ld, int64_t i, int transposed,
+                                           double G0, double G1, double G2, double S[3]) {
+    double J[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) J[c] = VPM_P(F_J + c);
+    if (transposed) {
+        S[0] = __dadd_rn(__dadd_rn(__dmul_rn(J[0], G0), __dmul_rn(J[1], G1)), __dmul_rn(J[2], G2));
+        S[1] = __dadd_rn(__dadd_rn(__dmul_rn(J[3], G0), __dmul_rn(J[4], G1)), __dmul_rn(J[5], G2));
+        S[2] = __dadd_rn(__dadd_rn(__dmul_rn(J[6], G0), __dmul_rn(J[7], G1)), __dmul_rn(J[8], G2));
+    } else {
+        S[0] = __dadd_rn(__dadd_rn(__dmul_rn(J[0], G0), __dmul_rn(J[3], G1)), __dmul_rn(J[6], G2));
+        S[1] = __dadd_rn(__dadd_rn(__dmul_rn(J[1], G0), __dmul_rn(J[4], G1)), __dmul_rn(J[7], G2));
+        S[2] = __dadd_rn(__dadd_rn(__dmul_rn(J[2], G0), __dmul_rn(J[5], G1)), __dmul_rn(J[8], G2));
+    }
+}
+
+__device__ __forceinline__ double dot3(double a0, double a1, double a2, double b0, double b1, double b2) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+
+__device__ __forceinline__ double sgn(double x) { return (double)((x > 0) - (x < 0)); }
+
+// sigma *= factor for the non-static particles (dynamic procedure test/domain filter switch)
+__global__ void scale_sigma_kernel(double* __restrict__ soa, int64_t ld, int64_t n, double factor, int divide) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+    VPM_P(F_SIGMA) = divide ? VPM_P(F_SIGMA) / factor : VPM_P(F_SIGMA) * factor;
+}
+
+// test-filter results: M[:,1] = S, M[:,2] = SFS, rest of M = 0
+__global__ void dyn_store_test_kernel(double* __restrict__ soa, int64_t ld, int64_t n, int transposed) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+    double S[3];
+    stretching(soa, ld, i, transposed, VPM_P(F_GAMMA), VPM_P(F_GAMMA + 1), VPM_P(F_GAMMA + 2), S);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        VPM_P(F_M + k) = S[k];
+        VPM_P(F_M + 3 + k) = VPM_P(F_SFS + k);
+        VPM_P(F_M + 6 + k) = 0.0;
+    }
+}
+
+// domain-filter results, C_d with Lagrangian averaging and clamps, flush M   
+__global__ void dyn_coeff_kernel(double* __restrict__ soa, int64_t ld, int64_t n, int transposed, double alpha,
+                                 double rlxf, double minC, double maxC, int force_positive, double zeta0) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+    double G0 = VPM_P(F_GAMMA), G1 = VPM_P(F_GAMMA + 1), G2 = VPM_P(F_GAMMA + 2);
+    double S[3];
+    stretching(soa, ld, i, transposed, G0, G1, G2, S);
+    double M1[3], M2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        M1[k] = __dsub_rn(VPM_P(F_M + k), S[k]);
+        M2[k] = __dsub_rn(VPM_P(F_M + 3 + k), VPM_P(F_SFS + k));
+    }
+    double sg = VPM_P(F_SIGMA);
+    double nume = dot3(M1[0], M1[1], M1[2], G0, G1, G2);
+    nume = __dmul_rn(nume, __dsub_rn(__dmul_rn(3.0, alpha), 2.0));
+    double deno = dot3(M2[0], M2[1], M2[2], G0, G1, G2);
+    deno = deno / (zeta0 / __dmul_rn(__dmul_rn(sg, sg), sg));
+    double C1 = VPM_P(F_C + 1), C2 = VPM_P(F_C + 2);
+    if (C2 == 0) {
+        C2 = deno;
+        if (C2 == 0) C2 = 2.220446049250313e-16;
+    }
+    nume = __dadd_rn(__dmul_rn(rlxf, nume), __dmul_rn(__dsub_rn(1.0, rlxf), C1));
+    deno = __dadd_rn(__dmul_rn(rlxf, deno), __dmul_rn(__dsub_rn(1.0, rlxf), C2));
+    if (fabs(nume / deno) > maxC) {
+        if (fabs(deno) < fabs(C2)) deno = sgn(deno) * fabs(C2);
+        nume = sgn(nume) * fabs(deno) * maxC;
+    } else if (fabs(nume / deno) < minC) {
+        nume = sgn(nume) * fabs(deno) * minC;
+    }
+    double C0 = nume / deno;
+    if (force_positive) C0 = fabs(C0);
+    VPM_P(F_C) = C0;
+    VPM_P(F_C + 1) = nume;
+    VPM_P(F_C + 2) = deno;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) VPM_P(F_M + k) = 0.0;
+}
+
+__global__ void const_coeff_kernel(double* __restrict__ soa, int64_t ld, int64_t n, double Cs) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+    VPM_P(F_C) = Cs;
+}
+
+// clipping_backscatter, control_directional, control_magnitude — applied in that order per particle; each only
+// touches its own particle, so the reference's three sweeps fuse into one.
+__global__ void clip_control_kernel(double* __restrict__ soa, int64_t ld, int64_t n, int clippings, int controls,
+                                    double f, double zeta0, double t, int64_t nt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+    double G0 = VPM_P(F_GAMMA), G1 = VPM_P(F_GAMMA + 1), G2 = VPM_P(F_GAMMA + 2);
+    double E0 = VPM_P(F_SFS), E1 = VPM_P(F_SFS + 1), E2 = VPM_P(F_SFS + 2);
+    double C = VPM_P(F_C);
+    if (clippings & VPMB200_CLIP_BACKSCATTER) {
+        if (__dmul_rn(C, dot3(G0, G1, G2, E0, E1, E2)) < 0) {
+            C *= 0;
+            VPM_P(F_C) = C;
+        }
+    }
+    if (controls & VPMB200_CTRL_DIRECTIONAL) {
+        double aux = dot3(E0, E1, E2, G0, G1, G2);
+        aux = aux / dot3(G0, G1, G2, G0, G1, G2);
+        E0 = __dadd_rn(E0, __dadd_rn(-E0, __dmul_rn(aux, G0)));
+        E1 = __dadd_rn(E1, __dadd_rn(-E1, __dmul_rn(aux, G1)));
+        E2 = __dadd_rn(E2, __dadd_rn(-E2, __dmul_rn(aux, G2)));
+    }
+    if ((controls & VPMB200_CTRL_MAGNITUDE) && nt != 0 && C != 0) {
+        double deltat = t / (double)nt;
+        double sg = VPM_P(F_SIGMA);
+        double aux = dot3(E0, E1, E2, G0, G1, G2);
+        aux = aux / dot3(G0, G1, G2, G0, G1, G2);
+        aux = __dsub_rn(aux, __dmul_rn(__dadd_rn(1.0, __dmul_rn(3.0, f)), (zeta0 / __dmul_rn(__dmul_rn(sg, sg), sg))) / deltat / C);
+        if (aux > 0) {
+            E0 = __dadd_rn(E0, __dmul_rn(-aux, G0));
+            E1 = __dadd_rn(E1, __dmul_rn(-aux, G1));
+            E2 = __dadd_rn(E2, __dmul_rn(-aux, G2));
+        }
+    }
+    if (controls) {
+        VPM_P(F_SFS) = E0;
+        VPM_P(F_SFS + 1) = E1;
+        VPM_P(F_SFS + 2) = E2;
+    }
+}
+
+struct UpdateParams {
+    double a, b, dt;
+    double Uinf0, Uinf1, Uinf2;
+    double f, g, zeta0, nu, rlxf;
+    int transposed, viscous, relaxation;
+    int euler;        // 1: Euler step — no q-storage, relaxation (if relax_inline) before core spreading
+    int relax_inline;
+};
+
+__device__ __forceinline__ void relax_gamma(const double* __restrict__ soa, int64_t ld, int64_t i, int relaxation,
+                                            double rlxf, double& G0, double& G1, double& G2) {
+    // omega = curl u from J; J[i,j] at i + 3 j
+    double w1 = __dsub_rn(VPM_P(F_J + 2 + 3 * 1), VPM_P(F_J + 1 + 3 * 2));
+    double w2 = __dsub_rn(VPM_P(F_J + 0 + 3 * 2), VPM_P(F_J + 2 + 3 * 0));
+    double w3 = __dsub_rn(VPM_P(F_J + 1 + 3 * 0), VPM_P(F_J + 0 + 3 * 1));
+    double nrmw = sqrt(dot3(w1, w2, w3, w1, w2, w3));
+    double nrmG = sqrt(dot3(G0, G1, G2, G0, G1, G2));
+    double omr = __dsub_rn(1.0, rlxf);
+    double b2 = 1.0;
+    if (relaxation == VPMB200_RELAX_CORRECTEDPEDRIZZETTI)
+        b2 = __dsub_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(2.0, omr), rlxf),
+                                      __dsub_rn(1.0, dot3(G0, G1, G2, w1, w2, w3) / __dmul_rn(nrmG, nrmw))));
+    G0 = __dadd_rn(__dmul_rn(omr, G0), __dmul_rn(__dmul_rn(rlxf, nrmG), w1) / nrmw);
+    G1 = __dadd_rn(__dmul_rn(omr, G1), __dmul_rn(__dmul_rn(rlxf, nrmG), w2) / nrmw);
+    G2 = __dadd_rn(__dmul_rn(omr, G2), __dmul_rn(__dmul_rn(rlxf, nrmG), w3) / nrmw);
+    if (relaxation == VPMB200_RELAX_CORRECTEDPEDRIZZETTI) {
+        double sb = sqrt(b2);
+        G0 /= sb;
+        G1 /= sb;
+        G2 /= sb;
+    }
+}
+
+// One low-storage substep + core spreading (A.8) for every non-static particle.
+__global__ void update_kernel(double* __restrict__ soa, int64_t ld, int64_t n, UpdateParams p) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+    const double a = p.a, b = p.b, dt = p.dt;
+    const double Uinf[3] = {p.Uinf0, p.Uinf1, p.Uinf2};
+    double G[3] = {VPM_P(F_GAMMA), VPM_P(F_GAMMA + 1), VPM_P(F_GAMMA + 2)};
+    double E[3] = {VPM_P(F_SFS), VPM_P(F_SFS + 1), VPM_P(F_SFS + 2)};
+    const double C = VPM_P(F_C);
+    // position
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double q = p.euler ? 0.0 : VPM_P(F_M + k);
+        q = __dadd_rn(__dmul_rn(a, q), __dmul_rn(dt, __dadd_rn(VPM_P(F_U + k), Uinf[k])));
+        if (!p.euler) VPM_P(F_M + k) = q;
+        VPM_P(F_X + k) = __dadd_rn(VPM_P(F_X + k), __dmul_rn(b, q));
+    }
+    double S[3];
+    stretching(soa, ld, i, p.transposed, G[0], G[1], G[2], S);
+    double sg = VPM_P(F_SIGMA);
+    double sg3z = __dmul_rn(__dmul_rn(sg, sg), sg) / p.zeta0;
+    double Z = __dmul_rn(__dadd_rn(p.f, p.g) / __dadd_rn(1.0, __dmul_rn(3.0, p.f)), dot3(S[0], S[1], S[2], G[0], G[1], G[2]));
+    double CE = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(C, E[0]), G[0]), __dmul_rn(__dmul_rn(C, E[1]), G[1])),
+                          __dmul_rn(__dmul_rn(C, E[2]), G[2]));
+    Z = __dsub_rn(Z, __dmul_rn(__dmul_rn(p.f / __dadd_rn(1.0, __dmul_rn(3.0, p.f)), CE), sg3z));
+    Z = Z / dot3(G[0], G[1], G[2], G[0], G[1], G[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double q = p.euler ? 0.0 : VPM_P(F_M + 3 + k);
+        double rhs = __dsub_rn(__dsub_rn(S[k], __dmul_rn(__dmul_rn(3.0, Z), G[k])), __dmul_rn(__dmul_rn(C, E[k]), sg3z));
+        q = __dadd_rn(__dmul_rn(a, q), __dmul_rn(dt, rhs));
+        if (!p.euler) VPM_P(F_M + 3 + k) = q;
+        G[k] = __dadd_rn(G[k], __dmul_rn(b, q));
+    }
+    {
+        double q = p.euler ? 0.0 : VPM_P(F_M + 7);
+        q = __dsub_rn(__dmul_rn(a, q), __dmul_rn(dt, __dmul_rn(sg, Z)));
+        if (!p.euler) VPM_P(F_M + 7) = q;
+        sg = __dadd_rn(sg, __dmul_rn(b, q));
+    }
+    if (p.euler && p.relax_inline && p.relaxation != VPMB200_RELAX_NONE)
+        relax_gamma(soa, ld, i, p.relaxation, p.rlxf, G[0], G[1], G[2]);
+    if (p.viscous == VPMB200_VISCOUS_CORESPREADING) {
+        if (p.euler) {
+            sg = sqrt(__dadd_rn(__dmul_rn(sg, sg), __dmul_rn(__dmul_rn(2.0, p.nu), dt)));
+        } else {
+            double q = __dadd_rn(__dmul_rn(a, VPM_P(F_M + 6)), __dmul_rn(__dmul_rn(dt, 2.0), p.nu));
+            VPM_P(F_M + 6) = q;
+            sg = sqrt(__dadd_rn(__dmul_rn(sg, sg), __dmul_rn(b, q)));
+        }
+    }
+    VPM_P(F_GAMMA) = G[0];
+    VPM_P(F_GAMMA + 1) = G[1];
+    VPM_P(F_GAMMA + 2) = G[2];
+    VPM_P(F_SIGMA) = sg;
+}
+
+__global__ void relax_kernel(double* __restrict__ soa, int64_t ld, int64_t n, int relaxation, double rlxf) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+    double G0 = VPM_P(F_GAMMA), G1 = VPM_P(F_GAMMA + 1), G2 = VPM_P(F_GAMMA + 2);
+    relax_gamma(soa, ld, i, relaxation, rlxf, G0, G1, G2);
+    VPM_P(F_GAMMA) = G0;
+    VPM_P(F_GAMMA + 1) = G1;
+    VPM_P(F_GAMMA + 2) = G2;
+}
+
+// rungekutta3 resets its q-storage M for the non-static particles before the first substep
+__global__ void zero_m_kernel(double* __restrict__ soa, int64_t ld, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (VPM_P(F_STATIC) > 0) return;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) VPM_P(F_M + k) = 0.0;
+}
+
+// number of non-finite entries among X, Gamma, sigma
+__global__ void count_nonfinite_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, unsigned long long* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int bad = 0;
+    if (i < n)
+        for (int f = 0; f < 7; ++f) bad += !isfinite(VPM_P(f));
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);
+}
+
+#undef VPM_P
+
+}  // namespace vpm

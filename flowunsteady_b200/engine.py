@@ -1,0 +1,225 @@
+"""Thin object wrapper over the C ABI (include/vpmb200.h).  One Engine = one GPU-resident particle field.
+
+Host arrays use the reference's particle matrix: `particles[i, :]` is particle i's 43-field column, i.e. a
+C-contiguous (np, 43) numpy array is byte-identical to FLOWVPM's 43 x np column-major `pfield.particles`
+(/root/reference/src/FLOWUnsteady_simulation.jl:509-510).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import NFIELDS, EngineError, Schemes
+
+# 0-based field offsets (include/vpmb200.h)
+X, GAMMA, SIGMA, VOL, CIRCULATION, U, VORTICITY, J, PSE, M, CC, SFS, STATIC = 0, 3, 6, 7, 8, 9, 12, 15, 24, 27, 36, 39, 42
+
+FM_X, FM_GAMMA, FM_SIGMA, FM_VOL, FM_CIRCULATION, FM_U, FM_VORTICITY, FM_J, FM_PSE, FM_M, FM_C, FM_SFS, FM_STATIC = (
+    1 << k for k in range(13))
+FM_ALL = 0x1FFF
+FM_STATE = FM_X | FM_GAMMA | FM_SIGMA | FM_VOL | FM_CIRCULATION | FM_C | FM_STATIC
+
+KERNEL_IDS = {"gaussianerf": 0, "winckelmans": 1, "gaussian": 2, "singular": 3}
+RELAX_IDS = {"none": 0, "pedrizzetti": 1, "correctedpedrizzetti": 2}
+SFS_IDS = {"none": 0, "constant": 1, "dynamic": 2}
+VISCOUS_IDS = {"inviscid": 0, "corespreading": 1}
+INTEGRATION_IDS = {"euler": 0, "rungekutta3": 1}
+UJ_IDS = {"direct": 0, "fmm": 1}
+CLIP_BACKSCATTER = 1
+CTRL_DIRECTIONAL, CTRL_MAGNITUDE = 1, 2
+
+STAGE_SCALE_SIGMA_TEST, STAGE_STORE_TEST, STAGE_SCALE_SIGMA_DOMAIN, STAGE_DYNAMIC_COEFF = 1, 2, 3, 4
+STAGE_CONSTANT_COEFF, STAGE_CLIP_CONTROL, STAGE_ZERO_M, STAGE_UPDATE, STAGE_RELAX, STAGE_UPDATE_EULER_RELAX = 5, 6, 7, 8, 9, 10
+
+_ENUMS = {"kernel": KERNEL_IDS, "relaxation": RELAX_IDS, "sfs": SFS_IDS, "viscous": VISCOUS_IDS,
+          "integration": INTEGRATION_IDS, "uj": UJ_IDS}
+
+
+def default_schemes(**kw) -> Schemes:
+    s = Schemes()
+    _lib.lib().vpmb200_default_schemes(C.byref(s))
+    for k, v in kw.items():
+        if isinstance(v, str):
+            v = _ENUMS[k][v]
+        if not hasattr(s, k):
+            raise AttributeError(f"vpmb200_schemes has no member {k!r}")
+        setattr(s, k, v)
+    return s
+
+
+def _as_matrix(a: np.ndarray) -> np.ndarray:
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 2 and a.shape[1] >= NFIELDS
+            and a.strides[1] == 8 and a.strides[0] >= 8 * NFIELDS and a.strides[0] % 8 == 0):
+        raise ValueError("particles must be a float64 (np, >=43) array with contiguous rows")
+    return a
+
+
+class Engine:
+    """RAII wrapper of a vpmb200_handle."""
+
+    def __init__(self, max_particles: int, float_bits: int = 64, device: int = 0, schemes: Schemes | None = None):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        rc = self._L.vpmb200_create(int(max_particles), NFIELDS, int(float_bits), int(device), C.byref(self._h))
+        if rc != 0:
+            msg = self._L.vpmb200_last_error(None).decode()
+            self._h = None
+            raise EngineError(rc, msg)
+        self.max_particles = int(max_particles)
+        self.float_bits = int(float_bits)
+        self.device = int(device)
+        if schemes is not None:
+            self.set_schemes(schemes)
+
+    # ---- lifetime -------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vpmb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, self._L.vpmb200_last_error(self._h).decode())
+
+    # ---- schemes / time -------------------------------------------------------------------------------
+    def set_schemes(self, s: Schemes):
+        self._check(self._L.vpmb200_set_schemes(self._h, C.byref(s)))
+
+    def get_schemes(self) -> Schemes:
+        s = Schemes()
+        self._check(self._L.vpmb200_get_schemes(self._h, C.byref(s)))
+        return s
+
+    def set_time(self, t: float, nt: int):
+        self._check(self._L.vpmb200_set_time(self._h, float(t), int(nt)))
+
+    def get_time(self):
+        t, nt = C.c_double(), C.c_int64()
+        self._check(self._L.vpmb200_get_time(self._h, C.byref(t), C.byref(nt)))
+        return t.value, nt.value
+
+    # ---- data movement --------------------------------------------------------------------------------
+    @property
+    def np(self) -> int:
+        n = C.c_int64()
+        self._check(self._L.vpmb200_get_np(self._h, C.byref(n)))
+        return n.value
+
+    def upload(self, particles: np.ndarray, np_: int | None = None, field_mask: int = FM_ALL):
+        P = _as_matrix(particles)
+        n = P.shape[0] if np_ is None else int(np_)
+        self._check(self._L.vpmb200_upload(self._h, P.ctypes.data, P.strides[0] // 8, n, field_mask))
+
+    def download(self, particles: np.ndarray, np_: int | None = None, field_mask: int = FM_ALL):
+        P = _as_matrix(particles)
+        n = self.np if np_ is None else int(np_)
+        if n > P.shape[0]:
+            raise ValueError("host matrix is too small")
+        self._check(self._L.vpmb200_download(self._h, P.ctypes.data, P.strides[0] // 8, n, field_mask))
+        return P
+
+    def add_particles(self, cols: np.ndarray):
+        P = _as_matrix(np.atleast_2d(cols))
+        self._check(self._L.vpmb200_add_particles(self._h, P.ctypes.data, P.strides[0] // 8, P.shape[0]))
+
+    def remove_particle(self, i: int):
+        self._check(self._L.vpmb200_remove_particle(self._h, int(i)))
+
+    # ---- hot path -------------------------------------------------------------------------------------
+    def reset_particles(self):
+        self._check(self._L.vpmb200_reset_particles(self._h))
+
+    def reset_particles_sfs(self):
+        self._check(self._L.vpmb200_reset_particles_sfs(self._h))
+
+    def uj(self, reset: bool = True, reset_sfs: bool = False, sfs: bool = False):
+        self._check(self._L.vpmb200_uj(self._h, int(reset), int(reset_sfs), int(sfs)))
+
+    def uj_probe(self, Xp: np.ndarray, want_J: bool = False):
+        Xp = np.ascontiguousarray(Xp, dtype=np.float64).reshape(-1, 3)
+        m = Xp.shape[0]
+        Uo = np.zeros((m, 3))
+        Jo = np.zeros((m, 9)) if want_J else None
+        self._check(self._L.vpmb200_uj_probe(self._h, Xp.ctypes.data, m, Uo.ctypes.data,
+                                             Jo.ctypes.data if want_J else None))
+        return (Uo, Jo) if want_J else Uo
+
+    def sfs(self, a: float = 1.0, b: float = 1.0):
+        self._check(self._L.vpmb200_sfs(self._h, float(a), float(b)))
+
+    def nextstep(self, dt: float, Uinf=(0.0, 0.0, 0.0), relax: bool = True):
+        u = (C.c_double * 3)(*[float(v) for v in Uinf])
+        self._check(self._L.vpmb200_nextstep(self._h, float(dt), u, int(relax)))
+
+    def stage(self, stage: int, a: float = 0.0, b: float = 0.0, dt: float = 0.0, Uinf=None):
+        u = (C.c_double * 3)(*[float(v) for v in Uinf]) if Uinf is not None else None
+        self._check(self._L.vpmb200_stage(self._h, int(stage), float(a), float(b), float(dt), u))
+
+    def count_nonfinite(self) -> int:
+        c = C.c_int64()
+        self._check(self._L.vpmb200_count_nonfinite(self._h, C.byref(c)))
+        return c.value
+
+    # ---- device-level hooks ---------------------------------------------------------------------------
+    def device_field(self, field: int):
+        p, ld = C.c_void_p(), C.c_int64()
+        self._check(self._L.vpmb200_device_field(self._h, int(field), C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+    @property
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._check(self._L.vpmb200_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def synchronize(self):
+        self._check(self._L.vpmb200_synchronize(self._h))
+
+    @staticmethod
+    def record_doubles(n: int) -> int:
+        return _lib.lib().vpmb200_record_doubles(int(n))
+
+    def pack_uj_records(self, dst_ptr: int):
+        self._check(self._L.vpmb200_pack_uj_records(self._h, C.c_void_p(dst_ptr)))
+
+    def pack_estr_records(self, dst_ptr: int):
+        self._check(self._L.vpmb200_pack_estr_records(self._h, C.c_void_p(dst_ptr)))
+
+    def uj_from_records(self, rec_ptr: int, nsrc: int, accumulate: bool):
+        self._check(self._L.vpmb200_uj_from_records(self._h, C.c_void_p(rec_ptr), int(nsrc), int(accumulate)))
+
+    def estr_from_records(self, rec_ptr: int, nsrc: int):
+        self._check(self._L.vpmb200_estr_from_records(self._h, C.c_void_p(rec_ptr), int(nsrc)))
+
+
+def new_particles(x, gamma, sigma, static=None, vol=None, circulation=None, C_=None) -> np.ndarray:
+    """(n, 43) particle matrix with X, Gamma, sigma (and optional vol, circulation, C, static) filled in."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 3)
+    n = x.shape[0]
+    P = np.zeros((n, NFIELDS))
+    P[:, X:X + 3] = x
+    P[:, GAMMA:GAMMA + 3] = gamma
+    P[:, SIGMA] = sigma
+    if vol is not None:
+        P[:, VOL] = vol
+    if circulation is not None:
+        P[:, CIRCULATION] = circulation
+    if C_ is not None:
+        P[:, CC:CC + 3] = C_
+    if static is not None:
+        P[:, STATIC] = np.asarray(static, dtype=np.float64)
+    return P

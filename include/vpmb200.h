@@ -1,0 +1,219 @@
+/*
+ * vpmb200.h — C ABI of the B200-native rVPM particle-field engine (libvpmb200.so).
+ *
+ * This is the drop-in boundary for the hot path FLOWUnsteady drives every time step through the FLOWVPM
+ * `ParticleField` plugin API.  Citations are into /root/reference (FLOWUnsteady v3.4.0):
+ *
+ *   reference call site                                              replaced by
+ *   ---------------------------------------------------------------  ------------------------------------
+ *   vpm.ParticleField(max, T; formulation, viscous, kernel, UJ, SFS,  vpmb200_create + vpmb200_set_schemes
+ *       integration, transposed, relaxation, fmm)                     (src/FLOWUnsteady_simulation.jl:239-253)
+ *   pfield.UJ(pfield)               (simulation.jl:544,               vpmb200_uj
+ *                                    processing_force.jl:238)
+ *   vpm._reset_particles(pfield)    (processing_force.jl:237)         vpmb200_reset_particles
+ *   pfield.SFS(pfield; a, b)        (inside vpm.nextstep)             vpmb200_sfs
+ *   vpm.nextstep(pfield, dt; relax) (simulation.jl:358)               vpmb200_nextstep
+ *   probes appended + pfield.UJ     (simulation.jl:494-570)           vpmb200_uj_probe
+ *   pfield.particles[:, 1:np]       (simulation.jl:509-510)           vpmb200_upload / vpmb200_download
+ *   vpm.add_particle / remove_particle (simulation.jl:363,486,551)    vpmb200_add_particles / vpmb200_remove_particle
+ *
+ * Conventions
+ *   - All functions return 0 on success, a negative VPMB200_E* code otherwise; no exceptions cross the ABI.
+ *     vpmb200_last_error(h) returns a human-readable message for the last failure on that handle.
+ *   - Host pointers are borrowed for the duration of the call only.  The engine owns all device memory.
+ *   - The particle matrix is the reference's: column-major, `nfields` (= 43) doubles per particle, one column per
+ *     particle, leading dimension `ld` >= nfields (field offsets below).
+ *   - A handle is bound to one CUDA device and one stream; calls on a handle are serialised by the caller.
+ *   - There is NO CPU fallback: create fails with VPMB200_ENODEVICE when no sm_100 GPU is present.
+ */
+#ifndef VPMB200_H
+#define VPMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPMB200_NFIELDS 43
+/* 0-based row offsets in a particle column */
+#define VPMB200_X 0
+#define VPMB200_GAMMA 3
+#define VPMB200_SIGMA 6
+#define VPMB200_VOL 7
+#define VPMB200_CIRCULATION 8
+#define VPMB200_U 9
+#define VPMB200_VORTICITY 12
+#define VPMB200_J 15 /* J[i,j] = du_i/dx_j at 15 + i + 3 j */
+#define VPMB200_PSE 24
+#define VPMB200_M 27
+#define VPMB200_C 36
+#define VPMB200_SFS 39
+#define VPMB200_STATIC 42
+
+/* field-group bit masks for vpmb200_upload / vpmb200_download */
+#define VPMB200_FM_X (1u << 0)
+#define VPMB200_FM_GAMMA (1u << 1)
+#define VPMB200_FM_SIGMA (1u << 2)
+#define VPMB200_FM_VOL (1u << 3)
+#define VPMB200_FM_CIRCULATION (1u << 4)
+#define VPMB200_FM_U (1u << 5)
+#define VPMB200_FM_VORTICITY (1u << 6)
+#define VPMB200_FM_J (1u << 7)
+#define VPMB200_FM_PSE (1u << 8)
+#define VPMB200_FM_M (1u << 9)
+#define VPMB200_FM_C (1u << 10)
+#define VPMB200_FM_SFS (1u << 11)
+#define VPMB200_FM_STATIC (1u << 12)
+#define VPMB200_FM_ALL 0x1fffu
+/* what the host owns between calls (everything the integrator reads) */
+#define VPMB200_FM_STATE (VPMB200_FM_X | VPMB200_FM_GAMMA | VPMB200_FM_SIGMA | VPMB200_FM_VOL | \
+                          VPMB200_FM_CIRCULATION | VPMB200_FM_C | VPMB200_FM_STATIC)
+
+/* error codes */
+#define VPMB200_OK 0
+#define VPMB200_EINVAL (-1)
+#define VPMB200_ENODEVICE (-2)
+#define VPMB200_ECUDA (-3)
+#define VPMB200_ECAPACITY (-4) /* more particles than max_particles (reference: simulation.jl:255-261) */
+#define VPMB200_ENOTSUP (-5)
+
+/* scheme ids — the reference's scheme objects (src/FLOWUnsteady_simulation.jl:36-44) */
+enum { VPMB200_KERNEL_GAUSSIANERF = 0, VPMB200_KERNEL_WINCKELMANS = 1, VPMB200_KERNEL_GAUSSIAN = 2,
+       VPMB200_KERNEL_SINGULAR = 3 };
+enum { VPMB200_RELAX_NONE = 0, VPMB200_RELAX_PEDRIZZETTI = 1, VPMB200_RELAX_CORRECTEDPEDRIZZETTI = 2 };
+enum { VPMB200_SFS_NONE = 0, VPMB200_SFS_CONSTANT = 1, VPMB200_SFS_DYNAMIC = 2 };
+enum { VPMB200_CLIP_BACKSCATTER = 1 };
+enum { VPMB200_CTRL_DIRECTIONAL = 1, VPMB200_CTRL_MAGNITUDE = 2 };
+enum { VPMB200_VISCOUS_INVISCID = 0, VPMB200_VISCOUS_CORESPREADING = 1 };
+enum { VPMB200_INTEGRATION_EULER = 0, VPMB200_INTEGRATION_RK3 = 1 };
+enum { VPMB200_UJ_DIRECT = 0, VPMB200_UJ_FMM = 1 };
+
+/* Mirrors the scheme fields of vpm.ParticleField (simulation.jl:239-244).  Same layout as oracle's vpmo_schemes
+ * for the first 18 members so tests can drive both from one description. */
+typedef struct {
+    int32_t kernel;         /* vpm_kernel: gaussianerf | winckelmans | gaussian | singular                */
+    double f, g;            /* vpm_formulation: rVPM (0, 1/5) | cVPM (0, 0)                                */
+    int32_t transposed;     /* vpm_transposed                                                              */
+    int32_t relaxation;     /* vpm_relaxation                                                              */
+    double rlxf;            /*   relaxation factor (0.3)                                                   */
+    int32_t sfs;            /* vpm_SFS: none | constant | dynamic                                          */
+    double alpha;           /*   DynamicSFS alpha (test-filter ratio)                                      */
+    double sfs_rlxf;        /*   DynamicSFS rlxf (Lagrangian average)                                      */
+    double minC, maxC;      /*   DynamicSFS clamps                                                         */
+    double Cs;              /*   ConstantSFS coefficient                                                   */
+    int32_t force_positive; /*   pseudo3level_positive                                                     */
+    int32_t clippings;      /*   VPMB200_CLIP_* mask                                                       */
+    int32_t controls;       /*   VPMB200_CTRL_* mask                                                       */
+    int32_t viscous;        /* vpm_viscous: Inviscid | CoreSpreading (sigma update; RBF re-fit not included) */
+    double nu;              /*   kinematic viscosity                                                       */
+    int32_t integration;    /* vpm_integration: euler | rungekutta3                                        */
+    /* --- beyond the oracle's struct --- */
+    int32_t uj;             /* vpm_UJ: direct | fmm                                                        */
+    int32_t fmm_p;          /* vpm_fmm = vpm.FMM(; p=4, ncrit=50, theta=0.4, nonzero_sigma) simulation.jl:43 */
+    int32_t fmm_ncrit;
+    double fmm_theta;
+    int32_t fmm_nonzero_sigma;
+} vpmb200_schemes;
+
+typedef struct vpmb200_engine* vpmb200_handle;
+
+/* FLOWUnsteady's defaults (simulation.jl:36-44, except uj = direct). */
+int32_t vpmb200_default_schemes(vpmb200_schemes* s);
+
+/* max_particles: capacity (reference: max_particles, simulation.jl:124,239).  nfields must be 43.
+ * float_bits: 64 (FP64 pair arithmetic) or 32 (FP32 pair arithmetic, FP64 state; reference knob vpm_floattype,
+ * simulation.jl:137).  device: CUDA ordinal. */
+int32_t vpmb200_create(int64_t max_particles, int32_t nfields, int32_t float_bits, int32_t device,
+                       vpmb200_handle* out);
+int32_t vpmb200_destroy(vpmb200_handle h);
+const char* vpmb200_last_error(vpmb200_handle h);
+
+int32_t vpmb200_set_schemes(vpmb200_handle h, const vpmb200_schemes* s);
+int32_t vpmb200_get_schemes(vpmb200_handle h, vpmb200_schemes* s);
+
+/* Field time and step counter (pfield.t, pfield.nt). */
+int32_t vpmb200_set_time(vpmb200_handle h, double t, int64_t nt);
+int32_t vpmb200_get_time(vpmb200_handle h, double* t, int64_t* nt);
+
+/* Replace the device field by columns 0..np-1 of `particles` (only the groups in field_mask are copied; others
+ * keep their device values).  np becomes the particle count. */
+int32_t vpmb200_upload(vpmb200_handle h, const double* particles, int64_t ld, int64_t np, uint32_t field_mask);
+/* Copy the groups in field_mask of particles 0..np-1 back into `particles`. */
+int32_t vpmb200_download(vpmb200_handle h, double* particles, int64_t ld, int64_t np, uint32_t field_mask);
+int32_t vpmb200_get_np(vpmb200_handle h, int64_t* np);
+
+/* vpm.add_particle: append n columns.  vpm.remove_particle(pfield, i): 0-based i; the last particle is swapped
+ * into slot i (the reference's behaviour). */
+int32_t vpmb200_add_particles(vpmb200_handle h, const double* cols, int64_t ld, int64_t n);
+int32_t vpmb200_remove_particle(vpmb200_handle h, int64_t i);
+
+/* vpm._reset_particles: U, J, PSE <- 0.   _reset_particles_sfs: SFS <- 0. */
+int32_t vpmb200_reset_particles(vpmb200_handle h);
+int32_t vpmb200_reset_particles_sfs(vpmb200_handle h);
+
+/* pfield.UJ(pfield; reset, reset_sfs, sfs): U and J at every particle from every particle; with sfs != 0 also
+ * accumulates the SFS term E_str.  NOTE the reference call `pfield.UJ(pfield)` is reset=1, reset_sfs=0, sfs=0. */
+int32_t vpmb200_uj(vpmb200_handle h, int32_t reset, int32_t reset_sfs, int32_t sfs);
+
+/* Velocity (and optionally J) induced by the field at m probe points X (3 x m column-major).  Equivalent to the
+ * reference's add_probe + pfield.UJ + get_U sequence (simulation.jl:536-547) without evaluating the other
+ * targets.  U: 3 x m.  J: 9 x m or NULL. */
+int32_t vpmb200_uj_probe(vpmb200_handle h, const double* X, int64_t m, double* U, double* J);
+
+/* pfield.SFS(pfield; a, b): evaluates U, J (+ SFS, C_d) as the SFS scheme prescribes for RK coefficients (a, b). */
+int32_t vpmb200_sfs(vpmb200_handle h, double a, double b);
+
+/* vpm.nextstep(pfield, dt; relax): one euler / rungekutta3 step (UJ + SFS + update + relaxation + core
+ * spreading); Uinf is the freestream pfield.Uinf(t) evaluated by the host (3 doubles). */
+int32_t vpmb200_nextstep(vpmb200_handle h, double dt, const double* Uinf, int32_t relax);
+
+/* Monitors: np, number of non-finite X/Gamma/sigma entries, enstrophy 0.5 sum Gamma.omega is left to the host. */
+int32_t vpmb200_count_nonfinite(vpmb200_handle h, int64_t* count);
+
+/* ---- device-level hooks (multi-GPU sharding, benchmarking; pointers are CUDA device pointers) ------------- */
+
+/* Pointer to SoA field row `field` (0..42) of the device state: element i of that row is particle i. */
+int32_t vpmb200_device_field(vpmb200_handle h, int32_t field, double** ptr, int64_t* ld);
+/* The CUDA stream (cudaStream_t) every call on this handle is enqueued on. */
+int32_t vpmb200_stream(vpmb200_handle h, void** stream);
+/* Block the host until all enqueued work on the handle has finished. */
+int32_t vpmb200_synchronize(vpmb200_handle h);
+
+/* Pack the 10-double UJ source records of local particles [0, np) into dst (device, >= vpmb200_record_capacity
+ * doubles).  Records are what the pair kernels stream; ranks all-gather them (NCCL) to shard the direct path. */
+int64_t vpmb200_record_doubles(int64_t nparticles); /* doubles needed for n particles incl. tile padding */
+int32_t vpmb200_pack_uj_records(vpmb200_handle h, double* dst);
+int32_t vpmb200_pack_estr_records(vpmb200_handle h, double* dst);
+/* U, J (or SFS) of the LOCAL particles from `nsrc` external source records (device pointer, padded to whole
+ * tiles as vpmb200_record_doubles prescribes); accumulate != 0 adds to the current values. */
+int32_t vpmb200_uj_from_records(vpmb200_handle h, const double* records, int64_t nsrc, int32_t accumulate);
+int32_t vpmb200_estr_from_records(vpmb200_handle h, const double* records, int64_t nsrc);
+/* The per-particle stages of pfield.SFS / nextstep, exposed so a sharded driver can interleave its exchange:
+ * stage ids in vpmb200_stage. */
+enum {
+    VPMB200_STAGE_SCALE_SIGMA_TEST = 1,   /* sigma *= alpha (non-static)                 */
+    VPMB200_STAGE_STORE_TEST = 2,         /* M[:,1] = S, M[:,2] = SFS                    */
+    VPMB200_STAGE_SCALE_SIGMA_DOMAIN = 3, /* sigma /= alpha                              */
+    VPMB200_STAGE_DYNAMIC_COEFF = 4,      /* M -= ..., C_d, clamp, flush M               */
+    VPMB200_STAGE_CONSTANT_COEFF = 5,     /* C[1] = Cs                                   */
+    VPMB200_STAGE_CLIP_CONTROL = 6,       /* clippings + controls                        */
+    VPMB200_STAGE_ZERO_M = 7,             /* rungekutta3 q-storage reset                 */
+    VPMB200_STAGE_UPDATE = 8,             /* one (a, b) substep incl. core spreading     */
+    VPMB200_STAGE_RELAX = 9,              /* relaxation(p)                               */
+    VPMB200_STAGE_UPDATE_EULER_RELAX = 10 /* euler update with relaxation(p) applied inline */
+};
+int32_t vpmb200_stage(vpmb200_handle h, int32_t stage, double a, double b, double dt, const double* Uinf);
+
+/* Measurement helper: FP64 FMA peak of `device` in TFLOP/s (best of `repeats` launches of a register-only DFMA
+ * kernel, `iters` x 128 FMAs per thread).  bench.py uses it as the roofline denominator of the FP64-bound pair
+ * kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int32_t vpmb200_measure_fp64_peak(int32_t device, int32_t iters, int32_t repeats, double* tflops, double* ms);
+
+/* Library identification. */
+const char* vpmb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,139 @@
+"""GPU parity of K1 (UJ_direct) against the CPU oracle and the mpmath golden vectors, through the C ABI.
+
+Tolerance: 1e-12 relative in the max norm (BASELINE.json north_star) for FP64; 2e-5 for the FP32 variant.
+"""
+import numpy as np
+import pytest
+
+from tests.util import mixed_field, relmax
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 2e-5
+KERNELS = ["gaussianerf", "winckelmans", "gaussian", "singular"]
+
+
+def _engine(n, kernel, bits=64):
+    import flowunsteady_b200 as fb
+    return fb.Engine(max(n, 1), float_bits=bits, schemes=fb.default_schemes(kernel=kernel))
+
+
+def _run_uj(P, kernel, bits=64):
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import engine as E
+    n = P.shape[0]
+    with _engine(n, kernel, bits) as eng:
+        eng.upload(P)
+        eng.uj()
+        out = np.zeros_like(P)
+        eng.download(out)
+    return out[:, E.U:E.U + 3], out[:, E.J:E.J + 9], out
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_mpmath(golden, kernel):
+    """U and J at the particles and at off-particle probes vs 50-digit mpmath (tests/golden/uj_mp.npz)."""
+    import flowunsteady_b200 as fb
+    x, g, s, probes = golden["x"], golden["gamma"], golden["sigma"], golden["probes"]
+    n = x.shape[0]
+    P = fb.new_particles(x, g, s)
+    U, J, _ = _run_uj(P, kernel)
+    Ug, Jg = golden[f"U_{kernel}"], golden[f"J_{kernel}"]
+    # the `gaussian` kernel's reference form cancels catastrophically for the 1e-7-separated pair; it gets 1e-9
+    tol = 1e-9 if kernel == "gaussian" else TOL64
+    assert relmax(U, Ug[:n]) < tol
+    assert relmax(J, Jg[:n]) < tol
+    with _engine(n, kernel) as eng:
+        eng.upload(P)
+        Up, Jp = eng.uj_probe(probes, want_J=True)
+    assert relmax(Up, Ug[n:]) < tol
+    assert relmax(Jp, Jg[n:]) < tol
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1000, 5000])
+def test_uj_vs_oracle(kernel, n):
+    """Ragged sizes around the tile/CTA width, statics and zero-strength particles included."""
+    import flowunsteady_b200 as fb
+    from oracle import oracle as o
+    x, g, s, static = mixed_field(n, seed=n)
+    P = fb.new_particles(x, g, s, static=static)
+    U, J, _ = _run_uj(P, kernel)
+    Uo, Jo = o.uj_direct(kernel, x, g, s, x, accum=1)
+    assert relmax(U, Uo) < TOL64
+    assert relmax(J, Jo) < TOL64
+
+
+def test_uj_large_sampled():
+    """N = 200k vortex rings: 2048 sampled targets against the long-double oracle over all sources."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    from oracle import oracle as o
+    x, g, s = fields.vortex_rings(200_000)
+    P = fb.new_particles(x, g, s)
+    U, J, _ = _run_uj(P, "gaussianerf")
+    idx = np.random.default_rng(1234).choice(x.shape[0], 2048, replace=False)
+    Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x[idx], accum=1)
+    assert relmax(U[idx], Uo) < TOL64
+    assert relmax(J[idx], Jo) < TOL64
+    # divergence-free velocity: tr J = 0 to round-off at every particle (size-independent property)
+    tr = J[:, 0] + J[:, 4] + J[:, 8]
+    assert np.abs(tr).max() < 1e-11 * np.abs(J).max()
+
+
+def test_uj_accumulate_and_reset_flags():
+    """reset=False accumulates on top of the current U, J (pfield.UJ(pfield; reset=false))."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import engine as E
+    x, g, s, static = mixed_field(700, seed=3)
+    P = fb.new_particles(x, g, s, static=static)
+    with _engine(700, "gaussianerf") as eng:
+        eng.upload(P)
+        eng.uj()
+        a = eng.download(np.zeros_like(P)).copy()
+        eng.uj(reset=False)
+        b = eng.download(np.zeros_like(P)).copy()
+        eng.reset_particles()
+        c = eng.download(np.zeros_like(P)).copy()
+    assert relmax(b[:, E.U:E.U + 3], 2 * a[:, E.U:E.U + 3]) < 1e-15
+    assert relmax(b[:, E.J:E.J + 9], 2 * a[:, E.J:E.J + 9]) < 1e-15
+    assert np.all(c[:, E.U:E.U + 3] == 0) and np.all(c[:, E.J:E.J + 9] == 0)
+    # state rows are untouched by UJ
+    assert np.array_equal(a[:, :9], P[:, :9])
+
+
+def test_uj_linearity_full_size_property():
+    """Linearity in Gamma: UJ(2 Gamma) == 2 UJ(Gamma) bit-for-bit (scaling by 2 is exact in binary FP)."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    x, g, s = fields.random_field(20_000)
+    U1, J1, _ = _run_uj(fb.new_particles(x, g, s), "gaussianerf")
+    U2, J2, _ = _run_uj(fb.new_particles(x, 2 * g, s), "gaussianerf")
+    assert np.array_equal(U2, 2 * U1)
+    assert np.array_equal(J2, 2 * J1)
+
+
+@pytest.mark.parametrize("kernel", ["gaussianerf", "winckelmans", "singular"])
+def test_uj_fp32_variant(kernel):
+    import flowunsteady_b200 as fb
+    from oracle import oracle as o
+    x, g, s, static = mixed_field(3000, seed=11)
+    P = fb.new_particles(x, g, s, static=static)
+    U, J, _ = _run_uj(P, kernel, bits=32)
+    Uo, Jo = o.uj_direct(kernel, x, g, s, x, accum=1)
+    assert relmax(U, Uo) < TOL32
+    assert relmax(J, Jo) < 20 * TOL32   # J ~ 1/r^3-weighted: FP32 position differences cost more digits
+
+
+def test_empty_field_and_errors():
+    import flowunsteady_b200 as fb
+    with fb.Engine(16) as eng:
+        eng.uj()                         # np == 0 is a no-op (vpm.nextstep guards np > 0 the same way)
+        eng.nextstep(0.1)
+        assert eng.np == 0 and eng.get_time() == (0.1, 1)
+        with pytest.raises(fb.EngineError) as ei:
+            eng.upload(np.zeros((17, 43)))
+        assert ei.value.code == -4       # VPMB200_ECAPACITY
+        with pytest.raises(fb.EngineError):
+            eng.set_schemes(fb.default_schemes(kernel=7))
