@@ -23,13 +23,20 @@ constexpr double CONST4 = 0.07957747154594767;
 constexpr double CONST1 = 0.06349363593424097;
 
 // ---- source records streamed through shared memory by the pairwise kernels ------------------------
-// 10 reals per source (80 B in FP64, 40 B in FP32), 16-byte aligned so they move as LDS.128 broadcasts.
-//   UJ pass  : { x, y, z, 1/sigma^2 | G'x, G'y, G'z, 1/sigma^3 | 1/sigma^5, sigma }, G' = -Gamma/(4 pi)
-//   E_str    : { x, y, z, 1/sigma^2 | cGx, cGy, cGz, c vx     | c vy, c vz },  c = zeta(0)/sigma^3 (kernel
+// 10 doubles (80 B) per source, 16-byte aligned so they move as LDS.128 broadcasts:
+//   UJ pass  : { x, y | z, G'x | G'y, G'z | T_FAR sigma^2, 1/sigma^3 | 1/sigma^5, 1/sigma^2 },  G' = -Gamma/(4 pi)
+//              (the far-field branch reads only the first three quads)
+//   E_str    : { x, y | z, 1/sigma^2 | cGx, cGy | cGz, c vx | c vy, c vz },  c = zeta(0)/sigma^3 (kernel
 //              normalisation folded in), v = J^T Gamma (transposed scheme) or J Gamma (classic)
+// A tile is TILE_SRC records followed by one 10-double header { xmin, xmax, ymin, ymax, zmin, zmax,
+// max(T_FAR sigma^2), n_real, 0, 0 } (bounding box of the tile's real sources), so a tile moves with ONE bulk copy
+// and tiles from different ranks concatenate (the multi-GPU direct path all-gathers whole tiles).
+// Tail slots of the last tile repeat the position of the tile's first real source with zero strength: they
+// contribute exactly 0 on every branch and never sit closer to a target than a real source does.
 constexpr int REC_REALS = 10;
-
-constexpr int TILE_SRC = 256;   // sources per shared-memory tile (20 KB in FP64)
+constexpr int TILE_SRC = 256;                              // sources per shared-memory tile
+constexpr int TILE_DOUBLES = (TILE_SRC + 1) * REC_REALS;   // 2570 doubles = 20,560 B per tile incl. header
+constexpr int TILE_HDR = TILE_SRC * REC_REALS;             // offset of the header inside a tile
 
 // ---- PTX helpers: mbarrier + 1-D bulk TMA copy (cp.async.bulk, SASS UBLKCP) -----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

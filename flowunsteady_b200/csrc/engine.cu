@@ -143,26 +143,24 @@ int32_t do_reset(vpmb200_engine* e) {
 }
 
 int32_t pack_uj(vpmb200_engine* e, double* dst) {
-    int64_t ntot = round_up(e->np, TILE_SRC);
-    if (ntot == 0) return VPMB200_OK;
-    pack_uj_records_kernel<<<blocks_for(ntot, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, ntot, dst);
+    if (e->np <= 0) return VPMB200_OK;
+    pack_uj_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(e->state, e->ld, e->np, dst);
     CU_TRY(e, cudaGetLastError());
     return VPMB200_OK;
 }
 
 int32_t pack_estr(vpmb200_engine* e, double* dst) {
-    int64_t ntot = round_up(e->np, TILE_SRC);
-    if (ntot == 0) return VPMB200_OK;
-    pack_estr_records_kernel<<<blocks_for(ntot, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, ntot,
-                                                                             e->sch.transposed, zeta0_of(e->sch.kernel), dst);
+    if (e->np <= 0) return VPMB200_OK;
+    pack_estr_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(
+        e->state, e->ld, e->np, e->sch.transposed, zeta0_of(e->sch.kernel), e->sch.kernel == K_GAUSSIANERF ? 1 : 0, dst);
     CU_TRY(e, cudaGetLastError());
     return VPMB200_OK;
 }
 
-int32_t uj_local_from(vpmb200_engine* e, const double* rec, int64_t nsrc, int accumulate) {
+int32_t uj_local_from(vpmb200_engine* e, const double* rec, int64_t ntiles_, int accumulate) {
     double* S = e->state;
     const int64_t ld = e->ld;
-    int ntiles = (int)(round_up(nsrc, TILE_SRC) / TILE_SRC);
+    int ntiles = (int)ntiles_;
     CU_TRY(e, dispatch_uj(e, rec, ntiles, S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld, S + (size_t)(F_X + 2) * ld,
                           e->np, S + (size_t)F_U * ld, S + (size_t)F_J * ld, ld, accumulate));
     return VPMB200_OK;
@@ -176,11 +174,10 @@ int32_t do_uj(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     if (reset_sfs && (rc = zero_rows(e, F_SFS, 3))) return rc;
     if (e->np <= 0) return VPMB200_OK;
     if ((rc = pack_uj(e, e->rec))) return rc;
-    if ((rc = uj_local_from(e, e->rec, e->np, reset ? 0 : 1))) return rc;
+    if ((rc = uj_local_from(e, e->rec, vpmb200_tiles_for(e->np), reset ? 0 : 1))) return rc;
     if (sfs) {
         if ((rc = pack_estr(e, e->rec))) return rc;
-        int ntiles = (int)(round_up(e->np, TILE_SRC) / TILE_SRC);
-        CU_TRY(e, dispatch_estr(e, e->rec, ntiles));
+        CU_TRY(e, dispatch_estr(e, e->rec, (int)vpmb200_tiles_for(e->np)));
     }
     return VPMB200_OK;
 }
@@ -373,7 +370,7 @@ int32_t vpmb200_create(int64_t max_particles, int32_t nfields, int32_t float_bit
     CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaMalloc(&e->state, sizeof(double) * (size_t)NFIELDS * e->ld));
     CREATE_TRY(cudaMemsetAsync(e->state, 0, sizeof(double) * (size_t)NFIELDS * e->ld, e->stream));
-    CREATE_TRY(cudaMalloc(&e->rec, sizeof(double) * (size_t)vpmb200_record_doubles(e->maxp)));
+    CREATE_TRY(cudaMalloc(&e->rec, sizeof(double) * (size_t)(vpmb200_tiles_for(e->maxp) * TILE_DOUBLES)));
     CREATE_TRY(cudaMalloc(&e->aos, sizeof(double) * (size_t)NFIELDS * e->maxp));
     CREATE_TRY(cudaMalloc(&e->gh_table, sizeof(vpm_gt_GH)));
     CREATE_TRY(cudaMalloc(&e->z_table, sizeof(vpm_gt_Z)));
@@ -550,7 +547,7 @@ int32_t vpmb200_uj_probe(vpmb200_handle e, const double* X, int64_t m, double* U
     split_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(stage, 3, m, soaX, pl);
     CU_TRY(e, cudaGetLastError());
     if ((rc = pack_uj(e, e->rec))) return rc;
-    int ntiles = (int)(round_up(e->np, TILE_SRC) / TILE_SRC);
+    int ntiles = (int)vpmb200_tiles_for(e->np);
     CU_TRY(e, dispatch_uj(e, e->rec, ntiles, soaX, soaX + pl, soaX + 2 * pl, m, soaU, soaJ, pl, 0));
     join_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(soaU, pl, 3, m, stage);
     CU_TRY(e, cudaGetLastError());
@@ -636,10 +633,9 @@ int32_t vpmb200_synchronize(vpmb200_handle e) {
     return VPMB200_OK;
 }
 
-int64_t vpmb200_record_doubles(int64_t nparticles) {
-    if (nparticles < 0) return 0;
-    return round_up(nparticles, TILE_SRC) * REC_REALS;
-}
+int64_t vpmb200_tiles_for(int64_t nparticles) { return nparticles <= 0 ? 0 : round_up(nparticles, TILE_SRC) / TILE_SRC; }
+
+int64_t vpmb200_tile_doubles(void) { return TILE_DOUBLES; }
 
 int32_t vpmb200_pack_uj_records(vpmb200_handle e, double* dst) {
     CHECK_HANDLE(e);
@@ -655,29 +651,20 @@ int32_t vpmb200_pack_estr_records(vpmb200_handle e, double* dst) {
     return pack_estr(e, dst);
 }
 
-int32_t vpmb200_uj_from_records(vpmb200_handle e, const double* records, int64_t nsrc, int32_t accumulate) {
+int32_t vpmb200_uj_from_records(vpmb200_handle e, const double* tiles, int64_t ntiles, int32_t accumulate) {
     CHECK_HANDLE(e);
-    if (nsrc < 0 || (nsrc > 0 && !records)) return fail(e, VPMB200_EINVAL, "bad records");
+    if (ntiles < 0 || (ntiles > 0 && !tiles)) return fail(e, VPMB200_EINVAL, "bad tiles");
     CU_TRY(e, cudaSetDevice(e->device));
     if (e->np <= 0) return VPMB200_OK;
-    if (nsrc == 0) {
-        if (!accumulate) {
-            int32_t rc = zero_rows(e, F_U, 3);
-            if (rc) return rc;
-            return zero_rows(e, F_J, 9);
-        }
-        return VPMB200_OK;
-    }
-    return uj_local_from(e, records, nsrc, accumulate);
+    return uj_local_from(e, tiles, ntiles, accumulate);  // ntiles == 0 writes zeros unless accumulating
 }
 
-int32_t vpmb200_estr_from_records(vpmb200_handle e, const double* records, int64_t nsrc) {
+int32_t vpmb200_estr_from_records(vpmb200_handle e, const double* tiles, int64_t ntiles) {
     CHECK_HANDLE(e);
-    if (nsrc < 0 || (nsrc > 0 && !records)) return fail(e, VPMB200_EINVAL, "bad records");
+    if (ntiles < 0 || (ntiles > 0 && !tiles)) return fail(e, VPMB200_EINVAL, "bad tiles");
     CU_TRY(e, cudaSetDevice(e->device));
-    if (e->np <= 0 || nsrc == 0) return VPMB200_OK;
-    int ntiles = (int)(round_up(nsrc, TILE_SRC) / TILE_SRC);
-    CU_TRY(e, dispatch_estr(e, records, ntiles));
+    if (e->np <= 0 || ntiles == 0) return VPMB200_OK;
+    CU_TRY(e, dispatch_estr(e, tiles, (int)ntiles));
     return VPMB200_OK;
 }
 

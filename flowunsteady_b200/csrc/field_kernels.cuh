@@ -10,6 +10,7 @@
 
 #include "../../include/vpmb200.h"
 #include "common.cuh"
+#include "gauss_table.inc"
 
 namespace vpm {
 
@@ -78,40 +79,84 @@ __global__ void move_column_kernel(double* __restrict__ soa, int64_t ld, int64_t
     if (f < NFIELDS) soa[(size_t)f * ld + dst] = soa[(size_t)f * ld + src];
 }
 
-// UJ source records (common.cuh): i in [0, ntiles * TILE_SRC); i >= n writes a null record.
-__global__ void pack_uj_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, int64_t ntot,
-                                       double* __restrict__ rec) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntot) return;
-    double2* r = reinterpret_cast<double2*>(rec + (size_t)i * REC_REALS);
-    if (i < n) {
-        double x = soa[(size_t)(F_X + 0) * ld + i], y = soa[(size_t)(F_X + 1) * ld + i], z = soa[(size_t)(F_X + 2) * ld + i];
+// Block-wide bounding box + max(T_FAR sigma^2) of a tile's real sources -> 10-double tile header (common.cuh).
+// One CTA of TILE_SRC threads per tile.
+__device__ __forceinline__ void write_tile_header(double* __restrict__ hdr, bool real, double x, double y, double z,
+                                                  double rfar2, int nreal) {
+    __shared__ double red[7][TILE_SRC / 32];
+    const double big = 1.0e300;
+    double v[7] = {real ? x : big, real ? -x : big, real ? y : big, real ? -y : big, real ? z : big, real ? -z : big,
+                   real ? -rfar2 : big};
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[c] = fmin(v[c], __shfl_xor_sync(0xffffffffu, v[c], o));
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 7; ++c) red[c][threadIdx.x >> 5] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        double out = 0.0;
+        if (threadIdx.x < 7) {
+            double m = red[threadIdx.x][0];
+            for (int k = 1; k < TILE_SRC / 32; ++k) m = fmin(m, red[threadIdx.x][k]);
+            out = (threadIdx.x & 1) || threadIdx.x == 6 ? -m : m;  // slots 1,3,5 are maxima, 6 is max rfar2
+            if (threadIdx.x == 6 && nreal == 0) out = 0.0;
+        } else if (threadIdx.x == 7) {
+            out = (double)nreal;
+        }
+        hdr[threadIdx.x] = out;
+    }
+}
+
+// UJ source tiles (common.cuh).  Grid: ntiles CTAs of TILE_SRC threads; slot i >= n repeats the tile's first real
+// source position with zero strength.
+__global__ void __launch_bounds__(TILE_SRC)
+pack_uj_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, double* __restrict__ rec) {
+    const int64_t t0 = (int64_t)blockIdx.x * TILE_SRC;
+    const int64_t i = t0 + threadIdx.x;
+    const bool real = i < n;
+    const int64_t isrc = real ? i : t0;  // t0 < n always (the grid is ceil(n / TILE_SRC))
+    double* tile = rec + (size_t)blockIdx.x * TILE_DOUBLES;
+    double2* r = reinterpret_cast<double2*>(tile + (size_t)threadIdx.x * REC_REALS);
+    double x = soa[(size_t)(F_X + 0) * ld + isrc], y = soa[(size_t)(F_X + 1) * ld + isrc], z = soa[(size_t)(F_X + 2) * ld + isrc];
+    double rfar2 = 0.0;
+    if (real) {
         double gx = soa[(size_t)(F_GAMMA + 0) * ld + i], gy = soa[(size_t)(F_GAMMA + 1) * ld + i],
                gz = soa[(size_t)(F_GAMMA + 2) * ld + i];
         double sg = soa[(size_t)F_SIGMA * ld + i];
         double si = 1.0 / sg, si2 = si * si, si3 = si2 * si;
+        rfar2 = VPM_GT_TFAR * (sg * sg);
         r[0] = make_double2(x, y);
-        r[1] = make_double2(z, si2);
-        r[2] = make_double2(-CONST4 * gx, -CONST4 * gy);
-        r[3] = make_double2(-CONST4 * gz, si3);
-        r[4] = make_double2(si3 * si2, sg);
+        r[1] = make_double2(z, -CONST4 * gx);
+        r[2] = make_double2(-CONST4 * gy, -CONST4 * gz);
+        r[3] = make_double2(rfar2, si3);
+        r[4] = make_double2(si3 * si2, si2);
     } else {
-        r[0] = make_double2(0.0, 0.0);
-        r[1] = make_double2(0.0, 1.0);
+        r[0] = make_double2(x, y);
+        r[1] = make_double2(z, 0.0);
         r[2] = make_double2(0.0, 0.0);
-        r[3] = make_double2(0.0, 0.0);
+        r[3] = make_double2(VPM_GT_TFAR, 0.0);
         r[4] = make_double2(0.0, 1.0);
     }
+    int64_t nreal = n - t0;
+    write_tile_header(tile + TILE_HDR, real, x, y, z, rfar2, (int)(nreal > TILE_SRC ? TILE_SRC : nreal));
 }
 
-// E_str source records: c = zeta_norm / sigma^3, v = J^T Gamma (transposed) or J Gamma.
-__global__ void pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, int64_t ntot,
-                                         int transposed, double zeta_norm, double* __restrict__ rec) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntot) return;
-    double2* r = reinterpret_cast<double2*>(rec + (size_t)i * REC_REALS);
-    if (i < n) {
-        double x = soa[(size_t)(F_X + 0) * ld + i], y = soa[(size_t)(F_X + 1) * ld + i], z = soa[(size_t)(F_X + 2) * ld + i];
+// E_str source tiles: c = zeta_norm / sigma^3, v = J^T Gamma (transposed) or J Gamma.  `cutoff` != 0 stores
+// max(T_FAR sigma^2) in the header (kernels whose zeta vanishes beyond T_FAR); otherwise +inf-like (never skipped).
+__global__ void __launch_bounds__(TILE_SRC)
+pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, int transposed, double zeta_norm,
+                         int cutoff, double* __restrict__ rec) {
+    const int64_t t0 = (int64_t)blockIdx.x * TILE_SRC;
+    const int64_t i = t0 + threadIdx.x;
+    const bool real = i < n;
+    const int64_t isrc = real ? i : t0;
+    double* tile = rec + (size_t)blockIdx.x * TILE_DOUBLES;
+    double2* r = reinterpret_cast<double2*>(tile + (size_t)threadIdx.x * REC_REALS);
+    double x = soa[(size_t)(F_X + 0) * ld + isrc], y = soa[(size_t)(F_X + 1) * ld + isrc], z = soa[(size_t)(F_X + 2) * ld + isrc];
+    double rfar2 = 0.0;
+    if (real) {
         double g0 = soa[(size_t)(F_GAMMA + 0) * ld + i], g1 = soa[(size_t)(F_GAMMA + 1) * ld + i],
                g2 = soa[(size_t)(F_GAMMA + 2) * ld + i];
         double sg = soa[(size_t)F_SIGMA * ld + i];
@@ -130,18 +175,21 @@ __global__ void pack_estr_records_kernel(const double* __restrict__ soa, int64_t
         }
         double si = 1.0 / sg, si2 = si * si;
         double c = zeta_norm * (si2 * si);
+        rfar2 = cutoff ? VPM_GT_TFAR * (sg * sg) : 1.0e300;
         r[0] = make_double2(x, y);
         r[1] = make_double2(z, si2);
         r[2] = make_double2(c * g0, c * g1);
         r[3] = make_double2(c * g2, c * v0);
         r[4] = make_double2(c * v1, c * v2);
     } else {
-        r[0] = make_double2(0.0, 0.0);
-        r[1] = make_double2(0.0, 1.0);
+        r[0] = make_double2(x, y);
+        r[1] = make_double2(z, 1.0);
         r[2] = make_double2(0.0, 0.0);
         r[3] = make_double2(0.0, 0.0);
         r[4] = make_double2(0.0, 0.0);
     }
+    int64_t nreal = n - t0;
+    write_tile_header(tile + TILE_HDR, real, x, y, z, rfar2, (int)(nreal > TILE_SRC ? TILE_SRC : nreal));
 }
 
 // ------------------------------------------------------------------------------------------------------------

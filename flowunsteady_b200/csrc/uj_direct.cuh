@@ -65,6 +65,9 @@ __device__ __forceinline__ void uj_accumulate(UJAcc& a, double dx, double dy, do
     a.w2 = fma(A, gz, a.w2);
 }
 
+// x != 0 for a non-negative double, on the integer pipe (keeps DSETP off the FP64 pipe)
+__device__ __forceinline__ bool nonzero_f64(double x) { return (__double2hiint(x) | __double2loint(x)) != 0; }
+
 // Far field / singular kernel: A = 1/r^3, B = -3/r^5.  Requires r2 > 0.
 __device__ __forceinline__ void ab_singular(double r2, double& A, double& B) {
     double ri = rsqrt_f64(r2);
@@ -103,16 +106,19 @@ __device__ __forceinline__ void ab_winckelmans(double t, double sinv3, double si
     B = (fma(-3.0, t, -10.5) * w7) * sinv5;
 }
 
-// exp(x) for x <= 0 in FP64 (|rel err| < 2e-16): Cody-Waite reduction + degree-11 Taylor/Horner.
-__device__ __forceinline__ double exp_neg_f64(double x) {
-    if (x < -708.0) return 0.0;
+// exp(x) and 1 - exp(x) for x <= 0 in FP64 (|rel err| < 3e-16 each): Cody-Waite reduction + degree-12 Horner.
+// 1 - exp(x) is formed from the polynomial without its leading 1 when no scaling is needed, so it keeps full
+// relative accuracy as x -> 0 (the reference's `1 - exp(-r^3)` cancels there; we are more accurate, not less).
+__device__ __forceinline__ void exp_neg_f64(double x, double& e, double& one_minus_e) {
+    if (x < -708.0) { e = 0.0; one_minus_e = 1.0; return; }
     const double L2E = 1.4426950408889634, LN2H = 6.93147180369123816490e-01, LN2L = 1.90821492927058770002e-10;
     double m = fma(x, L2E, MAGIC_RINT);
     int k = __double2loint(m);
     double kf = m - MAGIC_RINT;
     double r = fma(kf, -LN2H, x);
     r = fma(kf, -LN2L, r);
-    double p = 2.50521083854417187751e-08;                 // 1/11!
+    double p = 2.08767569878680989792e-09;                 // 1/12!
+    p = fma(p, r, 2.50521083854417187751e-08);             // 1/11!
     p = fma(p, r, 2.75573192239858906526e-07);             // 1/10!
     p = fma(p, r, 2.75573192239858906526e-06);             // 1/9!
     p = fma(p, r, 2.48015873015873015873e-05);             // 1/8!
@@ -123,75 +129,163 @@ __device__ __forceinline__ double exp_neg_f64(double x) {
     p = fma(p, r, 1.66666666666666666667e-01);             // 1/3!
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    // scale by 2^k through the exponent field (k in [-1022, 0])
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    double q = p * r;                                      // exp(r) - 1
+    if (k == 0) {
+        e = 1.0 + q;
+        one_minus_e = -q;
+    } else {
+        double er = 1.0 + q;
+        // scale by 2^k through the exponent field (k in [-1022, -1])
+        e = __hiloint2double(__double2hiint(er) + k * 1048576, __double2loint(er));
+        one_minus_e = 1.0 - e;
+    }
 }
 
 // `gaussian` kernel: g = 1 - exp(-s^3), g' = 3 s^2 exp(-s^3).  Requires t > 0.
 __device__ __forceinline__ void ab_gaussian(double t, double sinv3, double sinv5, double& A, double& B) {
     double rs = rsqrt_f64(t);       // 1/s
     double s3 = t * (t * rs);       // s^3
-    double e = exp_neg_f64(-s3);
+    double e, ome;
+    exp_neg_f64(-s3, e, ome);
     double rs2 = rs * rs;
-    double G = (1.0 - e) * (rs2 * rs);
+    double G = ome * (rs2 * rs);
     double H = (3.0 * (e - G)) * rs2;
     A = G * sinv3;
     B = H * sinv5;
 }
 
-// One (target, source) interaction.  `rec` points at the 10-double source record in shared memory.
-template <int KERNEL>
-__device__ __forceinline__ void uj_pair(UJAcc& a, double tx, double ty, double tz, const double2* __restrict__ rec,
-                                        const double2* __restrict__ tab) {
-    const double2 s0 = rec[0];  // x, y
-    const double2 s1 = rec[1];  // z, 1/sigma^2
-    const double2 s2 = rec[2];  // G'x, G'y
-    const double2 s3 = rec[3];  // G'z, 1/sigma^3
-    double dx = tx - s0.x, dy = ty - s0.y, dz = tz - s1.x;
+// ---- record accessors (layout in common.cuh) ---------------------------------------------------------------
+struct SrcCore {  // what every branch needs: three LDS.128
+    double x, y, z, gx, gy, gz;
+};
+__device__ __forceinline__ SrcCore load_core(const double2* __restrict__ rec) {
+    const double2 q0 = rec[0], q1 = rec[1], q2 = rec[2];
+    return SrcCore{q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+}
+
+// Far-field interaction (also the whole `singular` kernel when guarded): no table, no branch.
+__device__ __forceinline__ void uj_pair_far(UJAcc& a, double tx, double ty, double tz, const SrcCore& s) {
+    double dx = tx - s.x, dy = ty - s.y, dz = tz - s.z;
     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
     double A, B;
-    if (KERNEL == K_SINGULAR) {
-        ab_singular(r2 > 0.0 ? r2 : 1.0, A, B);
-        A = r2 > 0.0 ? A : 0.0;  // r == 0 skip (src/FLOWUnsteady_processing_force.jl:895)
-    } else if (KERNEL == K_GAUSSIANERF) {
-        double t = r2 * s1.y;
-        if (__all_sync(0xffffffffu, t >= VPM_GT_TFAR)) {
-            ab_singular(r2, A, B);  // t >= T_FAR > 0 implies r2 > 0
+    ab_singular(r2, A, B);
+    uj_accumulate(a, dx, dy, dz, s.gx, s.gy, s.gz, A, B);
+}
+
+// General interaction of the regularised kernels: per-lane choice between table/closed form and far field.
+template <int KERNEL>
+__device__ __forceinline__ void uj_pair_general(UJAcc& a, double dx, double dy, double dz, double r2, const SrcCore& s,
+                                                const double2* __restrict__ rec, const double2* __restrict__ tab) {
+    const double2 q3 = rec[3];  // T_FAR sigma^2, 1/sigma^3
+    const double2 q4 = rec[4];  // 1/sigma^5, 1/sigma^2
+    double A, B;
+    if (KERNEL == K_GAUSSIANERF) {
+        if (__double2hiint(r2) > __double2hiint(q3.x)) {
+            ab_singular(r2, A, B);
         } else {
-            if (t < VPM_GT_TFAR) {
-                ab_gauss_table(tab, t, s3.y, rec[4].x, A, B);
-                A = r2 > 0.0 ? A : 0.0;
-            } else {
-                ab_singular(r2, A, B);
-            }
+            ab_gauss_table(tab, r2 * q4.y, q3.y, q4.x, A, B);
+            A = nonzero_f64(r2) ? A : 0.0;  // r == 0 skip (src/FLOWUnsteady_processing_force.jl:895)
         }
     } else if (KERNEL == K_WINCKELMANS) {
-        double t = r2 * s1.y;
-        ab_winckelmans(t, s3.y, rec[4].x, A, B);
-        A = r2 > 0.0 ? A : 0.0;
+        ab_winckelmans(r2 * q4.y, q3.y, q4.x, A, B);
+        A = nonzero_f64(r2) ? A : 0.0;
     } else {  // K_GAUSSIAN
-        double t = r2 * s1.y;
-        ab_gaussian(t > 0.0 ? t : 1.0, s3.y, rec[4].x, A, B);
-        A = r2 > 0.0 ? A : 0.0;
-        B = r2 > 0.0 ? B : 0.0;
+        const double t = r2 * q4.y;
+        const bool nz = nonzero_f64(t);
+        ab_gaussian(nz ? t : 1.0, q3.y, q4.x, A, B);
+        A = nz ? A : 0.0;
+        B = nz ? B : 0.0;
     }
-    uj_accumulate(a, dx, dy, dz, s2.x, s2.y, s3.x, A, B);
+    uj_accumulate(a, dx, dy, dz, s.gx, s.gy, s.gz, A, B);
+}
+
+// Two sources at a time.  For gaussianerf a warp-uniform vote on "both sources are far for all 32 lanes" selects a
+// straight-line block with two independent rsqrt chains (ILP for the 2-cycle-issue FP64 pipe); the far test is an
+// integer compare of high words (for positive doubles hi(a) > hi(b) implies a > b; conservative by < 2^-20, which the
+// table's spare intervals cover), so it costs no FP64 issue slot.
+template <int KERNEL>
+__device__ __forceinline__ void uj_pair2(UJAcc& a, double tx, double ty, double tz, const double2* __restrict__ rec,
+                                         const double2* __restrict__ tab) {
+    const double2* recA = rec;
+    const double2* recB = rec + REC_REALS / 2;
+    const SrcCore sa = load_core(recA), sb = load_core(recB);
+    double dxa = tx - sa.x, dya = ty - sa.y, dza = tz - sa.z;
+    double dxb = tx - sb.x, dyb = ty - sb.y, dzb = tz - sb.z;
+    double r2a = fma(dza, dza, fma(dya, dya, dxa * dxa));
+    double r2b = fma(dzb, dzb, fma(dyb, dyb, dxb * dxb));
+    if (KERNEL == K_SINGULAR) {
+        const bool nza = nonzero_f64(r2a), nzb = nonzero_f64(r2b);
+        double Aa, Ba, Ab, Bb;
+        ab_singular(nza ? r2a : 1.0, Aa, Ba);
+        ab_singular(nzb ? r2b : 1.0, Ab, Bb);
+        uj_accumulate(a, dxa, dya, dza, sa.gx, sa.gy, sa.gz, nza ? Aa : 0.0, Ba);
+        uj_accumulate(a, dxb, dyb, dzb, sb.gx, sb.gy, sb.gz, nzb ? Ab : 0.0, Bb);
+    } else if (KERNEL == K_GAUSSIANERF) {
+        const bool far = __double2hiint(r2a) > __double2hiint(recA[3].x) && __double2hiint(r2b) > __double2hiint(recB[3].x);
+        if (__all_sync(0xffffffffu, far)) {
+            double Aa, Ba, Ab, Bb;
+            ab_singular(r2a, Aa, Ba);
+            ab_singular(r2b, Ab, Bb);
+            uj_accumulate(a, dxa, dya, dza, sa.gx, sa.gy, sa.gz, Aa, Ba);
+            uj_accumulate(a, dxb, dyb, dzb, sb.gx, sb.gy, sb.gz, Ab, Bb);
+        } else {
+            uj_pair_general<KERNEL>(a, dxa, dya, dza, r2a, sa, recA, tab);
+            uj_pair_general<KERNEL>(a, dxb, dyb, dzb, r2b, sb, recB, tab);
+        }
+    } else {
+        uj_pair_general<KERNEL>(a, dxa, dya, dza, r2a, sa, recA, tab);
+        uj_pair_general<KERNEL>(a, dxb, dyb, dzb, r2b, sb, recB, tab);
+    }
 }
 
 // Shared-memory layout of the pairwise kernels.
 struct __align__(16) PairSmem {
-    double tile[2][TILE_SRC * REC_REALS];
+    double tile[2][TILE_DOUBLES];
     uint64_t full[2];
+    double tbox[8];  // bounding box of this CTA's targets: xmin, xmax, ymin, ymax, zmin, zmax
+    double red[6][8];
 };
 
 constexpr int UJ_BT = 256;  // targets (= threads) per CTA
+constexpr uint32_t TILE_BYTES = TILE_DOUBLES * sizeof(double);
+
+// Bounding box of the CTA's live targets -> sm.tbox (all threads must call).
+__device__ __forceinline__ void cta_target_box(PairSmem& sm, bool live, double px, double py, double pz) {
+    const double big = 1.0e300;
+    double v[6] = {live ? px : big, live ? -px : big, live ? py : big, live ? -py : big, live ? pz : big, live ? -pz : big};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[c] = fmin(v[c], __shfl_xor_sync(0xffffffffu, v[c], o));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 6; ++c) sm.red[c][w] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double m = sm.red[threadIdx.x][0];
+        for (int k = 1; k < UJ_BT / 32; ++k) m = fmin(m, sm.red[threadIdx.x][k]);
+        sm.tbox[threadIdx.x] = (threadIdx.x & 1) ? -m : m;  // odd slots hold maxima
+    }
+    __syncthreads();
+}
+
+// Squared distance between the CTA's target box and a tile's source box (0 when they overlap).
+__device__ __forceinline__ double box_dist2(const double* __restrict__ tb, const double* __restrict__ hdr) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double gap = fmax(fmax(tb[2 * c] - hdr[2 * c + 1], hdr[2 * c] - tb[2 * c + 1]), 0.0);
+        d2 = fma(gap, gap, d2);
+    }
+    return d2;
+}
 
 constexpr size_t uj_smem_bytes(int kernel) {
     return sizeof(PairSmem) + (kernel == K_GAUSSIANERF ? sizeof(double) * 2 * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0);
 }
 
-// Grid: ceil(nt / UJ_BT) CTAs.  srec: ntiles * TILE_SRC records (tail padded with null records).
+// Grid: ceil(nt / UJ_BT) CTAs.  srec: ntiles tiles of TILE_DOUBLES doubles (records + header, common.cuh).
 // Targets: positions tx/ty/tz (nt each).  Outputs: component k of U at U[k * ldo + i], of J at J[k * ldo + i].
 template <int KERNEL>
 __global__ void __launch_bounds__(UJ_BT, 2)
@@ -204,7 +298,6 @@ uj_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* 
 
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * UJ_BT + tid;
-    constexpr uint32_t TILE_BYTES = TILE_SRC * REC_REALS * sizeof(double);
 
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
@@ -223,6 +316,7 @@ uj_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* 
 
     const bool live = i < nt;
     const double px = live ? tx[i] : 0.0, py = live ? ty[i] : 0.0, pz = live ? tz[i] : 0.0;
+    if (KERNEL == K_GAUSSIANERF) cta_target_box(sm, live, px, py, pz);
     UJAcc tot;
     acc_zero(tot);
 
@@ -231,14 +325,25 @@ uj_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* 
         if (tid == 0 && k + 1 < ntiles) {
             // buffer b^1 was last read in iteration k-1; the __syncthreads() that closed it orders those reads
             mbar_arrive_expect_tx(&sm.full[b ^ 1], TILE_BYTES);
-            bulk_g2s(sm.tile[b ^ 1], srec + (size_t)(k + 1) * TILE_SRC * REC_REALS, TILE_BYTES, &sm.full[b ^ 1]);
+            bulk_g2s(sm.tile[b ^ 1], srec + (size_t)(k + 1) * TILE_DOUBLES, TILE_BYTES, &sm.full[b ^ 1]);
         }
         mbar_wait(&sm.full[b], (k >> 1) & 1);
         const double2* rec = reinterpret_cast<const double2*>(sm.tile[b]);
         UJAcc a;
         acc_zero(a);
-#pragma unroll 2
-        for (int j = 0; j < TILE_SRC; ++j) uj_pair<KERNEL>(a, px, py, pz, rec + j * (REC_REALS / 2), tab);
+        bool tile_far = false;
+        if (KERNEL == K_GAUSSIANERF) {
+            const double* hdr = sm.tile[b] + TILE_HDR;
+            tile_far = box_dist2(sm.tbox, hdr) > hdr[6];  // CTA-uniform: whole tile beyond T_FAR sigma_max^2
+        }
+        if (tile_far) {
+            // every (target, source) pair of this tile is in the singular regime: no vote, no table, full ILP
+#pragma unroll 4
+            for (int j = 0; j < TILE_SRC; ++j) uj_pair_far(a, px, py, pz, load_core(rec + j * (REC_REALS / 2)));
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < TILE_SRC; j += 2) uj_pair2<KERNEL>(a, px, py, pz, rec + j * (REC_REALS / 2), tab);
+        }
         acc_add(tot, a);
         __syncthreads();
     }

@@ -97,7 +97,7 @@ __device__ __forceinline__ void uj_pair32(UJAcc32& a, float tx, float ty, float 
 }
 
 struct __align__(16) PairSmem32 {
-    double tile[2][TILE_SRC * REC_REALS];  // FP64 records as they arrive from HBM (bulk TMA)
+    double tile[2][TILE_DOUBLES];          // FP64 tiles as they arrive from HBM (bulk TMA)
     float tile32[TILE_SRC * REC32];        // the current tile converted to FP32, CTA-relative
     uint64_t full[2];
 };
@@ -118,7 +118,6 @@ uj_direct_f32_kernel(const double* __restrict__ srec, int ntiles, const double* 
     const int tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * UJ_BT;
     const int64_t i = i0 + tid;
-    constexpr uint32_t TILE_BYTES = TILE_SRC * REC_REALS * sizeof(double);
 
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
@@ -148,15 +147,16 @@ uj_direct_f32_kernel(const double* __restrict__ srec, int ntiles, const double* 
         const int b = k & 1;
         if (tid == 0 && k + 1 < ntiles) {
             mbar_arrive_expect_tx(&sm.full[b ^ 1], TILE_BYTES);
-            bulk_g2s(sm.tile[b ^ 1], srec + (size_t)(k + 1) * TILE_SRC * REC_REALS, TILE_BYTES, &sm.full[b ^ 1]);
+            bulk_g2s(sm.tile[b ^ 1], srec + (size_t)(k + 1) * TILE_DOUBLES, TILE_BYTES, &sm.full[b ^ 1]);
         }
         mbar_wait(&sm.full[b], (k >> 1) & 1);
         // convert this tile to FP32 (one record per thread: TILE_SRC == UJ_BT)
         {
             const double* r = sm.tile[b] + tid * REC_REALS;
             float4* o = reinterpret_cast<float4*>(sm.tile32 + tid * REC32);
-            o[0] = make_float4((float)(r[0] - ox), (float)(r[1] - oy), (float)(r[2] - oz), (float)r[3]);
-            o[1] = make_float4((float)r[4], (float)r[5], (float)r[6], (float)r[7]);
+            // FP64 record { x, y | z, G'x | G'y, G'z | T_FAR s^2, 1/s^3 | 1/s^5, 1/s^2 } -> FP32 working record
+            o[0] = make_float4((float)(r[0] - ox), (float)(r[1] - oy), (float)(r[2] - oz), (float)r[9]);
+            o[1] = make_float4((float)r[3], (float)r[4], (float)r[5], (float)r[7]);
             o[2] = make_float4((float)r[8], 0.f, 0.f, 0.f);
         }
         __syncthreads();

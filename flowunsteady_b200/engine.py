@@ -190,8 +190,12 @@ class Engine:
         self._check(self._L.vpmb200_synchronize(self._h))
 
     @staticmethod
-    def record_doubles(n: int) -> int:
-        return _lib.lib().vpmb200_record_doubles(int(n))
+    def tiles_for(n: int) -> int:
+        return _lib.lib().vpmb200_tiles_for(int(n))
+
+    @staticmethod
+    def tile_doubles() -> int:
+        return _lib.lib().vpmb200_tile_doubles()
 
     def pack_uj_records(self, dst_ptr: int):
         self._check(self._L.vpmb200_pack_uj_records(self._h, C.c_void_p(dst_ptr)))
@@ -199,11 +203,11 @@ class Engine:
     def pack_estr_records(self, dst_ptr: int):
         self._check(self._L.vpmb200_pack_estr_records(self._h, C.c_void_p(dst_ptr)))
 
-    def uj_from_records(self, rec_ptr: int, nsrc: int, accumulate: bool):
-        self._check(self._L.vpmb200_uj_from_records(self._h, C.c_void_p(rec_ptr), int(nsrc), int(accumulate)))
+    def uj_from_records(self, tiles_ptr: int, ntiles: int, accumulate: bool):
+        self._check(self._L.vpmb200_uj_from_records(self._h, C.c_void_p(tiles_ptr), int(ntiles), int(accumulate)))
 
-    def estr_from_records(self, rec_ptr: int, nsrc: int):
-        self._check(self._L.vpmb200_estr_from_records(self._h, C.c_void_p(rec_ptr), int(nsrc)))
+    def estr_from_records(self, tiles_ptr: int, ntiles: int):
+        self._check(self._L.vpmb200_estr_from_records(self._h, C.c_void_p(tiles_ptr), int(ntiles)))
 
 
 def new_particles(x, gamma, sigma, static=None, vol=None, circulation=None, C_=None) -> np.ndarray:

@@ -35,7 +35,7 @@ def vortex_rings(n_total: int = 1_000_000, nrings: int = 2, R: float = 1.0, a: f
                  Gamma0: float = 1.0, overlap: float = 2.125, disc: float = 2.0):
     """Config 3 (headline): coaxial vortex rings for the leapfrog case, discretised with Nphi cross-sections of
     1 + 3 nc (nc + 1) cells each; nc and Nphi are chosen for near-isotropic spacing h and the field is padded with
-    zero-strength particles on the axis to exactly n_total.  Gaussian vorticity of core size `a` over a disc of
+    (5 eps)-strength particles on the axis to exactly n_total.  Gaussian vorticity of core size `a` over a disc of
     radius disc*a; sigma = overlap * h (lambda = 2.125 as in examples/rotorhover/rotorhover.jl:155)."""
     a_c = disc * a
     per_ring = n_total / nrings
@@ -76,7 +76,9 @@ def vortex_rings(n_total: int = 1_000_000, nrings: int = 2, R: float = 1.0, a: f
         zp = np.linspace(-separation, (nrings + 1) * separation, npad)
         Xp = np.stack([np.zeros(npad), np.zeros(npad), zp], -1)
         X = np.concatenate([X, Xp])
-        G = np.concatenate([G, np.zeros((npad, 3))])
+        # zero-strength padding: floored to 5 eps per component exactly as the reference floors shed particles
+        # ("or ExaFMM will blow up", src/FLOWUnsteady_simulation.jl:464-468), so the integrator's 1/|Gamma|^2 is finite
+        G = np.concatenate([G, np.full((npad, 3), 5 * np.finfo(np.float64).eps)])
         sigma = np.concatenate([sigma, np.full(npad, overlap * h_eff)])
     return np.ascontiguousarray(X), np.ascontiguousarray(G), np.ascontiguousarray(sigma)
 

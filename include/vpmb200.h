@@ -180,15 +180,18 @@ int32_t vpmb200_stream(vpmb200_handle h, void** stream);
 /* Block the host until all enqueued work on the handle has finished. */
 int32_t vpmb200_synchronize(vpmb200_handle h);
 
-/* Pack the 10-double UJ source records of local particles [0, np) into dst (device, >= vpmb200_record_capacity
- * doubles).  Records are what the pair kernels stream; ranks all-gather them (NCCL) to shard the direct path. */
-int64_t vpmb200_record_doubles(int64_t nparticles); /* doubles needed for n particles incl. tile padding */
+/* Source tiles: what the pair kernels stream.  A tile is 256 source records of 10 doubles + one 10-double header
+ * (bounding box, far-field radius), 2570 doubles in all; n particles pack into ceil(n/256) tiles.  Ranks all-gather
+ * whole tiles (NCCL) to shard the direct path, so tile sets from different ranks simply concatenate. */
+int64_t vpmb200_tiles_for(int64_t nparticles);      /* number of tiles for n particles                       */
+int64_t vpmb200_tile_doubles(void);                 /* doubles per tile (2570)                               */
+/* Pack the LOCAL particles [0, np) into dst (device pointer, >= tiles_for(np) * tile_doubles() doubles). */
 int32_t vpmb200_pack_uj_records(vpmb200_handle h, double* dst);
 int32_t vpmb200_pack_estr_records(vpmb200_handle h, double* dst);
-/* U, J (or SFS) of the LOCAL particles from `nsrc` external source records (device pointer, padded to whole
- * tiles as vpmb200_record_doubles prescribes); accumulate != 0 adds to the current values. */
-int32_t vpmb200_uj_from_records(vpmb200_handle h, const double* records, int64_t nsrc, int32_t accumulate);
-int32_t vpmb200_estr_from_records(vpmb200_handle h, const double* records, int64_t nsrc);
+/* U, J (or SFS) of the LOCAL particles from `ntiles` external source tiles (device pointer); accumulate != 0
+ * adds to the current U, J.  The E_str variant always accumulates into SFS. */
+int32_t vpmb200_uj_from_records(vpmb200_handle h, const double* tiles, int64_t ntiles, int32_t accumulate);
+int32_t vpmb200_estr_from_records(vpmb200_handle h, const double* tiles, int64_t ntiles);
 /* The per-particle stages of pfield.SFS / nextstep, exposed so a sharded driver can interleave its exchange:
  * stage ids in vpmb200_stage. */
 enum {
