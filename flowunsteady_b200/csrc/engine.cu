@@ -35,6 +35,7 @@ struct vpmb200_engine {
     unsigned long long* counter = nullptr;
     double t = 0.0;
     int64_t nt = 0;
+    uint64_t launches = 0;      // kernels enqueued by this handle (bench.py's gpu_launches)
     vpmb200_schemes sch;
     std::string err;
 };
@@ -81,6 +82,7 @@ cudaError_t launch_uj(vpmb200_engine* e, const double* rec, int ntiles, const do
         if (st != cudaSuccess) return st;
         kfn<<<blocks_for(nt, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate,
                                                              e->gh_table_f32);
+        e->launches++;
         return cudaGetLastError();
     }
     auto kfn = uj_direct_f64_kernel<K>;
@@ -89,6 +91,7 @@ cudaError_t launch_uj(vpmb200_engine* e, const double* rec, int ntiles, const do
     if (st != cudaSuccess) return st;
     kfn<<<blocks_for(nt, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate,
                                                          e->gh_table);
+    e->launches++;
     return cudaGetLastError();
 }
 
@@ -115,6 +118,7 @@ cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
                                                             S + (size_t)(F_X + 2) * ld, e->np, S + (size_t)F_J * ld, ld,
                                                             e->sch.transposed, e->state + (size_t)F_SFS * ld, ld,
                                                             e->z_table);
+    e->launches++;
     return cudaGetLastError();
 }
 
@@ -131,6 +135,7 @@ int32_t zero_rows(vpmb200_engine* e, int first, int count) {
     if (e->np <= 0) return VPMB200_OK;
     zero_rows_kernel<<<blocks_for(e->np, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, first, count);
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     return VPMB200_OK;
 }
 
@@ -146,6 +151,7 @@ int32_t pack_uj(vpmb200_engine* e, double* dst) {
     if (e->np <= 0) return VPMB200_OK;
     pack_uj_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(e->state, e->ld, e->np, dst);
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     return VPMB200_OK;
 }
 
@@ -154,6 +160,7 @@ int32_t pack_estr(vpmb200_engine* e, double* dst) {
     pack_estr_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(
         e->state, e->ld, e->np, e->sch.transposed, zeta0_of(e->sch.kernel), e->sch.kernel == K_GAUSSIANERF ? 1 : 0, dst);
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     return VPMB200_OK;
 }
 
@@ -205,6 +212,7 @@ int32_t do_stage(vpmb200_engine* e, int stage, double a, double b, double dt, co
         const_coeff_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.Cs);
         break;
     case VPMB200_STAGE_CLIP_CONTROL:
+        if (!(s.clippings || s.controls)) return VPMB200_OK;
         if (s.clippings || s.controls)
             clip_control_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.clippings, s.controls, s.f, zeta0,
                                                            e->t, e->nt);
@@ -225,6 +233,7 @@ int32_t do_stage(vpmb200_engine* e, int stage, double a, double b, double dt, co
         break;
     }
     case VPMB200_STAGE_RELAX:
+        if (s.relaxation == VPMB200_RELAX_NONE) return VPMB200_OK;
         if (s.relaxation != VPMB200_RELAX_NONE)
             relax_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, s.relaxation, s.rlxf);
         break;
@@ -232,10 +241,11 @@ int32_t do_stage(vpmb200_engine* e, int stage, double a, double b, double dt, co
         return fail(e, VPMB200_EINVAL, "unknown stage id");
     }
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     return VPMB200_OK;
 }
 
-// pfield.SFS(pfield; a, b)   (oracle: vpmo_field_sfs)
+// pfield.SFS(pfield; a, b)   
 int32_t do_sfs(vpmb200_engine* e, double a, double b) {
     (void)b;
     const vpmb200_schemes& s = e->sch;
@@ -451,6 +461,7 @@ static int32_t upload_block(vpmb200_engine* e, const double* particles, int64_t 
     dim3 grid(blocks_for(n, 32), (NFIELDS + 31) / 32), block(32, 8);
     aos_to_soa_kernel<<<grid, block, 0, e->stream>>>(e->aos, NFIELDS, n, e->state, e->ld, dst0, mask);
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     // the borrowed host pointer must not be read after return
     CU_TRY(e, cudaStreamSynchronize(e->stream));
     return VPMB200_OK;
@@ -482,6 +493,7 @@ int32_t vpmb200_download(vpmb200_handle e, double* particles, int64_t ld, int64_
     dim3 grid(blocks_for(np, 32), (NFIELDS + 31) / 32), block(32, 8);
     soa_to_aos_kernel<<<grid, block, 0, e->stream>>>(e->state, e->ld, np, e->aos, NFIELDS, field_mask);
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     CU_TRY(e, cudaMemcpy2DAsync(particles, sizeof(double) * ld, e->aos, sizeof(double) * NFIELDS, sizeof(double) * NFIELDS,
                                 (size_t)np, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(e, cudaStreamSynchronize(e->stream));
@@ -506,6 +518,7 @@ int32_t vpmb200_remove_particle(vpmb200_handle e, int64_t i) {
     if (i != e->np - 1) {
         move_column_kernel<<<1, 64, 0, e->stream>>>(e->state, e->ld, i, e->np - 1);
         CU_TRY(e, cudaGetLastError());
+    e->launches++;
     }
     e->np -= 1;
     return VPMB200_OK;
@@ -546,16 +559,19 @@ int32_t vpmb200_uj_probe(vpmb200_handle e, const double* X, int64_t m, double* U
     CU_TRY(e, cudaMemcpyAsync(stage, X, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice, e->stream));
     split_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(stage, 3, m, soaX, pl);
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     if ((rc = pack_uj(e, e->rec))) return rc;
     int ntiles = (int)vpmb200_tiles_for(e->np);
     CU_TRY(e, dispatch_uj(e, e->rec, ntiles, soaX, soaX + pl, soaX + 2 * pl, m, soaU, soaJ, pl, 0));
     join_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(soaU, pl, 3, m, stage);
     CU_TRY(e, cudaGetLastError());
+    e->launches++;
     CU_TRY(e, cudaMemcpyAsync(U, stage, sizeof(double) * 3 * (size_t)m, cudaMemcpyDeviceToHost, e->stream));
     if (J) {
         double* stageJ = stage + 3 * pl;
         join_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(soaJ, pl, 9, m, stageJ);
         CU_TRY(e, cudaGetLastError());
+    e->launches++;
         CU_TRY(e, cudaMemcpyAsync(J, stageJ, sizeof(double) * 9 * (size_t)m, cudaMemcpyDeviceToHost, e->stream));
     }
     CU_TRY(e, cudaStreamSynchronize(e->stream));
@@ -603,6 +619,7 @@ int32_t vpmb200_count_nonfinite(vpmb200_handle e, int64_t* count) {
     if (e->np > 0) {
         count_nonfinite_kernel<<<blocks_for(e->np, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, e->counter);
         CU_TRY(e, cudaGetLastError());
+    e->launches++;
     }
     unsigned long long c = 0;
     CU_TRY(e, cudaMemcpyAsync(&c, e->counter, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
@@ -623,6 +640,13 @@ int32_t vpmb200_stream(vpmb200_handle e, void** stream) {
     CHECK_HANDLE(e);
     if (!stream) return fail(e, VPMB200_EINVAL, "stream is NULL");
     *stream = (void*)e->stream;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_launch_count(vpmb200_handle e, uint64_t* count) {
+    CHECK_HANDLE(e);
+    if (!count) return fail(e, VPMB200_EINVAL, "count is NULL");
+    *count = e->launches;
     return VPMB200_OK;
 }
 

@@ -186,6 +186,12 @@ class Engine:
         self._check(self._L.vpmb200_stream(self._h, C.byref(s)))
         return s.value or 0
 
+    @property
+    def launch_count(self) -> int:
+        c = C.c_uint64()
+        self._check(self._L.vpmb200_launch_count(self._h, C.byref(c)))
+        return c.value
+
     def synchronize(self):
         self._check(self._L.vpmb200_synchronize(self._h))
 

@@ -1,0 +1,524 @@
+"""Host-side mirror of the FLOWVPM interface that FLOWUnsteady drives, backed by the GPU engine.
+
+FLOWUnsteady selects the hot path through scheme *objects* stored in `vpm.ParticleField` and calls it as
+`pfield.UJ(pfield)` (/root/reference/src/FLOWUnsteady_simulation.jl:544, src/FLOWUnsteady_processing_force.jl:238) and
+`vpm.nextstep(pfield, dt; relax)` (simulation.jl:358).  This module keeps those names, argument meanings and error
+behaviour, with Python standing in for Julia (no julia binary exists in this image; the ccall glue a maintainer would
+add is in INTEGRATION.md and julia/FLOWVPMB200.jl).  Differences forced by the language: indices are 0-based, keyword
+`ε_tol` is spelled `eps_tol`, and `pfield.particles` is a (maxparticles, 43) row-major numpy array — byte-identical to
+the reference's 43 x maxparticles column-major matrix.
+
+Every numerical call goes to libvpmb200.so (CUDA); there is no CPU implementation here.  The Kernel objects expose
+`g_dgdr` etc. as small host functions only because the reference's API has them (processing_force.jl:866-868).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field as _dc_field
+from typing import Callable, Iterator, Optional, Sequence
+
+import numpy as np
+
+from . import engine as _E
+from .engine import Engine, EngineError
+
+# ---- particle-matrix row indices (vpm.X_INDEX ... in FLOWVPM v4; 0-based here) -------------------------------
+X_INDEX = slice(_E.X, _E.X + 3)
+GAMMA_INDEX = slice(_E.GAMMA, _E.GAMMA + 3)
+SIGMA_INDEX = _E.SIGMA
+VOL_INDEX = _E.VOL
+CIRCULATION_INDEX = _E.CIRCULATION
+U_INDEX = slice(_E.U, _E.U + 3)
+VORTICITY_INDEX = slice(_E.VORTICITY, _E.VORTICITY + 3)
+J_INDEX = slice(_E.J, _E.J + 9)
+PSE_INDEX = slice(_E.PSE, _E.PSE + 3)
+M_INDEX = slice(_E.M, _E.M + 9)
+C_INDEX = slice(_E.CC, _E.CC + 3)
+SFS_INDEX = slice(_E.SFS, _E.SFS + 3)
+STATIC_INDEX = _E.STATIC
+NFIELDS = _E.NFIELDS
+
+_C1 = 1.0 / (2.0 * math.pi) ** 1.5
+_C2 = math.sqrt(2.0 / math.pi)
+_C4 = 1.0 / (4.0 * math.pi)
+
+
+# ---- kernels (vpm.Kernel) ------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Kernel:
+    name: str
+    id: int
+    zeta: Callable[[float], float]
+    g: Callable[[float], float]
+    dgdr: Callable[[float], float]
+    g_dgdr: Callable[[float], tuple]
+
+
+def _gauserf(r):
+    aux = _C2 * r * math.exp(-r * r / 2)
+    return math.erf(r / math.sqrt(2)) - aux, r * aux
+
+
+def _wnk(r):
+    a0 = (r * r + 1) ** 2.5
+    return r ** 3 * (r * r + 2.5) / a0, 7.5 * r * r / (a0 * (r * r + 1))
+
+
+def _gaus(r):
+    e = math.exp(-r ** 3)
+    return 1 - e, 3 * r * r * e
+
+
+gaussianerf = Kernel("gaussianerf", 0, lambda r: _C1 * math.exp(-r * r / 2), lambda r: _gauserf(r)[0],
+                     lambda r: _gauserf(r)[1], _gauserf)
+winckelmans = Kernel("winckelmans", 1, lambda r: _C4 * 7.5 / (r * r + 1) ** 3.5, lambda r: _wnk(r)[0],
+                     lambda r: _wnk(r)[1], _wnk)
+gaussian = Kernel("gaussian", 2, lambda r: 3 * _C4 * math.exp(-r ** 3), lambda r: _gaus(r)[0], lambda r: _gaus(r)[1], _gaus)
+singular = Kernel("singular", 3, lambda r: 1.0 if r == 0 else 0.0, lambda r: 1.0, lambda r: 0.0, lambda r: (1.0, 0.0))
+kernel_default = gaussianerf
+
+
+# ---- formulations (vpm.rVPM / vpm.cVPM; rvpm.md:197-239) --------------------------------------------------------
+@dataclass(frozen=True)
+class Formulation:
+    f: float
+    g: float
+
+
+formulation_rVPM = rVPM = Formulation(0.0, 1.0 / 5.0)
+formulation_cVPM = cVPM = Formulation(0.0, 0.0)
+formulation_default = rVPM
+
+
+# ---- viscous schemes ---------------------------------------------------------------------------------------------
+class ViscousScheme:
+    pass
+
+
+@dataclass
+class Inviscid(ViscousScheme):
+    nu: float = 0.0
+
+
+@dataclass
+class CoreSpreading(ViscousScheme):
+    """vpm.CoreSpreading(nu, sgm0, zeta; beta, itmax, tol) (examples/rotorhover/rotorhover.jl:170).  The engine applies
+    the sigma update of SURVEY.md A.8; the RBF re-fit on sigma/sgm0 > beta is not built yet (all shipped examples run
+    Inviscid)."""
+    nu: float
+    sgm0: float
+    zeta: object = None
+    beta: float = 1.5
+    itmax: int = 15
+    tol: float = 1e-3
+
+
+def isinviscid(v) -> bool:
+    return isinstance(v, Inviscid)
+
+
+def iscorespreading(v) -> bool:
+    return isinstance(v, CoreSpreading)
+
+
+def zeta_fmm(pfield):  # placeholder object passed as CoreSpreading's `zeta` (simulation.jl:232)
+    raise NotImplementedError("zeta_fmm (RBF vorticity evaluation) is not built yet")
+
+
+def _kernel_compatibility(viscous) -> tuple:
+    """Kernels a viscous scheme accepts (src/FLOWUnsteady_simulation.jl:308-314)."""
+    return (gaussianerf,) if iscorespreading(viscous) else (gaussianerf, winckelmans, gaussian, singular)
+
+
+# ---- relaxation --------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Relaxation:
+    name: str
+    id: int
+    nsteps_relax: int = 1
+    rlxf: float = 0.3
+
+
+pedrizzetti = relaxation_pedrizzeti = Relaxation("pedrizzetti", 1)
+correctedpedrizzetti = relaxation_correctedpedrizzeti = Relaxation("correctedpedrizzetti", 2)
+norelaxation = relaxation_none = Relaxation("none", 0, nsteps_relax=-1, rlxf=0.0)
+relaxation_default = pedrizzetti
+
+
+# ---- FMM settings (vpm.FMM; simulation.jl:43) ---------------------------------------------------------------------
+@dataclass
+class FMM:
+    p: int = 4
+    ncrit: int = 50
+    theta: float = 0.4
+    nonzero_sigma: bool = False
+    eps_tol: Optional[float] = None
+
+
+# ---- SFS schemes (examples/rotorhover/rotorhover.jl:53-55,172-182) ----------------------------------
+def Estr_direct(pfield):
+    pfield.UJ(pfield, sfs=True, reset=True, reset_sfs=True)
+
+
+def Estr_fmm(pfield):
+    pfield.UJ(pfield, sfs=True, reset=True, reset_sfs=True)
+
+
+def pseudo3level(*a, **k):  # marker objects: the procedure itself runs on the GPU (K4)
+    raise RuntimeError("pseudo3level is evaluated inside the engine; pass it to DynamicSFS")
+
+
+def pseudo3level_positive(*a, **k):
+    raise RuntimeError("pseudo3level_positive is evaluated inside the engine; pass it to DynamicSFS")
+
+
+def clipping_backscatter(*a, **k):
+    raise RuntimeError("clipping_backscatter is evaluated inside the engine; pass it in `clippings`")
+
+
+def control_directional(*a, **k):
+    raise RuntimeError("control_directional is evaluated inside the engine; pass it in `controls`")
+
+
+def control_magnitude(*a, **k):
+    raise RuntimeError("control_magnitude is evaluated inside the engine; pass it in `controls`")
+
+
+def control_sigmasensor(*a, **k):
+    raise RuntimeError("control_sigmasensor is not implemented (upstream form unverified)")
+
+
+class SubFilterScale:
+    id = 0
+
+    def __call__(self, pfield, a: float = 1.0, b: float = 1.0):
+        pfield._call_sfs(a, b)
+
+
+class NoSFS(SubFilterScale):
+    id = 0
+
+
+@dataclass
+class ConstantSFS(SubFilterScale):
+    model: Callable = Estr_fmm
+    Cs: float = 1.0
+    clippings: Sequence = ()
+    controls: Sequence = ()
+    id = 1
+
+
+@dataclass
+class DynamicSFS(SubFilterScale):
+    model: Callable = Estr_fmm
+    procedure: Callable = pseudo3level_positive
+    alpha: float = 0.667
+    rlxf: float = 0.005
+    minC: float = 0.0
+    maxC: float = 1.0
+    clippings: Sequence = ()
+    controls: Sequence = ()
+    id = 2
+
+
+def isSFSenabled(sfs) -> bool:
+    return not isinstance(sfs, NoSFS)
+
+
+SFS_none = NoSFS()
+SFS_Cs_nobackscatter = ConstantSFS(Estr_fmm, Cs=1.0, clippings=(clipping_backscatter,))
+SFS_Cd_twolevel_nobackscatter = DynamicSFS(Estr_fmm, pseudo3level_positive, alpha=0.999, clippings=(clipping_backscatter,))
+SFS_Cd_threelevel_nobackscatter = DynamicSFS(Estr_fmm, pseudo3level_positive, alpha=0.667, clippings=(clipping_backscatter,))
+SFS_default = SFS_none
+
+
+# ---- UJ schemes ----------------------------------------------------------------------------------------------------
+def UJ_direct(pfield, reset: bool = True, reset_sfs: bool = False, sfs: bool = False, rbf: bool = False, **_):
+    """pfield.UJ(pfield; reset, reset_sfs, sfs): U and J at every particle by direct P2P on the GPU (K1 [+ K2])."""
+    if rbf:
+        raise NotImplementedError("rbf=True (vorticity by zeta) is not built yet")
+    pfield._call_uj(_E.UJ_IDS["direct"], reset, reset_sfs, sfs)
+
+
+def UJ_fmm(pfield, reset: bool = True, reset_sfs: bool = False, sfs: bool = False, rbf: bool = False, sort: bool = True, **_):
+    if rbf:
+        raise NotImplementedError("rbf=True (vorticity by zeta) is not built yet")
+    pfield._call_uj(_E.UJ_IDS["fmm"], reset, reset_sfs, sfs)
+
+
+# ---- time integration ----------------------------------------------------------------------------------------------
+def euler(pfield, dt: float, relax: bool = False, custom_UJ=None):
+    pfield._call_nextstep(_E.INTEGRATION_IDS["euler"], dt, relax, custom_UJ)
+
+
+def rungekutta3(pfield, dt: float, relax: bool = False, custom_UJ=None):
+    pfield._call_nextstep(_E.INTEGRATION_IDS["rungekutta3"], dt, relax, custom_UJ)
+
+
+# ---- the particle field --------------------------------------------------------------------------------------------
+class Particle:
+    """View of one particle column (vpm.get_particle): fields are numpy views into pfield.particles."""
+    __slots__ = ("_c",)
+
+    def __init__(self, col: np.ndarray):
+        self._c = col
+
+    X = property(lambda s: s._c[X_INDEX])
+    Gamma = property(lambda s: s._c[GAMMA_INDEX])
+    sigma = property(lambda s: s._c[SIGMA_INDEX:SIGMA_INDEX + 1])
+    vol = property(lambda s: s._c[VOL_INDEX:VOL_INDEX + 1])
+    circulation = property(lambda s: s._c[CIRCULATION_INDEX:CIRCULATION_INDEX + 1])
+    U = property(lambda s: s._c[U_INDEX])
+    J = property(lambda s: s._c[J_INDEX].reshape(3, 3).T)   # J[i, j] = du_i/dx_j
+    M = property(lambda s: s._c[M_INDEX].reshape(3, 3).T)
+    C = property(lambda s: s._c[C_INDEX])
+    SFS = property(lambda s: s._c[SFS_INDEX])
+    static = property(lambda s: bool(s._c[STATIC_INDEX] > 0))
+
+
+def get_X(P): return P.X
+def get_Gamma(P): return P.Gamma
+def get_sigma(P): return P.sigma
+def get_vol(P): return P.vol
+def get_circulation(P): return P.circulation
+def get_U(P): return P.U
+def get_C(P): return P.C
+def get_J(P): return P.J
+def get_SFS(P): return P.SFS
+
+
+class ParticleField:
+    """vpm.ParticleField(maxparticles, R; Uinf, formulation, viscous, kernel, UJ, SFS, integration, transposed,
+    relaxation, fmm)  — constructor call at src/FLOWUnsteady_simulation.jl:239-253.
+
+    `particles` is host memory owned by the caller's side of the boundary (the reference's Julia matrix).  Each hot-path
+    call uploads the groups the engine reads and downloads the groups it wrote (`sync="always"`, the drop-in
+    behaviour), or keeps the field device-resident between calls (`sync="lazy"`: call `pull()` before reading and
+    `mark_dirty()` after writing `particles` by hand).
+    """
+
+    def __init__(self, maxparticles: int, R=np.float64, *, Uinf: Callable[[float], Sequence[float]] = lambda t: (0.0, 0.0, 0.0),
+                 formulation: Formulation = formulation_default, viscous: ViscousScheme = None, kernel: Kernel = kernel_default,
+                 UJ: Callable = UJ_fmm, SFS: SubFilterScale = SFS_default, integration: Callable = rungekutta3,
+                 transposed: bool = True, relaxation: Relaxation = relaxation_default, fmm: FMM = None,
+                 device: int = 0, sync: str = "always", pinned: bool = False):
+        if R not in (np.float64, np.float32, float):
+            raise TypeError("R must be Float64 or Float32 (vpm_floattype, simulation.jl:137)")
+        viscous = Inviscid() if viscous is None else viscous
+        if kernel not in _kernel_compatibility(viscous):
+            raise ValueError(f"Kernel {kernel.name} is not compatible with viscous scheme {type(viscous).__name__}")
+        if sync not in ("always", "lazy"):
+            raise ValueError("sync must be 'always' or 'lazy'")
+        self.maxparticles = int(maxparticles)
+        self.R = R
+        if pinned:
+            import torch
+            self._pin = torch.empty((self.maxparticles, NFIELDS), dtype=torch.float64, pin_memory=True)
+            self._pin.zero_()
+            self.particles = self._pin.numpy()
+        else:
+            self.particles = np.zeros((self.maxparticles, NFIELDS))
+        self.np = 0
+        self.nt = 0
+        self.t = 0.0
+        self.Uinf = Uinf
+        self.formulation, self.viscous, self.kernel = formulation, viscous, kernel
+        self.UJ, self.SFS, self.integration = UJ, SFS, integration
+        self.transposed, self.relaxation = bool(transposed), relaxation
+        self.fmm = FMM() if fmm is None else fmm
+        self.sync = sync
+        self._engine = Engine(self.maxparticles, float_bits=32 if R is np.float32 else 64, device=device)
+        self._host_dirty = True     # host matrix holds changes the device has not seen
+        self._dev_dirty = 0         # field-group mask the device holds newer than the host
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ---- scheme translation ------------------------------------------------------------------------------------
+    def _schemes(self, uj_id: int, integration_id: Optional[int] = None):
+        sfs = self.SFS
+        kw = dict(kernel=self.kernel.id, f=self.formulation.f, g=self.formulation.g, transposed=int(self.transposed),
+                  relaxation=self.relaxation.id, rlxf=self.relaxation.rlxf, sfs=sfs.id, uj=uj_id,
+                  fmm_p=self.fmm.p, fmm_ncrit=self.fmm.ncrit, fmm_theta=self.fmm.theta,
+                  fmm_nonzero_sigma=int(self.fmm.nonzero_sigma))
+        if isinstance(sfs, (ConstantSFS, DynamicSFS)):
+            clip = 0
+            for c in sfs.clippings:
+                if c is clipping_backscatter:
+                    clip |= _E.CLIP_BACKSCATTER
+                else:
+                    raise NotImplementedError(f"clipping {getattr(c, '__name__', c)} is not available in the engine")
+            ctrl = 0
+            for c in sfs.controls:
+                if c is control_directional:
+                    ctrl |= _E.CTRL_DIRECTIONAL
+                elif c is control_magnitude:
+                    ctrl |= _E.CTRL_MAGNITUDE
+                else:
+                    raise NotImplementedError(f"control {getattr(c, '__name__', c)} is not available in the engine")
+            kw.update(clippings=clip, controls=ctrl)
+        if isinstance(sfs, ConstantSFS):
+            kw.update(Cs=sfs.Cs)
+        if isinstance(sfs, DynamicSFS):
+            if sfs.procedure not in (pseudo3level, pseudo3level_positive):
+                raise NotImplementedError("only the pseudo3level procedures are available in the engine")
+            kw.update(alpha=sfs.alpha, sfs_rlxf=sfs.rlxf, minC=sfs.minC, maxC=sfs.maxC,
+                      force_positive=int(sfs.procedure is pseudo3level_positive))
+        if iscorespreading(self.viscous):
+            kw.update(viscous=1, nu=self.viscous.nu)
+        if integration_id is not None:
+            kw.update(integration=integration_id)
+        return _E.default_schemes(**kw)
+
+    def _uj_id(self) -> int:
+        if self.UJ is UJ_direct:
+            return _E.UJ_IDS["direct"]
+        if self.UJ is UJ_fmm:
+            return _E.UJ_IDS["fmm"]
+        raise NotImplementedError("custom UJ callables cannot run inside the GPU engine; use vpm.UJ_direct or vpm.UJ_fmm")
+
+    # ---- host <-> device synchronisation -------------------------------------------------------------------------
+    def mark_dirty(self):
+        """Tell the field that `particles` was modified on the host."""
+        self._host_dirty = True
+
+    def _push(self, mask: int = _E.FM_ALL):
+        if self.sync == "always" or self._host_dirty:
+            self._engine.upload(self.particles, self.np, mask)
+            self.h2d_bytes += self.np * 8 * _rows(mask)
+            self._host_dirty = False
+        self._engine.set_time(self.t, self.nt)
+
+    def _pulled(self, mask: int):
+        if self.sync == "always":
+            self.pull(mask)
+        else:
+            self._dev_dirty |= mask
+
+    def pull(self, mask: Optional[int] = None):
+        """Bring device results back into `particles`."""
+        mask = self._dev_dirty if mask is None else mask
+        if mask and self.np > 0:
+            self._engine.download(self.particles, self.np, mask)
+            self.d2h_bytes += self.np * 8 * _rows(mask)
+        self._dev_dirty &= ~mask
+
+    # ---- hot-path entry points (called by the scheme objects) -----------------------------------------------------
+    def _call_uj(self, uj_id: int, reset: bool, reset_sfs: bool, sfs: bool):
+        self._engine.set_schemes(self._schemes(uj_id))
+        self._push(_E.FM_ALL if not (reset and reset_sfs) else _E.FM_STATE | _E.FM_SFS | _E.FM_U | _E.FM_J)
+        self._engine.uj(reset, reset_sfs, sfs)
+        self._pulled(_E.FM_U | _E.FM_J | _E.FM_PSE | (_E.FM_SFS if (sfs or reset_sfs) else 0))
+
+    def _call_sfs(self, a: float, b: float):
+        self._engine.set_schemes(self._schemes(self._uj_id()))
+        self._push(_E.FM_ALL)
+        self._engine.sfs(a, b)
+        self._pulled(_E.FM_U | _E.FM_J | _E.FM_PSE | _E.FM_SFS | _E.FM_C | _E.FM_M | _E.FM_SIGMA)
+
+    def _call_nextstep(self, integration_id: int, dt: float, relax: bool, custom_UJ):
+        if custom_UJ is not None:
+            raise NotImplementedError("custom_UJ cannot run inside the GPU engine")
+        self._engine.set_schemes(self._schemes(self._uj_id(), integration_id))
+        self._push(_E.FM_STATE | _E.FM_M)
+        self._engine.nextstep(dt, tuple(self.Uinf(self.t)), relax)
+        self._pulled(_E.FM_ALL & ~(_E.FM_VOL | _E.FM_CIRCULATION | _E.FM_STATIC | _E.FM_VORTICITY))
+
+    # ---- probes: Vvpm_on_Xs without evaluating every target (simulation.jl:494-570) -------------------------------
+    def U_at(self, Xs, want_J: bool = False):
+        self._engine.set_schemes(self._schemes(_E.UJ_IDS["direct"]))
+        self._push(_E.FM_STATE)
+        return self._engine.uj_probe(np.asarray(Xs, dtype=np.float64), want_J)
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine
+
+
+def _rows(mask: int) -> int:
+    counts = (3, 3, 1, 1, 1, 3, 3, 9, 3, 9, 3, 3, 1)
+    return sum(c for k, c in enumerate(counts) if (mask >> k) & 1)
+
+
+# ---- free functions of the FLOWVPM API ---------------------------------------------------------------------------------
+def get_np(pfield: ParticleField) -> int:
+    return pfield.np
+
+
+def get_particle(pfield: ParticleField, i: int) -> Particle:
+    if i < 0 or i >= pfield.np:
+        raise IndexError(f"Requested invalid particle index {i}")
+    return Particle(pfield.particles[i])
+
+
+def iterator(pfield: ParticleField, start_i: int = 0, end_i: Optional[int] = None, include_static: bool = False) -> Iterator[Particle]:
+    end_i = pfield.np if end_i is None else end_i
+    for i in range(start_i, end_i):
+        if include_static or not pfield.particles[i, STATIC_INDEX] > 0:
+            yield Particle(pfield.particles[i])
+
+
+iterate = iterator
+
+
+def add_particle(pfield: ParticleField, X, Gamma=None, sigma=None, *, vol=0.0, circulation=1.0, C=0.0, static=False, index=-1):
+    """vpm.add_particle(pfield, X, Gamma, sigma; vol, circulation, C, static, index) (simulation.jl:486,572) or
+    vpm.add_particle(pfield, P) with a Particle."""
+    if pfield.np == pfield.maxparticles:
+        raise RuntimeError(f"PARTICLE OVERFLOW. Max number of particles {pfield.maxparticles} has been reached")
+    col = pfield.particles[pfield.np]
+    if isinstance(X, Particle):
+        col[:] = X._c
+    else:
+        col[:] = 0.0
+        col[X_INDEX] = X
+        col[GAMMA_INDEX] = Gamma
+        col[SIGMA_INDEX] = float(np.ravel(sigma)[0])
+        col[VOL_INDEX] = float(np.ravel(vol)[0])
+        col[CIRCULATION_INDEX] = abs(float(np.ravel(circulation)[0]))
+        col[C_INDEX] = C
+        col[STATIC_INDEX] = 1.0 if static else 0.0
+    pfield.np += 1
+    pfield.mark_dirty()
+
+
+def remove_particle(pfield: ParticleField, i: int):
+    """vpm.remove_particle(pfield, i): the last particle is moved into slot i (0-based here)."""
+    if i < 0 or i >= pfield.np:
+        raise IndexError(f"Requested removal of invalid particle index {i}")
+    if pfield._dev_dirty:
+        pfield.pull()
+    if i != pfield.np - 1:
+        pfield.particles[i] = pfield.particles[pfield.np - 1]
+    pfield.np -= 1
+    pfield.mark_dirty()
+
+
+def _reset_particles(pfield: ParticleField):
+    """vpm._reset_particles (processing_force.jl:237): U, J, PSE <- 0."""
+    pfield.particles[:pfield.np, U_INDEX] = 0.0
+    pfield.particles[:pfield.np, J_INDEX] = 0.0
+    pfield.particles[:pfield.np, PSE_INDEX] = 0.0
+    pfield.mark_dirty()
+
+
+def _reset_particles_sfs(pfield: ParticleField):
+    pfield.particles[:pfield.np, SFS_INDEX] = 0.0
+    pfield.mark_dirty()
+
+
+def nextstep(pfield: ParticleField, dt: float, relax: bool = False, custom_UJ=None):
+    """vpm.nextstep(pfield, dt; relax, custom_UJ) (simulation.jl:358)."""
+    if pfield.np > 0:
+        pfield.integration(pfield, dt, relax=relax, custom_UJ=custom_UJ)
+    else:
+        pass
+    pfield.t += dt
+    pfield.nt += 1
+
+
+def monitor_enstrophy_value(pfield: ParticleField) -> float:
+    """0.5 sum Gamma_p . omega(x_p) with omega = curl u from J (vpm.monitor_enstrophy, monitors.jl:614)."""
+    P = pfield.particles[:pfield.np]
+    Jm = P[:, J_INDEX]
+    w = np.stack([Jm[:, 5] - Jm[:, 7], Jm[:, 6] - Jm[:, 2], Jm[:, 1] - Jm[:, 3]], -1)
+    return 0.5 * float(np.einsum("ij,ij->", P[:, GAMMA_INDEX], w))
