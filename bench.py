@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the rVPM particle-field hot path on B200.
+
+Metric (BASELINE.json): particle interactions/s and s/timestep (UJ + SFS + RK3) at N = 1M, direct P2P FP64.
+Workload (BASELINE.json configs[2]): synthetic isolated vortex-ring leapfrog, N = 1,000,000 particles, gaussianerf.
+A *step* is one `vpm.nextstep` with rungekutta3 + pedrizzetti relaxation and SFS_none (FLOWUnsteady's defaults,
+/root/reference/src/FLOWUnsteady_simulation.jl:36-44): 3 substeps + the relaxation evaluation = 4 full U/J
+evaluations = 4 N^2 ordered (target, source) interactions, plus the O(N) pack / update / relaxation kernels.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 1000000] [--sfs none|dynamic]
+
+N > 1 is launched by the driver as torchrun (one rank per GPU, NCCL); particles are block-partitioned over ranks
+(strong scaling at fixed N; flowunsteady_b200/dist.py).  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores): the
+reference's own implementation is Julia code in an un-vendored dependency and no julia binary exists in this image
+(DESIGN.md §3), so there is no oracle/_ref; each of its steps is a bounded sample (1024 targets x N sources per
+evaluation) of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_INTERACTION = 86          # U + J, gaussianerf, reference expression form
+EVALS_PER_STEP = {"none": 4, "dynamic": 5}   # full U/J evaluations per RK3 + pedrizzetti step
+
+
+# --------------------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="particles (BASELINE config: 1M)")
+    ap.add_argument("--sfs", default="none", choices=["none", "dynamic"], help="SFS scheme of the timed step")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-targets", type=int, default=4096, help="targets of the CPU baseline slab")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "", 1).isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "", 1).isdigit()]
+        reasons = []
+        for k, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(len(s) > k and s[k].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        busy = [v for v in sm if v > 0.5 * (max(mx) if mx else 1)]
+        return {"sm_mhz": statistics.median(busy or sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_field(n: int):
+    from flowunsteady_b200 import fields
+    return fields.vortex_rings(n)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: OpenMP restatement of the reference algorithm on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as o
+    o.build()
+    n = args.n
+    x, g, s = make_field(n)
+    m = 1024                                                   # bounded sample: targets per evaluation
+    idx = np.random.default_rng(1234).choice(n, m, replace=False)
+    xt = np.ascontiguousarray(x[idx])
+    evals = EVALS_PER_STEP[args.sfs]
+    cores = o.num_threads()
+
+    def step():
+        for _ in range(evals):
+            o.uj_direct("gaussianerf", x, g, s, xt, accum=0)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = evals * m * n / dt
+    line = {
+        "impl": "reference", "metric": "particle interactions/s (UJ+SFS+RK3 step, direct P2P FP64)", "value": value,
+        "unit": "interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "vortex-ring leapfrog, direct P2P FP64, gaussianerf", "particles": n, "sfs": args.sfs,
+                   "evaluations_per_step": evals},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": "port",
+                         "sample": f"{m} targets x {n} sources per U/J evaluation, {evals} evaluations per step; "
+                                   "OpenMP restatement of the reference algorithm (oracle/vpm_oracle.c), not FLOWVPM itself"},
+        "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "full_step_ms_extrapolated": dt * 1e3 * n / m,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import _lib, engine as E, vpm
+    from flowunsteady_b200.dist import ShardedField, partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200: flowunsteady_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    n = args.n
+    x, g, s = make_field(n)
+    lo, hi = partition(n, world)[rank]
+    P_local = fb.new_particles(x[lo:hi], g[lo:hi], s[lo:hi])
+    sch = fb.default_schemes(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti", uj="direct")
+    if args.sfs == "dynamic":   # SFS_Cd_twolevel_nobackscatter (rotorhover high fidelity, rotorhover.jl:53-55)
+        sch = fb.default_schemes(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti", uj="direct",
+                                 sfs="dynamic", alpha=0.999, force_positive=1, clippings=1)
+    evals = EVALS_PER_STEP[args.sfs]
+    dt_sim, Uinf = 1.0e-3, (0.0, 0.0, 0.0)
+
+    eng = fb.Engine(hi - lo, float_bits=64, device=local_rank, schemes=sch)
+    eng.upload(P_local)
+    field = ShardedField(eng, max_local=hi - lo, device=f"cuda:{local_rank}")
+    ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, reps):
+        """Device time of `reps` calls of fn on the engine's stream, bracketed by barrier + synchronize; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(reps):
+            fn()
+        e1.record(ext)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local_rank}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step():
+        field.nextstep(dt_sim, Uinf, relax=True)
+
+    # ---- FP64 peak of this GPU, live (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) -----------------
+    L = _lib.lib()
+    tf, ms_ = C.c_double(), C.c_double()
+    L.vpmb200_measure_fp64_peak(local_rank, 2000, 5, C.byref(tf), C.byref(ms_))
+    fp64_peak_tflops = tf.value
+
+    # ---- device-resident throughput: W warm-up + K timed steps ------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    ms_total = timed(step, args.steps)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = evals * float(n) * float(n) / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone: one U/J evaluation (K1 + its pack kernel) ---------------------------------------------
+    k1_reps = 3
+    k1_ms = timed(lambda: field.uj(True, False, False), k1_reps) / k1_reps
+    k1_rate = float(n) * float(n) / (k1_ms * 1e-3)
+    achieved_tflops = k1_rate * FLOPS_PER_INTERACTION / 1e12 / world       # per GPU
+    roofline = {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None, "traffic": None,
+                "kernel": "uj_direct_f64_kernel<gaussianerf>", "kernel_ms": k1_ms,
+                "interactions_per_s": k1_rate, "flops_per_interaction": FLOPS_PER_INTERACTION,
+                "peak_source": "live DFMA microbenchmark on this GPU (vpmb200_measure_fp64_peak); "
+                               "MEASURED_PEAKS.json has HBM/bf16 only"}
+    traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----------------
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            pf = vpm.ParticleField(n, formulation=vpm.rVPM, kernel=vpm.gaussianerf, UJ=vpm.UJ_direct,
+                                   SFS=(vpm.SFS_Cd_twolevel_nobackscatter if args.sfs == "dynamic" else vpm.SFS_none),
+                                   integration=vpm.rungekutta3, relaxation=vpm.pedrizzetti, device=local_rank,
+                                   sync="always", pinned=True)
+            pf.particles[:n] = P_local
+            pf.np = n
+            eng.close()                                   # free the first field's HBM before timing the second
+            vpm.nextstep(pf, dt_sim, relax=True)          # warm-up
+            pf.h2d_bytes = pf.d2h_bytes = 0
+            t0 = time.perf_counter()
+            ksteps = max(1, min(args.steps, 2))
+            for _ in range(ksteps):
+                vpm.nextstep(pf, dt_sim, relax=True)      # upload state -> RK3 step on the GPU -> download results
+            pf.engine.synchronize()
+            dt_e2e = (time.perf_counter() - t0) / ksteps
+            e2e = {"value": evals * float(n) * float(n) / dt_e2e, "unit": "interactions/s",
+                   "h2d_bytes_per_step": pf.h2d_bytes // ksteps, "d2h_bytes_per_step": pf.d2h_bytes // ksteps,
+                   "ms_per_step": dt_e2e * 1e3, "steps": ksteps, "api": "flowunsteady_b200.vpm.nextstep(ParticleField)"}
+        else:
+            # sharded: every rank uploads its shard from pinned host memory, steps, and downloads its shard
+            host = torch.empty((hi - lo, 43), dtype=torch.float64, pin_memory=True)
+            host.numpy()[:] = P_local
+            hb = host.numpy()
+
+            def e2e_step():
+                eng.upload(hb, field_mask=E.FM_STATE)
+                field.nextstep(dt_sim, Uinf, relax=True)
+                eng.download(hb, field_mask=E.FM_ALL)
+
+            e2e_step()
+            ksteps = max(1, min(args.steps, 2))
+            ms_e2e = timed(e2e_step, ksteps) / ksteps
+            e2e = {"value": evals * float(n) * float(n) / (ms_e2e * 1e-3), "unit": "interactions/s",
+                   "h2d_bytes_per_step": 13 * 8 * n, "d2h_bytes_per_step": 43 * 8 * n, "ms_per_step": ms_e2e,
+                   "steps": ksteps, "api": "Engine.upload + dist.ShardedField.nextstep + Engine.download per rank"}
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as o
+        o.build()
+        m = args.cpu_targets
+        idx = np.random.default_rng(1234).choice(n, m, replace=False)
+        xt = np.ascontiguousarray(x[idx])
+        o.uj_direct("gaussianerf", x[:50_000], g[:50_000], s[:50_000], xt[:256], accum=0)   # thread warm-up
+        t0 = time.perf_counter()
+        o.uj_direct("gaussianerf", x, g, s, xt, accum=0)
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": m * float(n) / dt_cpu, "unit": "interactions/s", "cores": o.num_threads(), "kind": "port",
+               "sample": f"one U/J evaluation of {m} sampled targets x {n} sources ({dt_cpu:.1f} s); full-field time "
+                         f"extrapolated linearly in targets = {dt_cpu * n / m:.0f} s per evaluation",
+               "note": "OpenMP restatement of the reference algorithm (oracle/vpm_oracle.c); the reference's Julia "
+                       "implementation (FLOWVPM) cannot run in this image"}
+
+    if rank == 0:
+        line = {
+            "metric": "particle interactions/s (UJ+SFS+RK3 step, direct P2P FP64)", "value": value,
+            "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "s_per_timestep": ms_per_step * 1e-3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "vortex-ring leapfrog (2 coaxial rings), direct P2P FP64, gaussianerf, rVPM, "
+                                   "rungekutta3 + pedrizzetti", "particles": n, "sfs": args.sfs,
+                       "evaluations_per_step": evals, "parallelism": f"targets block-partitioned over {world} GPU(s), "
+                       "source tiles all-gathered (NCCL)", "l2": "inputs larger than L2 (state 344 MB > 126 MB); state is "
+                       "rewritten every substep"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
