@@ -7,7 +7,7 @@ A *step* is one `vpm.nextstep` with rungekutta3 + pedrizzetti relaxation and SFS
 /root/reference/src/FLOWUnsteady_simulation.jl:36-44): 3 substeps + the relaxation evaluation = 4 full U/J
 evaluations = 4 N^2 ordered (target, source) interactions, plus the O(N) pack / update / relaxation kernels.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 1000000] [--sfs none|dynamic]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles 1000000] [--sfs none|dynamic]
 
 N > 1 is launched by the driver as torchrun (one rank per GPU, NCCL); particles are block-partitioned over ranks
 (strong scaling at fixed N; flowunsteady_b200/dist.py).  Rank 0 prints ONE JSON line.
@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="particles (BASELINE config: 1M)")
+    ap.add_argument("--particles", dest="n", type=int, default=1_000_000, help="particles (BASELINE config: 1M)")
     ap.add_argument("--sfs", default="none", choices=["none", "dynamic"], help="SFS scheme of the timed step")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -232,7 +232,10 @@ def run_ours(args):
     traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            tj = json.load(open(traffic_file))
+            if int(tj.get("n", -1)) == n and world == 1:      # only quote a capture of this very launch shape
+                roofline["traffic"] = tj.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass
 

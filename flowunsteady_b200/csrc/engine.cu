@@ -30,6 +30,9 @@ struct vpmb200_engine {
     double* gh_table = nullptr; // Gaussian-erf G/H table
     double* z_table = nullptr;  // Gaussian-erf zeta table
     float* gh_table_f32 = nullptr;
+    double* partial = nullptr;  // per-chunk partial outputs of source-split pair launches
+    size_t partial_doubles = 0;
+    int sm_count = 148;
     double* probe = nullptr;    // probe scratch: 3 (X) + 3 (U) + 9 (J) rows of probe_ld, + AoS staging
     int64_t probe_cap = 0;
     unsigned long long* counter = nullptr;
@@ -71,28 +74,82 @@ double zeta0_of(int kernel) {
     }
 }
 
+// Launch geometry of a pair kernel: enough (target block, source chunk) work items for >= ~24 waves of 2 CTAs/SM, so
+// the tail of the last wave costs a few percent at most (a 125k-target shard alone is only 1.65 waves).
+struct Geometry {
+    dim3 grid;
+    SplitArgs split;
+    int nchunks;
+};
+
+cudaError_t make_geometry(vpmb200_engine* e, int64_t nt, int ntiles, int ncomp, Geometry* g) {
+    const int nblocks = (int)blocks_for(nt, UJ_BT);
+    const int slots = 2 * e->sm_count;
+    int nchunks = 1;
+    if (nblocks < 24 * slots && ntiles >= 16) {
+        nchunks = (24 * slots + nblocks - 1) / nblocks;
+        if (nchunks > 64) nchunks = 64;
+        if (nchunks > ntiles / 8) nchunks = ntiles / 8;   // keep >= 8 tiles (2048 sources) per work item
+        if (nchunks < 1) nchunks = 1;
+    }
+    g->nchunks = nchunks;
+    g->grid = dim3((unsigned)nblocks, (unsigned)nchunks, 1);
+    g->split.partial = nullptr;
+    g->split.ldp = 0;
+    g->split.tiles_per_chunk = ntiles;
+    if (nchunks > 1) {
+        const int64_t ldp = round_up(nt, 32);
+        const size_t need = (size_t)nchunks * ncomp * ldp;
+        if (need > e->partial_doubles) {
+            if (e->partial) cudaFree(e->partial);
+            e->partial = nullptr;
+            e->partial_doubles = 0;
+            cudaError_t st = cudaMalloc(&e->partial, need * sizeof(double));
+            if (st != cudaSuccess) return st;
+            e->partial_doubles = need;
+        }
+        g->split.partial = e->partial;
+        g->split.ldp = ldp;
+        g->split.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
+        g->nchunks = (ntiles + g->split.tiles_per_chunk - 1) / g->split.tiles_per_chunk;
+        g->grid.y = (unsigned)g->nchunks;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t reduce_split(vpmb200_engine* e, const Geometry& g, int ncomp, int64_t nt, double* dstA, double* dstB, int nfirst,
+                         int64_t ldo, int accumulate) {
+    if (g.nchunks <= 1 || g.split.partial == nullptr) return cudaSuccess;
+    reduce_partials_kernel<<<blocks_for(nt, PK_BT), PK_BT, 0, e->stream>>>(g.split.partial, g.nchunks, ncomp, g.split.ldp, nt,
+                                                                         dstA, dstB, nfirst, ldo, accumulate);
+    e->launches++;
+    return cudaGetLastError();
+}
+
 template <int K>
 cudaError_t launch_uj(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty,
                       const double* tz, int64_t nt, double* U, double* J, int64_t ldo, int accumulate) {
     if (nt <= 0) return cudaSuccess;
+    Geometry g;
+    cudaError_t st = make_geometry(e, nt, ntiles, 12, &g);
+    if (st != cudaSuccess) return st;
     if (e->float_bits == 32) {
         auto kfn = uj_direct_f32_kernel<K>;
         size_t smem = uj_f32_smem_bytes(K);
-        cudaError_t st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (st != cudaSuccess) return st;
-        kfn<<<blocks_for(nt, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate,
-                                                             e->gh_table_f32);
-        e->launches++;
-        return cudaGetLastError();
+        kfn<<<g.grid, UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate, e->gh_table_f32, g.split);
+    } else {
+        auto kfn = uj_direct_f64_kernel<K>;
+        size_t smem = uj_smem_bytes(K);
+        st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (st != cudaSuccess) return st;
+        kfn<<<g.grid, UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate, e->gh_table, g.split);
     }
-    auto kfn = uj_direct_f64_kernel<K>;
-    size_t smem = uj_smem_bytes(K);
-    cudaError_t st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (st != cudaSuccess) return st;
-    kfn<<<blocks_for(nt, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, nt, U, J, ldo, accumulate,
-                                                         e->gh_table);
     e->launches++;
-    return cudaGetLastError();
+    st = cudaGetLastError();
+    if (st != cudaSuccess) return st;
+    return reduce_split(e, g, 12, nt, U, J, 3, ldo, accumulate);
 }
 
 cudaError_t dispatch_uj(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty,
@@ -108,18 +165,23 @@ cudaError_t dispatch_uj(vpmb200_engine* e, const double* rec, int ntiles, const 
 template <int K>
 cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
     if (e->np <= 0) return cudaSuccess;
+    Geometry g;
+    cudaError_t st = make_geometry(e, e->np, ntiles, 3, &g);
+    if (st != cudaSuccess) return st;
     auto kfn = estr_direct_f64_kernel<K>;
     size_t smem = estr_smem_bytes(K);
-    cudaError_t st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
     const double* S = e->state;
     const int64_t ld = e->ld;
-    kfn<<<blocks_for(e->np, UJ_BT), UJ_BT, smem, e->stream>>>(rec, ntiles, S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld,
-                                                            S + (size_t)(F_X + 2) * ld, e->np, S + (size_t)F_J * ld, ld,
-                                                            e->sch.transposed, e->state + (size_t)F_SFS * ld, ld,
-                                                            e->z_table);
+    double* sfs = e->state + (size_t)F_SFS * ld;
+    kfn<<<g.grid, UJ_BT, smem, e->stream>>>(rec, ntiles, S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld,
+                                          S + (size_t)(F_X + 2) * ld, e->np, S + (size_t)F_J * ld, ld, e->sch.transposed, sfs,
+                                          ld, e->z_table, g.split);
     e->launches++;
-    return cudaGetLastError();
+    st = cudaGetLastError();
+    if (st != cudaSuccess) return st;
+    return reduce_split(e, g, 3, e->np, sfs, sfs, 3, ld, 1);
 }
 
 cudaError_t dispatch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
@@ -363,6 +425,7 @@ int32_t vpmb200_create(int64_t max_particles, int32_t nfields, int32_t float_bit
     vpmb200_engine* e = new (std::nothrow) vpmb200_engine();
     if (!e) return VPMB200_EINVAL;
     e->device = device;
+    e->sm_count = prop.multiProcessorCount;
     e->float_bits = float_bits;
     e->maxp = max_particles;
     e->ld = round_up(max_particles, 256);
@@ -406,6 +469,7 @@ int32_t vpmb200_destroy(vpmb200_handle e) {
     cudaFree(e->z_table);
     cudaFree(e->gh_table_f32);
     cudaFree(e->probe);
+    cudaFree(e->partial);
     cudaFree(e->counter);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;

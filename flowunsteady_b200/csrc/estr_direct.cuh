@@ -75,7 +75,16 @@ __global__ void __launch_bounds__(UJ_BT, 2)
 estr_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* __restrict__ tx,
                        const double* __restrict__ ty, const double* __restrict__ tz, int64_t nt,
                        const double* __restrict__ Jt, int64_t ldj, int transposed, double* __restrict__ SFS,
-                       int64_t ldo, const double* __restrict__ z_table) {
+                       int64_t ldo, const double* __restrict__ z_table, SplitArgs split) {
+    int accumulate = 1;
+    if (split.partial != nullptr) {
+        const int t0 = blockIdx.y * split.tiles_per_chunk;
+        srec += (size_t)t0 * TILE_DOUBLES;
+        ntiles = min(ntiles - t0, split.tiles_per_chunk);
+        SFS = split.partial + (size_t)blockIdx.y * 3 * split.ldp;
+        ldo = split.ldp;
+        accumulate = 0;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem& sm = *reinterpret_cast<PairSmem*>(smem_raw);
     double* ztab = reinterpret_cast<double*>(smem_raw + sizeof(PairSmem));
@@ -135,9 +144,9 @@ estr_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double
             e1 = Jp[1] * tot.a0 + Jp[4] * tot.a1 + Jp[7] * tot.a2;
             e2 = Jp[2] * tot.a0 + Jp[5] * tot.a1 + Jp[8] * tot.a2;
         }
-        SFS[0 * ldo + i] += e0 - tot.b0;
-        SFS[1 * ldo + i] += e1 - tot.b1;
-        SFS[2 * ldo + i] += e2 - tot.b2;
+        SFS[0 * ldo + i] = (accumulate ? SFS[0 * ldo + i] : 0.0) + (e0 - tot.b0);
+        SFS[1 * ldo + i] = (accumulate ? SFS[1 * ldo + i] : 0.0) + (e1 - tot.b1);
+        SFS[2 * ldo + i] = (accumulate ? SFS[2 * ldo + i] : 0.0) + (e2 - tot.b2);
     }
 }
 

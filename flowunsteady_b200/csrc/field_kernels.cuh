@@ -192,6 +192,21 @@ pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, 
     write_tile_header(tile + TILE_HDR, real, x, y, z, rfar2, (int)(nreal > TILE_SRC ? TILE_SRC : nreal));
 }
 
+// Sum the per-chunk partial rows of a source-split pair launch in chunk order.  partial row (c * ncomp + k) holds
+// component k of chunk c; component k < nfirst goes to dstA[k * ldo + i], the rest to dstB[(k - nfirst) * ldo + i].
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nchunks, int ncomp, int64_t ldp, int64_t n,
+                                       double* __restrict__ dstA, double* __restrict__ dstB, int nfirst, int64_t ldo,
+                                       int accumulate) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < ncomp; ++k) {
+        double* d = k < nfirst ? dstA + (size_t)k * ldo + i : dstB + (size_t)(k - nfirst) * ldo + i;
+        double acc = accumulate ? *d : 0.0;
+        for (int c = 0; c < nchunks; ++c) acc += partial[((size_t)c * ncomp + k) * ldp + i];
+        *d = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Per-particle stages.  `P(f)` addresses row f of this thread's particle.
 // ------------------------------------------------------------------------------------------------------------

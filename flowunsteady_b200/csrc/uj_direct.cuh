@@ -285,13 +285,33 @@ constexpr size_t uj_smem_bytes(int kernel) {
     return sizeof(PairSmem) + (kernel == K_GAUSSIANERF ? sizeof(double) * 2 * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0);
 }
 
-// Grid: ceil(nt / UJ_BT) CTAs.  srec: ntiles tiles of TILE_DOUBLES doubles (records + header, common.cuh).
+// Source-split launch geometry: when there are too few target blocks to fill the GPU for many waves (small N, or a
+// rank's shard of a multi-GPU run) the source tiles are split into `nchunks` ranges and the grid becomes
+// (target blocks) x (chunks); chunk c writes its partial U, J into rows [12 c, 12 c + 12) of `partial` (row length ldp)
+// and reduce_partials_kernel sums the chunks in a fixed order (deterministic, unlike atomics).
+struct SplitArgs {
+    double* partial;       // nullptr: single chunk, write U/J directly
+    int64_t ldp;
+    int tiles_per_chunk;
+};
+
+// Grid: (ceil(nt / UJ_BT), nchunks) CTAs.  srec: ntiles tiles of TILE_DOUBLES doubles (records + header, common.cuh).
 // Targets: positions tx/ty/tz (nt each).  Outputs: component k of U at U[k * ldo + i], of J at J[k * ldo + i].
 template <int KERNEL>
 __global__ void __launch_bounds__(UJ_BT, 2)
 uj_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* __restrict__ tx,
                      const double* __restrict__ ty, const double* __restrict__ tz, int64_t nt, double* __restrict__ U,
-                     double* __restrict__ J, int64_t ldo, int accumulate, const double* __restrict__ gh_table) {
+                     double* __restrict__ J, int64_t ldo, int accumulate, const double* __restrict__ gh_table,
+                     SplitArgs split) {
+    if (split.partial != nullptr) {
+        const int t0 = blockIdx.y * split.tiles_per_chunk;
+        srec += (size_t)t0 * TILE_DOUBLES;
+        ntiles = min(ntiles - t0, split.tiles_per_chunk);
+        U = split.partial + (size_t)blockIdx.y * 12 * split.ldp;
+        J = U + 3 * split.ldp;
+        ldo = split.ldp;
+        accumulate = 0;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem& sm = *reinterpret_cast<PairSmem*>(smem_raw);
     double2* tab = reinterpret_cast<double2*>(smem_raw + sizeof(PairSmem));

@@ -110,7 +110,17 @@ template <int KERNEL>
 __global__ void __launch_bounds__(UJ_BT, 2)
 uj_direct_f32_kernel(const double* __restrict__ srec, int ntiles, const double* __restrict__ tx,
                      const double* __restrict__ ty, const double* __restrict__ tz, int64_t nt, double* __restrict__ U,
-                     double* __restrict__ J, int64_t ldo, int accumulate, const float* __restrict__ gh_table) {
+                     double* __restrict__ J, int64_t ldo, int accumulate, const float* __restrict__ gh_table,
+                     SplitArgs split) {
+    if (split.partial != nullptr) {
+        const int t0 = blockIdx.y * split.tiles_per_chunk;
+        srec += (size_t)t0 * TILE_DOUBLES;
+        ntiles = min(ntiles - t0, split.tiles_per_chunk);
+        U = split.partial + (size_t)blockIdx.y * 12 * split.ldp;
+        J = U + 3 * split.ldp;
+        ldo = split.ldp;
+        accumulate = 0;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairSmem32& sm = *reinterpret_cast<PairSmem32*>(smem_raw);
     float2* tab = reinterpret_cast<float2*>(smem_raw + sizeof(PairSmem32));
