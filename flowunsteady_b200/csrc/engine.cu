@@ -14,6 +14,7 @@
 #include "../../include/vpmb200.h"
 #include "estr_direct.cuh"
 #include "field_kernels.cuh"
+#include "fmm_host.cuh"
 #include "uj_direct.cuh"
 #include "uj_direct_f32.cuh"
 
@@ -38,6 +39,8 @@ struct vpmb200_engine {
     unsigned long long* counter = nullptr;
     double t = 0.0;
     int64_t nt = 0;
+    FmmWorkspace fmm;           // GPU FMM scratch (allocated on first UJ_fmm call)
+    std::vector<int> fmm_lvl;   // cell index range of every tree level
     uint64_t launches = 0;      // kernels enqueued by this handle (bench.py's gpu_launches)
     vpmb200_schemes sch;
     std::string err;
@@ -235,9 +238,46 @@ int32_t uj_local_from(vpmb200_engine* e, const double* rec, int64_t ntiles_, int
     return VPMB200_OK;
 }
 
-// pfield.UJ(pfield; reset, reset_sfs, sfs) on the direct path
+// pfield.UJ(pfield; ...) through the GPU FMM (fmm.cuh): U, J [and the near-field E_str] of every particle
+int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
+    const vpmb200_schemes& s = e->sch;
+    if (s.fmm_p < 2 || s.fmm_p > 6) return fail(e, VPMB200_ENOTSUP, "FMM expansion order p must be in 2..6");
+    if (s.fmm_ncrit < 1 || s.fmm_ncrit > FMM_MAX_NCRIT) return fail(e, VPMB200_EINVAL, "FMM ncrit must be in 1..256");
+    if (!(s.fmm_theta > 0.0 && s.fmm_theta < 1.0)) return fail(e, VPMB200_EINVAL, "FMM theta must be in (0, 1)");
+    if (e->float_bits != 64) return fail(e, VPMB200_ENOTSUP, "UJ_fmm runs in FP64 only");
+    if (e->np > 2000000000LL) return fail(e, VPMB200_ECAPACITY, "UJ_fmm indexes particles with 32-bit integers");
+    int32_t rc;
+    if (reset && (rc = zero_rows(e, F_PSE, 3))) return rc;
+    if (reset_sfs && (rc = zero_rows(e, F_SFS, 3))) return rc;
+    if (e->np <= 0) return VPMB200_OK;
+    std::string err;
+    if (fmm_reserve(e->fmm, e->np, s.fmm_ncrit, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    FmmWorkspace& w = e->fmm;
+    cudaError_t st = fmm_build(w, e->state, e->ld, e->np, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream, e->launches, err);
+    if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
+    const int block = std::min(256, std::max(32, (s.fmm_ncrit + 31) / 32 * 32));
+    CU_TRY(e, fmm_evaluate(w, s.fmm_p, s.kernel, block, e->gh_table, e->fmm_lvl, e->stream, e->launches));
+    const unsigned nb = blocks_for(e->np, PK_BT);
+    fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sU, w.lds, 3, e->np, w.perm, e->state + (size_t)F_U * e->ld, e->ld, reset ? 0 : 1);
+    fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sJ, w.lds, 9, e->np, w.perm, e->state + (size_t)F_J * e->ld, e->ld, reset ? 0 : 1);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 2;
+    if (sfs) {
+        fmm_gather_estr_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, w.perm, w.sJ, w.lds, s.transposed,
+                                                          zeta0_of(s.kernel), w.rec);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        CU_TRY(e, fmm_estr(w, s.kernel, block, s.transposed, e->z_table, e->stream, e->launches));
+        fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sE, w.lds, 3, e->np, w.perm, e->state + (size_t)F_SFS * e->ld, e->ld, 1);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
+    return VPMB200_OK;
+}
+
+// pfield.UJ(pfield; reset, reset_sfs, sfs)
 int32_t do_uj(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
-    if (e->sch.uj != VPMB200_UJ_DIRECT) return fail(e, VPMB200_ENOTSUP, "UJ_fmm is not built in this round; use uj = direct");
+    if (e->sch.uj == VPMB200_UJ_FMM) return do_uj_fmm(e, reset, reset_sfs, sfs);
     int32_t rc;
     if (reset && (rc = zero_rows(e, F_PSE, 3))) return rc;
     if (reset_sfs && (rc = zero_rows(e, F_SFS, 3))) return rc;
@@ -471,6 +511,7 @@ int32_t vpmb200_destroy(vpmb200_handle e) {
     cudaFree(e->probe);
     cudaFree(e->partial);
     cudaFree(e->counter);
+    fmm_free(e->fmm);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return VPMB200_OK;
@@ -611,8 +652,7 @@ int32_t vpmb200_uj_probe(vpmb200_handle e, const double* X, int64_t m, double* U
     if (m < 0) return fail(e, VPMB200_EINVAL, "m < 0");
     if (m == 0) return VPMB200_OK;
     if (!X || !U) return fail(e, VPMB200_EINVAL, "X or U is NULL");
-    if (e->sch.uj != VPMB200_UJ_DIRECT) return fail(e, VPMB200_ENOTSUP, "UJ_fmm is not built in this round");
-    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaSetDevice(e->device));   // probes always use the direct kernel: m targets x np sources
     int32_t rc = ensure_probe(e, m);
     if (rc) return rc;
     const int64_t pl = e->probe_cap;
@@ -704,6 +744,17 @@ int32_t vpmb200_stream(vpmb200_handle e, void** stream) {
     CHECK_HANDLE(e);
     if (!stream) return fail(e, VPMB200_EINVAL, "stream is NULL");
     *stream = (void*)e->stream;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_fmm_stats(vpmb200_handle e, int64_t* stats) {
+    CHECK_HANDLE(e);
+    if (!stats) return fail(e, VPMB200_EINVAL, "stats is NULL");
+    stats[0] = e->fmm.ncells;
+    stats[1] = e->fmm.nleaves;
+    stats[2] = e->fmm.nlevels;
+    stats[3] = e->fmm.n_m2l;
+    stats[4] = e->fmm.n_p2p;
     return VPMB200_OK;
 }
 

@@ -1,0 +1,597 @@
+// fmm.cuh — K3: GPU fast multipole evaluation of U and J (FLOWVPM's UJ_fmm, selected by `vpm_UJ = vpm.UJ_fmm` with
+// settings `vpm.FMM(; p=4, ncrit=50, theta=0.4, nonzero_sigma=false)`, /root/reference/src/FLOWUnsteady_simulation.jl:38,43;
+// the reference delegates to ExaFMM (C++/OpenMP, README.md:115-116) or FastMultipole.jl, neither of which is in
+// the tree — SURVEY.md §0.4).  What is matched is the ALGORITHM CLASS and its parameters, not bits:
+//   * adaptive octree over Morton-sorted particles, leaves hold <= ncrit particles;
+//   * well-separated test (R_i + R_j) < theta |c_i - c_j| with R the cell's half side (ExaFMM's convention);
+//   * far field: singular (1/r) kernel of the vector potential psi = (1/4 pi) sum Gamma/r  (`nonzero_sigma = false`),
+//     Cartesian Taylor expansions with multipoles to order p-1 and locals to order p+1, U = curl psi and J = grad U taken
+//     analytically from the local expansion (the reference obtains J by complex-step differentiation, rvpm.md:370);
+//   * near field: the regularised pair kernel of uj_direct.cuh (same device functions) over leaf pairs;
+//   * E_str (`sfs = true`): a second near-field pass over the same leaf pairs (Estr_fmm evaluates the SFS term in the
+//     near field only).
+// Everything runs on the device; the host only reads back a few counters per tree level / traversal sweep.
+// Deterministic: child order, pair lists (sorted by (target, source)) and all reductions have a fixed order.
+#pragma once
+
+#include <cub/cub.cuh>
+
+#include "estr_direct.cuh"
+#include "fmm_ops.inc"
+#include "uj_direct.cuh"
+
+namespace vpm {
+
+constexpr int FMM_MAXLEVEL = 21;      // 3 x 21 = 63-bit Morton keys
+constexpr int FMM_MAX_NCRIT = 256;
+
+struct FmmCell {
+    int start, count;    // particle range in Morton order
+    int parent, child0;  // first child (children are contiguous), -1 for none
+    int nchild, level;
+    double cx, cy, cz, R;  // centre and half side
+    double smax;           // largest core size sigma among the cell's particles (regularisation-aware acceptance)
+    double pad_;
+};
+
+// ---- bounding box -----------------------------------------------------------------------------------------------
+__global__ void fmm_bounds_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                  int64_t n, double* __restrict__ out /* gridDim.x * 6 */) {
+    __shared__ double red[6][8];
+    const double big = 1.0e300;
+    double v[6] = {big, big, big, big, big, big};  // min x, -max x, min y, -max y, min z, -max z
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a = x[i], b = y[i], c = z[i];
+        v[0] = fmin(v[0], a); v[1] = fmin(v[1], -a);
+        v[2] = fmin(v[2], b); v[3] = fmin(v[3], -b);
+        v[4] = fmin(v[4], c); v[5] = fmin(v[5], -c);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[c] = fmin(v[c], __shfl_xor_sync(0xffffffffu, v[c], o));
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 6; ++c) red[c][threadIdx.x >> 5] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double m = red[threadIdx.x][0];
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmin(m, red[threadIdx.x][k]);
+        out[blockIdx.x * 6 + threadIdx.x] = m;
+    }
+}
+
+// ---- Morton keys ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread3(uint64_t v) {  // 21 bits -> every third bit
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void fmm_keys_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                int64_t n, double x0, double y0, double z0, double inv_cell /* 2^21 / side */,
+                                uint64_t* __restrict__ keys, int* __restrict__ perm) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double lim = 2097151.0;
+    uint64_t ix = (uint64_t)fmin(fmax((x[i] - x0) * inv_cell, 0.0), lim);
+    uint64_t iy = (uint64_t)fmin(fmax((y[i] - y0) * inv_cell, 0.0), lim);
+    uint64_t iz = (uint64_t)fmin(fmax((z[i] - z0) * inv_cell, 0.0), lim);
+    keys[i] = (spread3(ix) << 2) | (spread3(iy) << 1) | spread3(iz);
+    perm[i] = (int)i;
+}
+
+// ---- gather into Morton order: target positions + UJ source records (common.cuh layout, no tile headers) -------------
+__global__ void fmm_gather_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, const int* __restrict__ perm,
+                                  double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz,
+                                  double* __restrict__ rec) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = perm[i];
+    double x = soa[(size_t)(F_X + 0) * ld + p], y = soa[(size_t)(F_X + 1) * ld + p], z = soa[(size_t)(F_X + 2) * ld + p];
+    double gx = soa[(size_t)(F_GAMMA + 0) * ld + p], gy = soa[(size_t)(F_GAMMA + 1) * ld + p], gz = soa[(size_t)(F_GAMMA + 2) * ld + p];
+    double sg = soa[(size_t)F_SIGMA * ld + p];
+    double si = 1.0 / sg, si2 = si * si, si3 = si2 * si;
+    sx[i] = x; sy[i] = y; sz[i] = z;
+    double2* r = reinterpret_cast<double2*>(rec + (size_t)i * REC_REALS);
+    r[0] = make_double2(x, y);
+    r[1] = make_double2(z, -CONST4 * gx);
+    r[2] = make_double2(-CONST4 * gy, -CONST4 * gz);
+    r[3] = make_double2(VPM_GT_TFAR * (sg * sg), si3);
+    r[4] = make_double2(si3 * si2, si2);
+}
+
+// E_str records in Morton order (estr_direct.cuh layout).  J is the field's CURRENT J (state rows, particle order), which
+// is also copied into Morton order (sJ) for the targets of the second pass.
+__global__ void fmm_gather_estr_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, const int* __restrict__ perm,
+                                       double* __restrict__ sJ, int64_t ldj, int transposed, double zeta_norm,
+                                       double* __restrict__ rec) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = perm[i];
+    double x = soa[(size_t)(F_X + 0) * ld + p], y = soa[(size_t)(F_X + 1) * ld + p], z = soa[(size_t)(F_X + 2) * ld + p];
+    double g0 = soa[(size_t)(F_GAMMA + 0) * ld + p], g1 = soa[(size_t)(F_GAMMA + 1) * ld + p], g2 = soa[(size_t)(F_GAMMA + 2) * ld + p];
+    double sg = soa[(size_t)F_SIGMA * ld + p];
+    double Jq[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        Jq[c] = soa[(size_t)(F_J + c) * ld + p];
+        sJ[(size_t)c * ldj + i] = Jq[c];
+    }
+    double v0, v1, v2;
+    if (transposed) {
+        v0 = Jq[0] * g0 + Jq[1] * g1 + Jq[2] * g2;
+        v1 = Jq[3] * g0 + Jq[4] * g1 + Jq[5] * g2;
+        v2 = Jq[6] * g0 + Jq[7] * g1 + Jq[8] * g2;
+    } else {
+        v0 = Jq[0] * g0 + Jq[3] * g1 + Jq[6] * g2;
+        v1 = Jq[1] * g0 + Jq[4] * g1 + Jq[7] * g2;
+        v2 = Jq[2] * g0 + Jq[5] * g1 + Jq[8] * g2;
+    }
+    double si = 1.0 / sg, si2 = si * si;
+    double c = zeta_norm * (si2 * si);
+    double2* r = reinterpret_cast<double2*>(rec + (size_t)i * REC_REALS);
+    r[0] = make_double2(x, y);
+    r[1] = make_double2(z, si2);
+    r[2] = make_double2(c * g0, c * g1);
+    r[3] = make_double2(c * g2, c * v0);
+    r[4] = make_double2(c * v1, c * v2);
+}
+
+// ---- tree build: one level at a time -------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_key(const uint64_t* __restrict__ keys, int lo, int hi, uint64_t v) {
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// For each cell of the level: number of non-empty children (0 if the cell is a leaf).
+__global__ void fmm_split_count_kernel(const FmmCell* __restrict__ cells, int c0, int c1, const uint64_t* __restrict__ keys,
+                                       int ncrit, int* __restrict__ nchild) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const FmmCell cell = cells[c];
+    int nc = 0;
+    if (cell.count > ncrit && cell.level < FMM_MAXLEVEL) {
+        const int shift = 3 * (FMM_MAXLEVEL - cell.level - 1);
+        const uint64_t prefix = (keys[cell.start] >> (shift + 3)) << 3;
+        int lo = cell.start;
+        for (int o = 0; o < 8; ++o) {
+            int hi = o == 7 ? cell.start + cell.count
+                            : lower_bound_key(keys, lo, cell.start + cell.count, (prefix | (uint64_t)(o + 1)) << shift);
+            nc += hi > lo;
+            lo = hi;
+        }
+    }
+    nchild[c - c0] = nc;
+}
+
+__global__ void fmm_split_emit_kernel(FmmCell* __restrict__ cells, int c0, int c1, const uint64_t* __restrict__ keys,
+                                      int ncrit, const int* __restrict__ child_off, int next0) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    FmmCell cell = cells[c];
+    if (!(cell.count > ncrit && cell.level < FMM_MAXLEVEL)) {
+        cells[c].child0 = -1;
+        cells[c].nchild = 0;
+        return;
+    }
+    const int shift = 3 * (FMM_MAXLEVEL - cell.level - 1);
+    const uint64_t prefix = (keys[cell.start] >> (shift + 3)) << 3;
+    int lo = cell.start, k = 0;
+    const int base = next0 + child_off[c - c0];
+    const double h = 0.5 * cell.R;
+    for (int o = 0; o < 8; ++o) {
+        int hi = o == 7 ? cell.start + cell.count
+                        : lower_bound_key(keys, lo, cell.start + cell.count, (prefix | (uint64_t)(o + 1)) << shift);
+        if (hi > lo) {
+            FmmCell ch;
+            ch.start = lo;
+            ch.count = hi - lo;
+            ch.parent = c;
+            ch.child0 = -1;
+            ch.nchild = 0;
+            ch.level = cell.level + 1;
+            ch.cx = cell.cx + ((o & 4) ? h : -h);   // key bit order: x, y, z (fmm_keys_kernel)
+            ch.cy = cell.cy + ((o & 2) ? h : -h);
+            ch.cz = cell.cz + ((o & 1) ? h : -h);
+            ch.R = h;
+            ch.smax = 0.0;
+            ch.pad_ = 0.0;
+            cells[base + k] = ch;
+            ++k;
+        }
+        lo = hi;
+    }
+    cells[c].child0 = base;
+    cells[c].nchild = k;
+}
+
+// ---- upward pass -----------------------------------------------------------------------------------------------------
+// Multipoles: M[(cell * 3 + comp) * NM + a].  One warp per leaf, fixed-order shuffle reduction.
+template <int P>
+__global__ void fmm_p2m_kernel(const FmmCell* __restrict__ cells, int ncells, const double* __restrict__ rec,
+                               double* __restrict__ M) {
+    using Ops = FmmOps<P>;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= ncells) return;
+    const FmmCell cell = cells[c];
+    if (cell.nchild != 0) return;
+    const int lane = threadIdx.x & 31;
+    double m0[Ops::NM], m1[Ops::NM], m2[Ops::NM];
+#pragma unroll
+    for (int a = 0; a < Ops::NM; ++a) m0[a] = m1[a] = m2[a] = 0.0;
+    for (int s = lane; s < cell.count; s += 32) {
+        const double* r = rec + (size_t)(cell.start + s) * REC_REALS;
+        // record holds G' = -Gamma/(4 pi): expand psi = sum (Gamma/4pi)/r  ->  charges q = -G'
+        Ops::p2m(r[0] - cell.cx, r[1] - cell.cy, r[2] - cell.cz, -r[3], -r[4], -r[5], m0, m1, m2);
+    }
+#pragma unroll
+    for (int a = 0; a < Ops::NM; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m0[a] += __shfl_xor_sync(0xffffffffu, m0[a], o);
+            m1[a] += __shfl_xor_sync(0xffffffffu, m1[a], o);
+            m2[a] += __shfl_xor_sync(0xffffffffu, m2[a], o);
+        }
+    }
+    if (lane == 0) {
+        double* out = M + (size_t)c * 3 * Ops::NM;
+#pragma unroll
+        for (int a = 0; a < Ops::NM; ++a) {
+            out[a] = m0[a];
+            out[Ops::NM + a] = m1[a];
+            out[2 * Ops::NM + a] = m2[a];
+        }
+    }
+}
+
+// smax of the leaves (one thread per cell; record slot 9 holds 1/sigma^2) and of the inner cells of one level.
+__global__ void fmm_smax_leaf_kernel(FmmCell* __restrict__ cells, int ncells, const double* __restrict__ rec) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const FmmCell cell = cells[c];
+    if (cell.nchild != 0) return;
+    double m = 1.0e300;  // min of 1/sigma^2
+    for (int s = 0; s < cell.count; ++s) m = fmin(m, rec[(size_t)(cell.start + s) * REC_REALS + 9]);
+    cells[c].smax = rsqrt(m);
+}
+__global__ void fmm_smax_up_kernel(FmmCell* __restrict__ cells, int c0, int c1) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const FmmCell cell = cells[c];
+    if (cell.nchild == 0) return;
+    double m = 0.0;
+    for (int k = 0; k < cell.nchild; ++k) m = fmax(m, cells[cell.child0 + k].smax);
+    cells[c].smax = m;
+}
+
+// One thread per (cell of the level, component): gather the children in order.
+template <int P>
+__global__ void fmm_m2m_kernel(const FmmCell* __restrict__ cells, int c0, int c1, double* __restrict__ M) {
+    using Ops = FmmOps<P>;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = c0 + t / 3, comp = t % 3;
+    if (c >= c1) return;
+    const FmmCell cell = cells[c];
+    if (cell.nchild == 0) return;
+    double mp[Ops::NM];
+#pragma unroll
+    for (int a = 0; a < Ops::NM; ++a) mp[a] = 0.0;
+    for (int k = 0; k < cell.nchild; ++k) {
+        const FmmCell ch = cells[cell.child0 + k];
+        double mc[Ops::NM];
+        const double* src = M + ((size_t)(cell.child0 + k) * 3 + comp) * Ops::NM;
+#pragma unroll
+        for (int a = 0; a < Ops::NM; ++a) mc[a] = src[a];
+        Ops::m2m(ch.cx - cell.cx, ch.cy - cell.cy, ch.cz - cell.cz, mc, mp);
+    }
+    double* dst = M + ((size_t)c * 3 + comp) * Ops::NM;
+#pragma unroll
+    for (int a = 0; a < Ops::NM; ++a) dst[a] = mp[a];
+}
+
+// ---- dual tree traversal (breadth-first over (target, source) cell pairs) ---------------------------------------------
+struct FmmCounters {
+    unsigned int next, m2l, p2p, overflow;
+};
+
+__device__ __forceinline__ void push_pair(uint64_t* __restrict__ list, unsigned int* __restrict__ counter, unsigned int cap,
+                                          unsigned int* __restrict__ overflow, int a, int b) {
+    unsigned int k = atomicAdd(counter, 1u);
+    if (k < cap) list[k] = ((uint64_t)(unsigned int)a << 32) | (unsigned int)b; else atomicExch(overflow, 1u);
+}
+
+// Pairs are 64-bit keys (target << 32 | source) so the M2L / P2P lists sort by (target, source) without repacking.
+__global__ void fmm_traverse_kernel(const FmmCell* __restrict__ cells, const uint64_t* __restrict__ frontier, unsigned int nfront,
+                                    double theta, double nzs_factor, uint64_t* __restrict__ next, unsigned int cap_next, uint64_t* __restrict__ m2l,
+                                    unsigned int cap_m2l, uint64_t* __restrict__ p2p, unsigned int cap_p2p,
+                                    FmmCounters* __restrict__ cnt) {
+    unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nfront) return;
+    const int pi = (int)(frontier[t] >> 32), pj = (int)(frontier[t] & 0xffffffffu);
+    const FmmCell ci = cells[pi], cj = cells[pj];
+    const double dx = ci.cx - cj.cx, dy = ci.cy - cj.cy, dz = ci.cz - cj.cz;
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    const double rs = ci.R + cj.R;
+    // well separated (ExaFMM's multipole acceptance criterion); with nonzero_sigma the closest possible pair of points
+    // must also be nzs_factor core sizes apart, so the singular far field is never used where g(r/sigma) != 1
+    bool well = rs * rs < theta * theta * d2;
+    if (well && nzs_factor > 0.0) well = sqrt(d2) - 1.7320508075688772 * rs > nzs_factor * cj.smax;
+    if (well) {
+        push_pair(m2l, &cnt->m2l, cap_m2l, &cnt->overflow, pi, pj);
+    } else if (ci.nchild == 0 && cj.nchild == 0) {
+        push_pair(p2p, &cnt->p2p, cap_p2p, &cnt->overflow, pi, cj.start);   // low word: first particle of the source leaf
+    } else if (cj.nchild == 0 || (ci.nchild != 0 && ci.R >= cj.R)) {
+        for (int k = 0; k < ci.nchild; ++k) push_pair(next, &cnt->next, cap_next, &cnt->overflow, ci.child0 + k, pj);
+    } else {
+        for (int k = 0; k < cj.nchild; ++k) push_pair(next, &cnt->next, cap_next, &cnt->overflow, pi, cj.child0 + k);
+    }
+}
+
+// off[c] = first index whose target is >= c (list sorted by (target, source)); off[ncells] = n
+__global__ void fmm_list_offsets_kernel(const uint64_t* __restrict__ keys, unsigned int n, int ncells, unsigned int* __restrict__ off) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncells) return;
+    unsigned int lo = 0, hi = n;
+    const uint64_t v = (uint64_t)(unsigned int)c << 32;
+    while (lo < hi) {
+        unsigned int mid = (lo + hi) >> 1;
+        if (keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    off[c] = lo;
+}
+
+// ---- M2L: one warp per target cell; lane l takes sources l, l+32, ... of the cell's (sorted) list with private
+//      accumulators in shared memory, then a fixed-order cross-lane sum.  L[(cell * 3 + comp) * NL + b].
+template <int P>
+__global__ void __launch_bounds__(32)
+fmm_m2l_kernel(const FmmCell* __restrict__ cells, int ncells, const uint64_t* __restrict__ keys,
+               const unsigned int* __restrict__ off, const double* __restrict__ M, double* __restrict__ L) {
+    using Ops = FmmOps<P>;
+    extern __shared__ double sacc[];  // [3 * NL][32]  (coefficient-major: conflict-free per-lane columns)
+    const int c = blockIdx.x;
+    const unsigned int b0 = off[c], b1 = off[c + 1];
+    if (b0 == b1) return;
+    const int lane = threadIdx.x;
+    for (int k = 0; k < 3 * Ops::NL; ++k) sacc[k * 32 + lane] = 0.0;
+    const FmmCell ci = cells[c];
+    for (unsigned int k = b0 + lane; k < b1; k += 32) {
+        const int j = (int)(keys[k] & 0xffffffffu);
+        const FmmCell cj = cells[j];
+        double D[Ops::NL];
+        Ops::dtensor(ci.cx - cj.cx, ci.cy - cj.cy, ci.cz - cj.cz, D);
+#pragma unroll 1
+        for (int comp = 0; comp < 3; ++comp) {
+            double m[Ops::NM];
+            const double* src = M + ((size_t)j * 3 + comp) * Ops::NM;
+#pragma unroll
+            for (int a = 0; a < Ops::NM; ++a) m[a] = src[a];
+            Ops::template m2l<32>(D, m, sacc + comp * Ops::NL * 32 + lane);   // this lane's private column
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < 3 * Ops::NL; k += 32) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) s += sacc[k * 32 + l];
+        L[(size_t)c * 3 * Ops::NL + k] = s;
+    }
+}
+
+// One thread per (cell of the level, component): add the parent's shifted expansion.
+template <int P>
+__global__ void fmm_l2l_kernel(const FmmCell* __restrict__ cells, int c0, int c1, double* __restrict__ L) {
+    using Ops = FmmOps<P>;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = c0 + t / 3, comp = t % 3;
+    if (c >= c1) return;
+    const FmmCell cell = cells[c];
+    if (cell.parent < 0) return;
+    const FmmCell par = cells[cell.parent];
+    const double* src = L + ((size_t)cell.parent * 3 + comp) * Ops::NL;
+    double* dst = L + ((size_t)c * 3 + comp) * Ops::NL;
+    Ops::l2l(cell.cx - par.cx, cell.cy - par.cy, cell.cz - par.cz, src, dst);
+}
+
+// ---- near field --------------------------------------------------------------------------------------------------
+// P2P list entries are (target leaf cell << 32 | first particle of the source leaf), sorted; `runs` gives every entry's
+// particle range.  Because the low word is a position in Morton order, consecutive entries are often adjacent ranges.
+__global__ void fmm_leaf_counts_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves,
+                                       int* __restrict__ count_at) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nleaves) {
+        const FmmCell c = cells[leaves[k]];
+        count_at[c.start] = c.count;
+    }
+}
+__global__ void fmm_p2p_runs_kernel(const uint64_t* __restrict__ keys, unsigned int n, const int* __restrict__ count_at,
+                                    int2* __restrict__ runs) {
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        const int start = (int)(keys[k] & 0xffffffffu);
+        runs[k] = make_int2(start, count_at[start]);
+    }
+}
+
+constexpr int LEAF_WARPS = 8;     // leaves per CTA (one warp each)
+constexpr int LEAF_BATCH = 64;    // source records staged per warp and pass (5 KB)
+
+// Stage up to LEAF_BATCH source records of the run list [k, b1) into this warp's shared-memory slice.  (run, off) is
+// the cursor: `off` records of run k are already consumed.  Returns the number of records staged.
+__device__ __forceinline__ int stage_batch(const int2* __restrict__ runs, unsigned int& k, unsigned int b1, int& off,
+                                           const double* __restrict__ rec, double* __restrict__ slice, int lane) {
+    int n = 0;
+    while (k < b1 && n < LEAF_BATCH) {
+        const int2 r = runs[k];
+        const int take = min(r.y - off, LEAF_BATCH - n);
+        const double2* g2 = reinterpret_cast<const double2*>(rec + (size_t)(r.x + off) * REC_REALS);
+        double2* s2 = reinterpret_cast<double2*>(slice + (size_t)n * REC_REALS);
+        for (int q = lane; q < take * (REC_REALS / 2); q += 32) s2[q] = g2[q];
+        n += take;
+        off += take;
+        if (off == r.y) { ++k; off = 0; }
+    }
+    return n;
+}
+
+// L2P + near-field P2P: one warp per leaf, one target per lane (leaves with more than 32 particles take several passes).
+// Outputs in Morton order: sU[k * lds + i], sJ[k * lds + i].
+template <int KERNEL, int P>
+__global__ void __launch_bounds__(32 * LEAF_WARPS)
+fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves,
+                   const int2* __restrict__ runs, const unsigned int* __restrict__ p2p_off, const double* __restrict__ rec,
+                   const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
+                   const double* __restrict__ L, const double* __restrict__ gh_table, double* __restrict__ sU,
+                   double* __restrict__ sJ, int64_t lds) {
+    using Ops = FmmOps<P>;
+    extern __shared__ __align__(16) double smem[];  // per warp: [3 * NL (padded even)] local expansion + [LEAF_BATCH * 10] records
+    constexpr int LPAD = (3 * Ops::NL + 1) & ~1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sL = smem + (size_t)warp * (LPAD + LEAF_BATCH * REC_REALS);
+    double* slice = sL + LPAD;
+    const int leaf = blockIdx.x * LEAF_WARPS + warp;
+    if (leaf >= nleaves) return;   // whole warp exits together
+    const int c = leaves[leaf];
+    const FmmCell cell = cells[c];
+    for (int k = lane; k < 3 * Ops::NL; k += 32) sL[k] = L[(size_t)c * 3 * Ops::NL + k];
+    __syncwarp();
+    const double2* tab = reinterpret_cast<const double2*>(gh_table);  // read through L1 (23 KB, hot)
+    const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
+
+    for (int t0 = 0; t0 < cell.count; t0 += 32) {
+        const bool live = t0 + lane < cell.count;
+        const int i = cell.start + (live ? t0 + lane : 0);
+        const double px = sx[i], py = sy[i], pz = sz[i];
+        UJAcc a;
+        acc_zero(a);
+        {   // far field: psi_n = local expansion n; U = curl psi, J = grad U
+            double g[3][3], h[3][6];
+#pragma unroll
+            for (int n = 0; n < 3; ++n) Ops::l2p(px - cell.cx, py - cell.cy, pz - cell.cz, sL + n * Ops::NL, g[n], h[n]);
+            a.u0 = g[2][1] - g[1][2];   // U_k = eps_kmn d_m psi_n
+            a.u1 = g[0][2] - g[2][0];
+            a.u2 = g[1][0] - g[0][1];
+            // J[k + 3 l] = d_l U_k = eps_kmn d_l d_m psi_n ; h index: xx 0, xy 1, xz 2, yy 3, yz 4, zz 5
+            a.j0 = h[2][1] - h[1][2]; a.j1 = h[0][2] - h[2][0]; a.j2 = h[1][0] - h[0][1];   // l = x: (xx, xy, xz) = 0, 1, 2
+            a.j3 = h[2][3] - h[1][4]; a.j4 = h[0][4] - h[2][1]; a.j5 = h[1][1] - h[0][3];   // l = y: (yx, yy, yz) = 1, 3, 4
+            a.j6 = h[2][4] - h[1][5]; a.j7 = h[0][5] - h[2][2]; a.j8 = h[1][2] - h[0][4];   // l = z: (zx, zy, zz) = 2, 4, 5
+        }
+        unsigned int k = b0;
+        int off = 0;
+        while (k < b1) {
+            __syncwarp();
+            const int ns = stage_batch(runs, k, b1, off, rec, slice, lane);
+            __syncwarp();
+            const double2* r2p = reinterpret_cast<const double2*>(slice);
+#pragma unroll 2
+            for (int s = 0; s < ns; ++s) {
+                const double2* r = r2p + s * (REC_REALS / 2);
+                const SrcCore sc = load_core(r);
+                double dx = px - sc.x, dy = py - sc.y, dz = pz - sc.z;
+                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                if (KERNEL == K_SINGULAR) {
+                    const bool nz = nonzero_f64(r2);
+                    double A, B;
+                    ab_singular(nz ? r2 : 1.0, A, B);
+                    uj_accumulate(a, dx, dy, dz, sc.gx, sc.gy, sc.gz, nz ? A : 0.0, B);
+                } else {
+                    uj_pair_general<KERNEL>(a, dx, dy, dz, r2, sc, r, tab);
+                }
+            }
+        }
+        if (live) {
+            a.j1 -= a.w2; a.j2 += a.w1;
+            a.j3 += a.w2; a.j5 -= a.w0;
+            a.j6 -= a.w1; a.j7 += a.w0;
+            double o[12] = {a.u0, a.u1, a.u2, a.j0, a.j1, a.j2, a.j3, a.j4, a.j5, a.j6, a.j7, a.j8};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) sU[(size_t)q * lds + i] = o[q];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) sJ[(size_t)q * lds + i] = o[3 + q];
+        }
+    }
+}
+
+// Near-field E_str over the same leaf pairs (second pass; needs the converged J of targets and sources).
+template <int KERNEL>
+__global__ void __launch_bounds__(32 * LEAF_WARPS)
+fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves,
+                     const int2* __restrict__ runs, const unsigned int* __restrict__ p2p_off, const double* __restrict__ rec,
+                     const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
+                     const double* __restrict__ sJ, int64_t lds, int transposed, const double* __restrict__ z_table,
+                     double* __restrict__ sE) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* slice = smem + (size_t)warp * (LEAF_BATCH * REC_REALS);
+    const int leaf = blockIdx.x * LEAF_WARPS + warp;
+    if (leaf >= nleaves) return;
+    const int c = leaves[leaf];
+    const FmmCell cell = cells[c];
+    const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
+    for (int t0 = 0; t0 < cell.count; t0 += 32) {
+        const bool live = t0 + lane < cell.count;
+        const int i = cell.start + (live ? t0 + lane : 0);
+        const double px = sx[i], py = sy[i], pz = sz[i];
+        EAcc a = {0, 0, 0, 0, 0, 0};
+        unsigned int k = b0;
+        int off = 0;
+        while (k < b1) {
+            __syncwarp();
+            const int ns = stage_batch(runs, k, b1, off, rec, slice, lane);
+            __syncwarp();
+            const double2* r2p = reinterpret_cast<const double2*>(slice);
+#pragma unroll 2
+            for (int s = 0; s < ns; ++s) estr_pair<KERNEL>(a, px, py, pz, r2p + s * (REC_REALS / 2), z_table);
+        }
+        if (live) {
+            double Jp[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) Jp[q] = sJ[(size_t)q * lds + i];
+            double e0, e1, e2;
+            if (transposed) {
+                e0 = Jp[0] * a.a0 + Jp[1] * a.a1 + Jp[2] * a.a2;
+                e1 = Jp[3] * a.a0 + Jp[4] * a.a1 + Jp[5] * a.a2;
+                e2 = Jp[6] * a.a0 + Jp[7] * a.a1 + Jp[8] * a.a2;
+            } else {
+                e0 = Jp[0] * a.a0 + Jp[3] * a.a1 + Jp[6] * a.a2;
+                e1 = Jp[1] * a.a0 + Jp[4] * a.a1 + Jp[7] * a.a2;
+                e2 = Jp[2] * a.a0 + Jp[5] * a.a1 + Jp[8] * a.a2;
+            }
+            sE[0 * lds + i] = e0 - a.b0;
+            sE[1 * lds + i] = e1 - a.b1;
+            sE[2 * lds + i] = e2 - a.b2;
+        }
+    }
+}
+
+// leaves of the tree, in cell order
+__global__ void fmm_mark_leaves_kernel(const FmmCell* __restrict__ cells, int ncells, int* __restrict__ flag) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells) flag[c] = cells[c].nchild == 0 ? 1 : 0;
+}
+__global__ void fmm_collect_leaves_kernel(const int* __restrict__ flag, const int* __restrict__ pos, int ncells,
+                                          int* __restrict__ leaves) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells && flag[c]) leaves[pos[c]] = c;
+}
+
+// Morton order -> particle order: dst[k * ld + perm[i]] (+)= src[k * lds + i]
+__global__ void fmm_scatter_kernel(const double* __restrict__ src, int64_t lds, int nrows, int64_t n, const int* __restrict__ perm,
+                                   double* __restrict__ dst, int64_t ld, int accumulate) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = perm[i];
+    for (int k = 0; k < nrows; ++k) {
+        double* d = dst + (size_t)k * ld + p;
+        const double v = src[(size_t)k * lds + i];
+        *d = accumulate ? *d + v : v;
+    }
+}
+
+}  // namespace vpm

@@ -1,0 +1,374 @@
+// fmm_host.cuh — host orchestration of the GPU FMM (fmm.cuh): workspace, tree build loop, traversal loop, passes.
+#pragma once
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "fmm.cuh"
+
+namespace vpm {
+
+struct FmmWorkspace {
+    int64_t cap_n = 0;
+    int cap_cells = 0;
+    unsigned int cap_pairs = 0, cap_p2p = 0;
+    uint64_t *keys = nullptr, *keys_alt = nullptr;
+    int *perm = nullptr, *perm_alt = nullptr;
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *rec = nullptr;  // Morton-ordered targets / source records
+    double *sU = nullptr, *sJ = nullptr, *sE = nullptr;                   // Morton-ordered outputs (3, 9, 3 rows of lds)
+    int64_t lds = 0;
+    FmmCell* cells = nullptr;
+    int *nchild = nullptr, *child_off = nullptr, *leaf_flag = nullptr, *leaf_pos = nullptr, *leaves = nullptr;
+    double *M = nullptr, *L = nullptr;
+    size_t ml_doubles_M = 0, ml_doubles_L = 0;
+    uint64_t *front_a = nullptr, *front_b = nullptr, *m2l = nullptr, *m2l_sorted = nullptr, *p2p = nullptr, *p2p_sorted = nullptr;
+    unsigned int *m2l_off = nullptr, *p2p_off = nullptr;
+    int2* runs = nullptr;          // particle range of every sorted P2P entry
+    int* count_at = nullptr;       // leaf particle count, indexed by the leaf's first particle
+    FmmCounters* counters = nullptr;
+    double* bounds = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    // statistics of the last evaluation
+    int ncells = 0, nleaves = 0, nlevels = 0;
+    unsigned int n_m2l = 0, n_p2p = 0;
+};
+
+inline void fmm_free(FmmWorkspace& w) {
+    void* ptrs[] = {w.keys, w.keys_alt, w.perm, w.perm_alt, w.sx, w.sy, w.sz, w.rec, w.sU, w.sJ, w.sE, w.cells, w.nchild,
+                    w.child_off, w.leaf_flag, w.leaf_pos, w.leaves, w.M, w.L, w.front_a, w.front_b, w.m2l, w.m2l_sorted,
+                    w.p2p, w.p2p_sorted, w.m2l_off, w.p2p_off, w.counters, w.bounds, w.cub_tmp, w.runs, w.count_at};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    w = FmmWorkspace();
+}
+
+#define FMM_TRY(call)                                        \
+    do {                                                     \
+        cudaError_t _st = (call);                            \
+        if (_st != cudaSuccess) {                            \
+            err = std::string(#call) + ": " + cudaGetErrorString(_st); \
+            return _st;                                      \
+        }                                                    \
+    } while (0)
+
+// (Re)allocate the pair-list buffers for the current cap_pairs / cap_p2p.
+inline cudaError_t fmm_alloc_pairs(FmmWorkspace& w, std::string& err) {
+    void** ptrs[] = {(void**)&w.front_a, (void**)&w.front_b, (void**)&w.m2l, (void**)&w.m2l_sorted, (void**)&w.p2p,
+                     (void**)&w.p2p_sorted, (void**)&w.runs};
+    for (void** p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    FMM_TRY(cudaMalloc(&w.front_a, sizeof(uint64_t) * w.cap_pairs));
+    FMM_TRY(cudaMalloc(&w.front_b, sizeof(uint64_t) * w.cap_pairs));
+    FMM_TRY(cudaMalloc(&w.m2l, sizeof(uint64_t) * w.cap_pairs));
+    FMM_TRY(cudaMalloc(&w.m2l_sorted, sizeof(uint64_t) * w.cap_pairs));
+    FMM_TRY(cudaMalloc(&w.p2p, sizeof(uint64_t) * w.cap_p2p));
+    FMM_TRY(cudaMalloc(&w.p2p_sorted, sizeof(uint64_t) * w.cap_p2p));
+    FMM_TRY(cudaMalloc(&w.runs, sizeof(int2) * w.cap_p2p));
+    return cudaSuccess;
+}
+
+// CUB scratch: the largest of the particle sort, the pair-key sorts and the scans
+inline cudaError_t fmm_alloc_cub(FmmWorkspace& w, std::string& err) {
+    if (w.cub_tmp) cudaFree(w.cub_tmp);
+    w.cub_tmp = nullptr;
+    size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_alt, w.perm, w.perm_alt, (int)w.cap_n);
+    cub::DeviceRadixSort::SortKeys(nullptr, b2, w.m2l, w.m2l_sorted, (int)w.cap_pairs);
+    cub::DeviceRadixSort::SortKeys(nullptr, b3, w.p2p, w.p2p_sorted, (int)w.cap_p2p);
+    cub::DeviceScan::ExclusiveSum(nullptr, b4, w.nchild, w.child_off, w.cap_cells);
+    w.cub_bytes = std::max(std::max(b1, b2), std::max(b3, b4));
+    FMM_TRY(cudaMalloc(&w.cub_tmp, w.cub_bytes));
+    return cudaSuccess;
+}
+
+inline cudaError_t fmm_reserve(FmmWorkspace& w, int64_t n, int ncrit, int PLmax_terms_NM, int PLmax_terms_NL, std::string& err) {
+    if (n <= w.cap_n && w.cap_cells > 0 && (size_t)w.cap_cells * 3 * PLmax_terms_NL <= w.ml_doubles_L) return cudaSuccess;
+    fmm_free(w);
+    const int64_t cap_n = std::max<int64_t>(n, 1024);
+    int64_t cells = std::max<int64_t>(8192, 24 * cap_n / std::max(ncrit, 1));
+    cells = std::min<int64_t>(cells, 2 * cap_n + 16);
+    w.cap_n = cap_n;
+    w.cap_cells = (int)cells;
+    w.cap_pairs = (unsigned int)std::min<int64_t>(160 * cells, 1500000000LL);
+    w.cap_p2p = (unsigned int)std::min<int64_t>(96 * cells, 1500000000LL);
+    w.lds = (cap_n + 31) / 32 * 32;
+    FMM_TRY(cudaMalloc(&w.keys, sizeof(uint64_t) * cap_n));
+    FMM_TRY(cudaMalloc(&w.keys_alt, sizeof(uint64_t) * cap_n));
+    FMM_TRY(cudaMalloc(&w.perm, sizeof(int) * cap_n));
+    FMM_TRY(cudaMalloc(&w.perm_alt, sizeof(int) * cap_n));
+    FMM_TRY(cudaMalloc(&w.sx, sizeof(double) * w.lds));
+    FMM_TRY(cudaMalloc(&w.sy, sizeof(double) * w.lds));
+    FMM_TRY(cudaMalloc(&w.sz, sizeof(double) * w.lds));
+    FMM_TRY(cudaMalloc(&w.rec, sizeof(double) * REC_REALS * cap_n));
+    FMM_TRY(cudaMalloc(&w.sU, sizeof(double) * 3 * w.lds));
+    FMM_TRY(cudaMalloc(&w.sJ, sizeof(double) * 9 * w.lds));
+    FMM_TRY(cudaMalloc(&w.sE, sizeof(double) * 3 * w.lds));
+    FMM_TRY(cudaMalloc(&w.cells, sizeof(FmmCell) * cells));
+    FMM_TRY(cudaMalloc(&w.nchild, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.child_off, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.leaf_flag, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.leaf_pos, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.leaves, sizeof(int) * cells));
+    w.ml_doubles_M = (size_t)cells * 3 * PLmax_terms_NM;
+    w.ml_doubles_L = (size_t)cells * 3 * PLmax_terms_NL;
+    FMM_TRY(cudaMalloc(&w.M, sizeof(double) * w.ml_doubles_M));
+    FMM_TRY(cudaMalloc(&w.L, sizeof(double) * w.ml_doubles_L));
+    FMM_TRY(fmm_alloc_pairs(w, err));
+    FMM_TRY(cudaMalloc(&w.m2l_off, sizeof(unsigned int) * (cells + 1)));
+    FMM_TRY(cudaMalloc(&w.p2p_off, sizeof(unsigned int) * (cells + 1)));
+    FMM_TRY(cudaMalloc(&w.counters, sizeof(FmmCounters)));
+    FMM_TRY(cudaMalloc(&w.bounds, sizeof(double) * 6 * 256));
+    FMM_TRY(cudaMalloc(&w.count_at, sizeof(int) * cap_n));
+    return fmm_alloc_cub(w, err);
+}
+
+template <int P>
+struct FmmPasses {
+    using Ops = FmmOps<P>;
+
+    static cudaError_t upward(FmmWorkspace& w, const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches) {
+        cudaError_t e;
+        if ((e = cudaMemsetAsync(w.M, 0, sizeof(double) * (size_t)w.ncells * 3 * Ops::NM, st)) != cudaSuccess) return e;
+        fmm_p2m_kernel<P><<<(w.ncells + 3) / 4, 128, 0, st>>>(w.cells, w.ncells, w.rec, w.M);
+        ++launches;
+        for (int l = (int)lvl.size() - 2; l >= 0; --l) {   // lvl[l] .. lvl[l+1] is level l
+            const int c0 = lvl[l], c1 = lvl[l + 1];
+            if (l == (int)lvl.size() - 2) continue;          // deepest level has no children
+            fmm_m2m_kernel<P><<<((c1 - c0) * 3 + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.M);
+            ++launches;
+        }
+        return cudaGetLastError();
+    }
+
+    static cudaError_t downward(FmmWorkspace& w, const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches) {
+        cudaError_t e;
+        if ((e = cudaMemsetAsync(w.L, 0, sizeof(double) * (size_t)w.ncells * 3 * Ops::NL, st)) != cudaSuccess) return e;
+        const size_t smem = sizeof(double) * 3 * Ops::NL * 32;
+        if ((e = cudaFuncSetAttribute(fmm_m2l_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+            return e;
+        fmm_m2l_kernel<P><<<w.ncells, 32, smem, st>>>(w.cells, w.ncells, w.m2l_sorted, w.m2l_off, w.M, w.L);
+        ++launches;
+        for (int l = 1; l + 1 < (int)lvl.size(); ++l) {
+            const int c0 = lvl[l], c1 = lvl[l + 1];
+            fmm_l2l_kernel<P><<<((c1 - c0) * 3 + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.L);
+            ++launches;
+        }
+        return cudaGetLastError();
+    }
+
+    template <int KERNEL>
+    static cudaError_t leaves_uj(FmmWorkspace& w, int block, const double* gh_table, cudaStream_t st, uint64_t& launches) {
+        (void)block;
+        const size_t smem = sizeof(double) * LEAF_WARPS * (((3 * Ops::NL + 1) & ~1) + (size_t)LEAF_BATCH * REC_REALS);
+        auto kfn = fmm_leaf_uj_kernel<KERNEL, P>;
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<(w.nleaves + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(
+            w.cells, w.leaves, w.nleaves, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
+        ++launches;
+        return cudaGetLastError();
+    }
+
+    static cudaError_t leaves_uj(FmmWorkspace& w, int kernel, int block, const double* gh_table, cudaStream_t st,
+                                 uint64_t& launches) {
+        switch (kernel) {
+        case K_GAUSSIANERF: return leaves_uj<K_GAUSSIANERF>(w, block, gh_table, st, launches);
+        case K_WINCKELMANS: return leaves_uj<K_WINCKELMANS>(w, block, gh_table, st, launches);
+        case K_GAUSSIAN: return leaves_uj<K_GAUSSIAN>(w, block, gh_table, st, launches);
+        default: return leaves_uj<K_SINGULAR>(w, block, gh_table, st, launches);
+        }
+    }
+};
+
+// Build the adaptive octree and the interaction lists for the particles currently gathered in the workspace.
+inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, int ncrit, double theta,
+                             double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err) {
+    const double* X = soa + (size_t)F_X * ld;
+    const double* Y = soa + (size_t)(F_X + 1) * ld;
+    const double* Z = soa + (size_t)(F_X + 2) * ld;
+    // ---- bounding cube
+    const int nb = 128;
+    fmm_bounds_kernel<<<nb, 256, 0, st>>>(X, Y, Z, n, w.bounds);
+    ++launches;
+    std::vector<double> hb(6 * nb);
+    FMM_TRY(cudaMemcpyAsync(hb.data(), w.bounds, sizeof(double) * 6 * nb, cudaMemcpyDeviceToHost, st));
+    FMM_TRY(cudaStreamSynchronize(st));
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int b = 0; b < nb; ++b)
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = std::min(lo[c], hb[6 * b + 2 * c]);
+            hi[c] = std::max(hi[c], -hb[6 * b + 2 * c + 1]);
+        }
+    for (int c = 0; c < 3; ++c)
+        if (!(lo[c] <= hi[c]) || !std::isfinite(lo[c]) || !std::isfinite(hi[c])) {
+            err = "FMM: particle positions are not finite";
+            return cudaErrorInvalidValue;
+        }
+    double side = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    side = side > 0 ? side * (1.0 + 1e-9) : 1.0;
+    const double cx = 0.5 * (lo[0] + hi[0]), cy = 0.5 * (lo[1] + hi[1]), cz = 0.5 * (lo[2] + hi[2]);
+    const double x0 = cx - 0.5 * side, y0 = cy - 0.5 * side, z0 = cz - 0.5 * side;
+    // ---- keys, sort, gather
+    const unsigned nbk = (unsigned)((n + 255) / 256);
+    fmm_keys_kernel<<<nbk, 256, 0, st>>>(X, Y, Z, n, x0, y0, z0, 2097152.0 / side, w.keys, w.perm);
+    ++launches;
+    size_t tb = w.cub_bytes;
+    FMM_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys_alt, w.perm, w.perm_alt, (int)n, 0, 63, st));
+    ++launches;
+    std::swap(w.keys, w.keys_alt);
+    std::swap(w.perm, w.perm_alt);
+    fmm_gather_kernel<<<nbk, 256, 0, st>>>(soa, ld, n, w.perm, w.sx, w.sy, w.sz, w.rec);
+    ++launches;
+    // ---- tree, level by level
+    FmmCell root;
+    root.start = 0; root.count = (int)n; root.parent = -1; root.child0 = -1; root.nchild = 0; root.level = 0;
+    root.cx = cx; root.cy = cy; root.cz = cz; root.R = 0.5 * side; root.smax = 0.0; root.pad_ = 0.0;
+    FMM_TRY(cudaMemcpyAsync(w.cells, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+    lvl.clear();
+    lvl.push_back(0);
+    lvl.push_back(1);
+    int ncells = 1;
+    while (true) {
+        const int c0 = lvl[lvl.size() - 2], c1 = lvl.back();
+        const int nc = c1 - c0;
+        fmm_split_count_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.nchild);
+        tb = w.cub_bytes;
+        FMM_TRY(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.nchild, w.child_off, nc, st));
+        int last_off = 0, last_n = 0;
+        FMM_TRY(cudaMemcpyAsync(&last_off, w.child_off + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaMemcpyAsync(&last_n, w.nchild + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaStreamSynchronize(st));
+        const int nnew = last_off + last_n;
+        launches += 2;
+        if (ncells + nnew > w.cap_cells) {
+            err = "FMM: octree needs more cells than the workspace holds (extremely clustered particles?)";
+            return cudaErrorMemoryAllocation;
+        }
+        fmm_split_emit_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.child_off, ncells);
+        ++launches;
+        if (nnew == 0) break;
+        ncells += nnew;
+        lvl.push_back(ncells);
+    }
+    w.ncells = ncells;
+    w.nlevels = (int)lvl.size() - 1;
+    // ---- leaves
+    fmm_mark_leaves_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(w.cells, ncells, w.leaf_flag);
+    tb = w.cub_bytes;
+    FMM_TRY(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.leaf_flag, w.leaf_pos, ncells, st));
+    fmm_collect_leaves_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(w.leaf_flag, w.leaf_pos, ncells, w.leaves);
+    launches += 3;
+    int lp = 0, lf = 0;
+    FMM_TRY(cudaMemcpyAsync(&lp, w.leaf_pos + ncells - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FMM_TRY(cudaMemcpyAsync(&lf, w.leaf_flag + ncells - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FMM_TRY(cudaStreamSynchronize(st));
+    w.nleaves = lp + lf;
+    if (nzs_factor > 0.0) {   // largest core size per cell, leaves first then level by level upward
+        fmm_smax_leaf_kernel<<<(ncells + 127) / 128, 128, 0, st>>>(w.cells, ncells, w.rec);
+        ++launches;
+        for (int l = (int)lvl.size() - 3; l >= 0; --l) {
+            fmm_smax_up_kernel<<<(lvl[l + 1] - lvl[l] + 127) / 128, 128, 0, st>>>(w.cells, lvl[l], lvl[l + 1]);
+            ++launches;
+        }
+    }
+    // ---- dual tree traversal (grows the pair buffers and starts over if a list overflows)
+    FmmCounters zero = {0, 0, 0, 0};
+    FmmCounters hc = zero;
+    for (int attempt = 0;; ++attempt) {
+        FMM_TRY(cudaMemcpyAsync(w.counters, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+        const uint64_t rootpair = 0;
+        FMM_TRY(cudaMemcpyAsync(w.front_a, &rootpair, sizeof(rootpair), cudaMemcpyHostToDevice, st));
+        unsigned int nfront = 1;
+        uint64_t *fa = w.front_a, *fb = w.front_b;
+        hc = zero;
+        while (nfront > 0) {
+            fmm_traverse_kernel<<<(nfront + 255) / 256, 256, 0, st>>>(w.cells, fa, nfront, theta, nzs_factor, fb, w.cap_pairs, w.m2l,
+                                                                     w.cap_pairs, w.p2p, w.cap_p2p, w.counters);
+            ++launches;
+            FMM_TRY(cudaMemcpyAsync(&hc, w.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            FMM_TRY(cudaStreamSynchronize(st));
+            if (hc.overflow) break;
+            nfront = hc.next;
+            const unsigned int z = 0;
+            FMM_TRY(cudaMemcpyAsync(&w.counters->next, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+            std::swap(fa, fb);
+        }
+        if (!hc.overflow) break;
+        if (attempt >= 6 || w.cap_pairs > 1000000000u || w.cap_p2p > 1000000000u) {
+            err = "FMM: interaction lists overflowed the workspace";
+            return cudaErrorMemoryAllocation;
+        }
+        // counters keep counting past the capacity, so they say which list to grow
+        if (hc.p2p >= w.cap_p2p) w.cap_p2p = std::max(w.cap_p2p * 2, hc.p2p + hc.p2p / 2);
+        if (hc.m2l >= w.cap_pairs || hc.next >= w.cap_pairs) w.cap_pairs *= 2;
+        FMM_TRY(fmm_alloc_pairs(w, err));
+        FMM_TRY(fmm_alloc_cub(w, err));
+    }
+    w.n_m2l = hc.m2l;
+    w.n_p2p = hc.p2p;
+    // ---- sort the lists by (target, source) and index them per target cell
+    int bits = 1;
+    while ((1 << bits) < ncells) ++bits;
+    if (w.n_m2l > 0) {
+        tb = w.cub_bytes;
+        FMM_TRY(cub::DeviceRadixSort::SortKeys(w.cub_tmp, tb, w.m2l, w.m2l_sorted, (int)w.n_m2l, 0, 32 + bits, st));
+        ++launches;
+    }
+    if (w.n_p2p > 0) {
+        tb = w.cub_bytes;
+        FMM_TRY(cub::DeviceRadixSort::SortKeys(w.cub_tmp, tb, w.p2p, w.p2p_sorted, (int)w.n_p2p, 0, 32 + bits, st));
+        ++launches;
+    }
+    fmm_list_offsets_kernel<<<(ncells + 256) / 256, 256, 0, st>>>(w.m2l_sorted, w.n_m2l, ncells, w.m2l_off);
+    fmm_list_offsets_kernel<<<(ncells + 256) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, ncells, w.p2p_off);
+    fmm_leaf_counts_kernel<<<(w.nleaves + 255) / 256, 256, 0, st>>>(w.cells, w.leaves, w.nleaves, w.count_at);
+    if (w.n_p2p > 0) fmm_p2p_runs_kernel<<<(w.n_p2p + 255) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, w.count_at, w.runs);
+    launches += 4;
+    FMM_TRY(cudaGetLastError());
+    return cudaSuccess;
+}
+
+template <int P>
+inline cudaError_t fmm_evaluate_p(FmmWorkspace& w, int kernel, int block, const double* gh_table, const std::vector<int>& lvl,
+                                  cudaStream_t st, uint64_t& launches) {
+    cudaError_t e;
+    if ((e = FmmPasses<P>::upward(w, lvl, st, launches)) != cudaSuccess) return e;
+    if ((e = FmmPasses<P>::downward(w, lvl, st, launches)) != cudaSuccess) return e;
+    return FmmPasses<P>::leaves_uj(w, kernel, block, gh_table, st, launches);
+}
+
+inline cudaError_t fmm_evaluate(FmmWorkspace& w, int p, int kernel, int block, const double* gh_table,
+                                const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches) {
+    switch (p) {
+    case 2: return fmm_evaluate_p<2>(w, kernel, block, gh_table, lvl, st, launches);
+    case 3: return fmm_evaluate_p<3>(w, kernel, block, gh_table, lvl, st, launches);
+    case 4: return fmm_evaluate_p<4>(w, kernel, block, gh_table, lvl, st, launches);
+    case 5: return fmm_evaluate_p<5>(w, kernel, block, gh_table, lvl, st, launches);
+    case 6: return fmm_evaluate_p<6>(w, kernel, block, gh_table, lvl, st, launches);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transposed, const double* z_table, cudaStream_t st,
+                            uint64_t& launches) {
+    (void)block;
+    const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)LEAF_BATCH * REC_REALS;
+#define FMM_ESTR_CASE(K)                                                                                                   \
+    fmm_leaf_estr_kernel<K><<<(w.nleaves + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(                     \
+        w.cells, w.leaves, w.nleaves, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
+    switch (kernel) {
+    case K_GAUSSIANERF: FMM_ESTR_CASE(K_GAUSSIANERF); break;
+    case K_WINCKELMANS: FMM_ESTR_CASE(K_WINCKELMANS); break;
+    case K_GAUSSIAN: FMM_ESTR_CASE(K_GAUSSIAN); break;
+    default: FMM_ESTR_CASE(K_SINGULAR); break;
+    }
+#undef FMM_ESTR_CASE
+    ++launches;
+    return cudaGetLastError();
+}
+
+}  // namespace vpm

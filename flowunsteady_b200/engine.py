@@ -186,6 +186,11 @@ class Engine:
         self._check(self._L.vpmb200_stream(self._h, C.byref(s)))
         return s.value or 0
 
+    def fmm_stats(self) -> dict:
+        a = (C.c_int64 * 5)()
+        self._check(self._L.vpmb200_fmm_stats(self._h, a))
+        return dict(zip(("cells", "leaves", "levels", "m2l_pairs", "p2p_pairs"), [int(v) for v in a]))
+
     @property
     def launch_count(self) -> int:
         c = C.c_uint64()

@@ -177,6 +177,8 @@ int32_t vpmb200_count_nonfinite(vpmb200_handle h, int64_t* count);
 int32_t vpmb200_device_field(vpmb200_handle h, int32_t field, double** ptr, int64_t* ld);
 /* The CUDA stream (cudaStream_t) every call on this handle is enqueued on. */
 int32_t vpmb200_stream(vpmb200_handle h, void** stream);
+/* Tree statistics of the last UJ_fmm evaluation: stats[0..4] = cells, leaves, levels, M2L pairs, P2P (leaf) pairs. */
+int32_t vpmb200_fmm_stats(vpmb200_handle h, int64_t* stats);
 /* Number of CUDA kernels this handle has enqueued since creation (bench.py reports the per-step delta). */
 int32_t vpmb200_launch_count(vpmb200_handle h, uint64_t* count);
 /* Block the host until all enqueued work on the handle has finished. */
