@@ -34,6 +34,7 @@ struct vpmb200_engine {
     double* partial = nullptr;  // per-chunk partial outputs of source-split pair launches
     size_t partial_doubles = 0;
     int sm_count = 148;
+    int direct_sort = 1;        // Morton-order the direct path internally (vpmb200_set_option)
     double* probe = nullptr;    // probe scratch: 3 (X) + 3 (U) + 9 (J) rows of probe_ld, + AoS staging
     int64_t probe_cap = 0;
     unsigned long long* counter = nullptr;
@@ -166,7 +167,8 @@ cudaError_t dispatch_uj(vpmb200_engine* e, const double* rec, int ntiles, const 
 }
 
 template <int K>
-cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
+cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty, const double* tz,
+                        const double* Jt, int64_t ldj, double* sfs, int64_t ldo, int accumulate) {
     if (e->np <= 0) return cudaSuccess;
     Geometry g;
     cudaError_t st = make_geometry(e, e->np, ntiles, 3, &g);
@@ -175,25 +177,30 @@ cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
     size_t smem = estr_smem_bytes(K);
     st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
-    const double* S = e->state;
-    const int64_t ld = e->ld;
-    double* sfs = e->state + (size_t)F_SFS * ld;
-    kfn<<<g.grid, UJ_BT, smem, e->stream>>>(rec, ntiles, S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld,
-                                          S + (size_t)(F_X + 2) * ld, e->np, S + (size_t)F_J * ld, ld, e->sch.transposed, sfs,
-                                          ld, e->z_table, g.split);
+    kfn<<<g.grid, UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, e->np, Jt, ldj, e->sch.transposed, sfs, ldo, e->z_table,
+                                          g.split, accumulate);
     e->launches++;
     st = cudaGetLastError();
     if (st != cudaSuccess) return st;
-    return reduce_split(e, g, 3, e->np, sfs, sfs, 3, ld, 1);
+    return reduce_split(e, g, 3, e->np, sfs, sfs, 3, ldo, accumulate);
 }
 
-cudaError_t dispatch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
+cudaError_t dispatch_estr_at(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty,
+                             const double* tz, const double* Jt, int64_t ldj, double* sfs, int64_t ldo, int accumulate) {
     switch (e->sch.kernel) {
-    case K_GAUSSIANERF: return launch_estr<K_GAUSSIANERF>(e, rec, ntiles);
-    case K_WINCKELMANS: return launch_estr<K_WINCKELMANS>(e, rec, ntiles);
-    case K_GAUSSIAN: return launch_estr<K_GAUSSIAN>(e, rec, ntiles);
-    default: return launch_estr<K_SINGULAR>(e, rec, ntiles);
+    case K_GAUSSIANERF: return launch_estr<K_GAUSSIANERF>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
+    case K_WINCKELMANS: return launch_estr<K_WINCKELMANS>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
+    case K_GAUSSIAN: return launch_estr<K_GAUSSIAN>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
+    default: return launch_estr<K_SINGULAR>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
     }
+}
+
+// E_str of the local particles (state rows as targets), accumulated into the state's SFS rows
+cudaError_t dispatch_estr(vpmb200_engine* e, const double* rec, int ntiles) {
+    const double* S = e->state;
+    const int64_t ld = e->ld;
+    return dispatch_estr_at(e, rec, ntiles, S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld, S + (size_t)(F_X + 2) * ld,
+                            S + (size_t)F_J * ld, ld, e->state + (size_t)F_SFS * ld, ld, 1);
 }
 
 int32_t zero_rows(vpmb200_engine* e, int first, int count) {
@@ -214,7 +221,7 @@ int32_t do_reset(vpmb200_engine* e) {
 
 int32_t pack_uj(vpmb200_engine* e, double* dst) {
     if (e->np <= 0) return VPMB200_OK;
-    pack_uj_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(e->state, e->ld, e->np, dst);
+    pack_uj_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(e->state, e->ld, e->np, nullptr, dst);
     CU_TRY(e, cudaGetLastError());
     e->launches++;
     return VPMB200_OK;
@@ -223,7 +230,7 @@ int32_t pack_uj(vpmb200_engine* e, double* dst) {
 int32_t pack_estr(vpmb200_engine* e, double* dst) {
     if (e->np <= 0) return VPMB200_OK;
     pack_estr_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(
-        e->state, e->ld, e->np, e->sch.transposed, zeta0_of(e->sch.kernel), e->sch.kernel == K_GAUSSIANERF ? 1 : 0, dst);
+        e->state, e->ld, e->np, nullptr, e->sch.transposed, zeta0_of(e->sch.kernel), e->sch.kernel == K_GAUSSIANERF ? 1 : 0, dst);
     CU_TRY(e, cudaGetLastError());
     e->launches++;
     return VPMB200_OK;
@@ -275,6 +282,43 @@ int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     return VPMB200_OK;
 }
 
+// Direct path with internal Morton ordering: targets and source tiles are both visited in Morton order, so a CTA's 256
+// targets and a tile's 256 sources are compact boxes and the tile-level far/near classification of K1/K2 stays
+// effective for ANY input order (random fields, freshly shed particles...).  Results are scattered back to particle order.
+int32_t do_uj_direct_sorted(vpmb200_engine* e, int reset, int sfs) {
+    std::string err;
+    if (fmm_reserve(e->fmm, e->np, 50, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    FmmWorkspace& w = e->fmm;
+    if (fmm_sort(w, e->state, e->ld, e->np, e->stream, e->launches, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    const int64_t n = e->np;
+    const unsigned nb = blocks_for(n, PK_BT);
+    const int ntiles = (int)vpmb200_tiles_for(n);
+    gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X, 1, n, w.perm, w.sx, w.lds);
+    gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X + 1, 1, n, w.perm, w.sy, w.lds);
+    gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X + 2, 1, n, w.perm, w.sz, w.lds);
+    pack_uj_records_kernel<<<blocks_for(n, TILE_SRC), TILE_SRC, 0, e->stream>>>(e->state, e->ld, n, w.perm, e->rec);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 4;
+    CU_TRY(e, dispatch_uj(e, e->rec, ntiles, w.sx, w.sy, w.sz, n, w.sU, w.sJ, w.lds, 0));
+    fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sU, w.lds, 3, n, w.perm, e->state + (size_t)F_U * e->ld, e->ld, reset ? 0 : 1);
+    fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sJ, w.lds, 9, n, w.perm, e->state + (size_t)F_J * e->ld, e->ld, reset ? 0 : 1);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 2;
+    if (sfs) {
+        // the E_str pass needs the field's CURRENT (total) J at targets and sources
+        gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_J, 9, n, w.perm, w.sJ, w.lds);
+        pack_estr_records_kernel<<<blocks_for(n, TILE_SRC), TILE_SRC, 0, e->stream>>>(
+            e->state, e->ld, n, w.perm, e->sch.transposed, zeta0_of(e->sch.kernel), e->sch.kernel == K_GAUSSIANERF ? 1 : 0, e->rec);
+        CU_TRY(e, cudaGetLastError());
+        e->launches += 2;
+        CU_TRY(e, dispatch_estr_at(e, e->rec, ntiles, w.sx, w.sy, w.sz, w.sJ, w.lds, w.sE, w.lds, 0));
+        fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sE, w.lds, 3, n, w.perm, e->state + (size_t)F_SFS * e->ld, e->ld, 1);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
+    return VPMB200_OK;
+}
+
 // pfield.UJ(pfield; reset, reset_sfs, sfs)
 int32_t do_uj(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     if (e->sch.uj == VPMB200_UJ_FMM) return do_uj_fmm(e, reset, reset_sfs, sfs);
@@ -282,6 +326,7 @@ int32_t do_uj(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     if (reset && (rc = zero_rows(e, F_PSE, 3))) return rc;
     if (reset_sfs && (rc = zero_rows(e, F_SFS, 3))) return rc;
     if (e->np <= 0) return VPMB200_OK;
+    if (e->direct_sort && e->np >= 4 * TILE_SRC && e->np < 2000000000LL) return do_uj_direct_sorted(e, reset, sfs);
     if ((rc = pack_uj(e, e->rec))) return rc;
     if ((rc = uj_local_from(e, e->rec, vpmb200_tiles_for(e->np), reset ? 0 : 1))) return rc;
     if (sfs) {
@@ -745,6 +790,16 @@ int32_t vpmb200_stream(vpmb200_handle e, void** stream) {
     if (!stream) return fail(e, VPMB200_EINVAL, "stream is NULL");
     *stream = (void*)e->stream;
     return VPMB200_OK;
+}
+
+int32_t vpmb200_set_option(vpmb200_handle e, const char* name, int64_t value) {
+    CHECK_HANDLE(e);
+    if (!name) return fail(e, VPMB200_EINVAL, "option name is NULL");
+    if (std::strcmp(name, "direct_sort") == 0) {
+        e->direct_sort = value != 0;
+        return VPMB200_OK;
+    }
+    return fail(e, VPMB200_EINVAL, std::string("unknown option: ") + name);
 }
 
 int32_t vpmb200_fmm_stats(vpmb200_handle e, int64_t* stats) {

@@ -75,8 +75,7 @@ __global__ void __launch_bounds__(UJ_BT, 2)
 estr_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* __restrict__ tx,
                        const double* __restrict__ ty, const double* __restrict__ tz, int64_t nt,
                        const double* __restrict__ Jt, int64_t ldj, int transposed, double* __restrict__ SFS,
-                       int64_t ldo, const double* __restrict__ z_table, SplitArgs split) {
-    int accumulate = 1;
+                       int64_t ldo, const double* __restrict__ z_table, SplitArgs split, int accumulate) {
     if (split.partial != nullptr) {
         const int t0 = blockIdx.y * split.tiles_per_chunk;
         srec += (size_t)t0 * TILE_DOUBLES;

@@ -112,11 +112,14 @@ __device__ __forceinline__ void write_tile_header(double* __restrict__ hdr, bool
 // UJ source tiles (common.cuh).  Grid: ntiles CTAs of TILE_SRC threads; slot i >= n repeats the tile's first real
 // source position with zero strength.
 __global__ void __launch_bounds__(TILE_SRC)
-pack_uj_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, double* __restrict__ rec) {
+pack_uj_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, const int* __restrict__ perm,
+                       double* __restrict__ rec) {
     const int64_t t0 = (int64_t)blockIdx.x * TILE_SRC;
-    const int64_t i = t0 + threadIdx.x;
-    const bool real = i < n;
-    const int64_t isrc = real ? i : t0;  // t0 < n always (the grid is ceil(n / TILE_SRC))
+    const int64_t islot = t0 + threadIdx.x;
+    const bool real = islot < n;
+    // slot -> particle: identity, or Morton order when the caller sorted (perm); t0 < n always
+    const int64_t isrc = perm ? perm[real ? islot : t0] : (real ? islot : t0);
+    const int64_t i = isrc;
     double* tile = rec + (size_t)blockIdx.x * TILE_DOUBLES;
     double2* r = reinterpret_cast<double2*>(tile + (size_t)threadIdx.x * REC_REALS);
     double x = soa[(size_t)(F_X + 0) * ld + isrc], y = soa[(size_t)(F_X + 1) * ld + isrc], z = soa[(size_t)(F_X + 2) * ld + isrc];
@@ -146,12 +149,13 @@ pack_uj_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, do
 // E_str source tiles: c = zeta_norm / sigma^3, v = J^T Gamma (transposed) or J Gamma.  `cutoff` != 0 stores
 // max(T_FAR sigma^2) in the header (kernels whose zeta vanishes beyond T_FAR); otherwise +inf-like (never skipped).
 __global__ void __launch_bounds__(TILE_SRC)
-pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, int transposed, double zeta_norm,
-                         int cutoff, double* __restrict__ rec) {
+pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, const int* __restrict__ perm, int transposed,
+                         double zeta_norm, int cutoff, double* __restrict__ rec) {
     const int64_t t0 = (int64_t)blockIdx.x * TILE_SRC;
-    const int64_t i = t0 + threadIdx.x;
-    const bool real = i < n;
-    const int64_t isrc = real ? i : t0;
+    const int64_t islot = t0 + threadIdx.x;
+    const bool real = islot < n;
+    const int64_t isrc = perm ? perm[real ? islot : t0] : (real ? islot : t0);
+    const int64_t i = isrc;
     double* tile = rec + (size_t)blockIdx.x * TILE_DOUBLES;
     double2* r = reinterpret_cast<double2*>(tile + (size_t)threadIdx.x * REC_REALS);
     double x = soa[(size_t)(F_X + 0) * ld + isrc], y = soa[(size_t)(F_X + 1) * ld + isrc], z = soa[(size_t)(F_X + 2) * ld + isrc];
@@ -190,6 +194,15 @@ pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, 
     }
     int64_t nreal = n - t0;
     write_tile_header(tile + TILE_HDR, real, x, y, z, rfar2, (int)(nreal > TILE_SRC ? TILE_SRC : nreal));
+}
+
+// dst[k * ldd + i] = src[(row0 + k) * ld + perm[i]]  — SoA rows into Morton order
+__global__ void gather_rows_kernel(const double* __restrict__ soa, int64_t ld, int row0, int nrows, int64_t n,
+                                   const int* __restrict__ perm, double* __restrict__ dst, int64_t ldd) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = perm[i];
+    for (int k = 0; k < nrows; ++k) dst[(size_t)k * ldd + i] = soa[(size_t)(row0 + k) * ld + p];
 }
 
 // Sum the per-chunk partial rows of a source-split pair launch in chunk order.  partial row (c * ncomp + k) holds

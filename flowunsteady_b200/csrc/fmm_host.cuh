@@ -184,13 +184,17 @@ struct FmmPasses {
     }
 };
 
-// Build the adaptive octree and the interaction lists for the particles currently gathered in the workspace.
-inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, int ncrit, double theta,
-                             double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err) {
+// Bounding cube + Morton keys + radix sort of the particles: fills w.keys (sorted), w.perm (Morton slot -> particle) and
+// the root cell geometry.  One host read-back (the 6 bounds).
+struct FmmRoot {
+    double cx, cy, cz, side;
+};
+
+inline cudaError_t fmm_sort(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, cudaStream_t st, uint64_t& launches,
+                            std::string& err, FmmRoot* root_out = nullptr) {
     const double* X = soa + (size_t)F_X * ld;
     const double* Y = soa + (size_t)(F_X + 1) * ld;
     const double* Z = soa + (size_t)(F_X + 2) * ld;
-    // ---- bounding cube
     const int nb = 128;
     fmm_bounds_kernel<<<nb, 256, 0, st>>>(X, Y, Z, n, w.bounds);
     ++launches;
@@ -205,14 +209,13 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
         }
     for (int c = 0; c < 3; ++c)
         if (!(lo[c] <= hi[c]) || !std::isfinite(lo[c]) || !std::isfinite(hi[c])) {
-            err = "FMM: particle positions are not finite";
+            err = "particle positions are not finite";
             return cudaErrorInvalidValue;
         }
     double side = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     side = side > 0 ? side * (1.0 + 1e-9) : 1.0;
     const double cx = 0.5 * (lo[0] + hi[0]), cy = 0.5 * (lo[1] + hi[1]), cz = 0.5 * (lo[2] + hi[2]);
     const double x0 = cx - 0.5 * side, y0 = cy - 0.5 * side, z0 = cz - 0.5 * side;
-    // ---- keys, sort, gather
     const unsigned nbk = (unsigned)((n + 255) / 256);
     fmm_keys_kernel<<<nbk, 256, 0, st>>>(X, Y, Z, n, x0, y0, z0, 2097152.0 / side, w.keys, w.perm);
     ++launches;
@@ -221,6 +224,21 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     ++launches;
     std::swap(w.keys, w.keys_alt);
     std::swap(w.perm, w.perm_alt);
+    if (root_out) *root_out = FmmRoot{cx, cy, cz, side};
+    return cudaSuccess;
+}
+
+// Build the adaptive octree and the interaction lists for the particles of the field.
+inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, int ncrit, double theta,
+                             double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err) {
+    FmmRoot rt;
+    {
+        cudaError_t e0 = fmm_sort(w, soa, ld, n, st, launches, err, &rt);
+        if (e0 != cudaSuccess) return e0;
+    }
+    const double cx = rt.cx, cy = rt.cy, cz = rt.cz, side = rt.side;
+    const unsigned nbk = (unsigned)((n + 255) / 256);
+    size_t tb = w.cub_bytes;
     fmm_gather_kernel<<<nbk, 256, 0, st>>>(soa, ld, n, w.perm, w.sx, w.sy, w.sz, w.rec);
     ++launches;
     // ---- tree, level by level

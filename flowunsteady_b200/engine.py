@@ -186,6 +186,9 @@ class Engine:
         self._check(self._L.vpmb200_stream(self._h, C.byref(s)))
         return s.value or 0
 
+    def set_option(self, name: str, value: int):
+        self._check(self._L.vpmb200_set_option(self._h, name.encode(), int(value)))
+
     def fmm_stats(self) -> dict:
         a = (C.c_int64 * 5)()
         self._check(self._L.vpmb200_fmm_stats(self._h, a))

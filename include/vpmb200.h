@@ -177,6 +177,9 @@ int32_t vpmb200_count_nonfinite(vpmb200_handle h, int64_t* count);
 int32_t vpmb200_device_field(vpmb200_handle h, int32_t field, double** ptr, int64_t* ld);
 /* The CUDA stream (cudaStream_t) every call on this handle is enqueued on. */
 int32_t vpmb200_stream(vpmb200_handle h, void** stream);
+/* Engine options.  "direct_sort" (default 1): visit targets and source tiles of the DIRECT path in Morton order
+ * internally (results are returned in particle order); 0 keeps the caller's particle order. */
+int32_t vpmb200_set_option(vpmb200_handle h, const char* name, int64_t value);
 /* Tree statistics of the last UJ_fmm evaluation: stats[0..4] = cells, leaves, levels, M2L pairs, P2P (leaf) pairs. */
 int32_t vpmb200_fmm_stats(vpmb200_handle h, int64_t* stats);
 /* Number of CUDA kernels this handle has enqueued since creation (bench.py reports the per-step delta). */
