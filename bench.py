@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--sfs", default="none", choices=["none", "dynamic"], help="SFS scheme of the timed step")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fmm", action="store_true", help="skip the secondary UJ_fmm figures")
     ap.add_argument("--cpu-targets", type=int, default=4096, help="targets of the CPU baseline slab")
     return ap.parse_args()
 
@@ -239,6 +240,45 @@ def run_ours(args):
         except Exception:
             pass
 
+    # ---- secondary: the same field through UJ_fmm (reference defaults p=4, ncrit=50, theta=0.4) — BASELINE configs[1]
+    #      (rotor hover high fidelity runs RK3 + dynamic SFS on the FMM path); single GPU only
+    fmm = None
+    if world == 1 and not args.no_fmm:
+        try:
+            P0 = fb.new_particles(x, g, s)
+            ref_idx = np.random.default_rng(1234).choice(n, 2048, replace=False)
+            with fb.Engine(n, schemes=fb.default_schemes(uj="direct")) as e0:      # direct U, J at 2048 probes = truth
+                e0.upload(P0)
+                Ud, Jd = e0.uj_probe(x[ref_idx], want_J=True)
+            fmm = {}
+            for tag, nzs in (("nonzero_sigma_false", 0), ("nonzero_sigma_true", 1)):
+                sch_f = fb.default_schemes(uj="fmm", fmm_p=4, fmm_ncrit=50, fmm_theta=0.4, fmm_nonzero_sigma=nzs,
+                                           sfs="dynamic", alpha=0.999, force_positive=1, clippings=1)
+                with fb.Engine(n, schemes=sch_f) as ef:
+                    ef.upload(P0)
+                    ef.uj(); ef.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        ef.uj()
+                    ef.synchronize()
+                    t_eval = (time.perf_counter() - t0) / 3
+                    out = ef.download(np.zeros_like(P0))
+                    # note: U at a particle excludes its own (r = 0) term in both paths, so probing AT particles is consistent
+                    eU = float(np.linalg.norm(out[ref_idx, 9:12] - Ud) / np.linalg.norm(Ud))
+                    eJ = float(np.linalg.norm(out[ref_idx, 15:24] - Jd) / np.linalg.norm(Jd))
+                    ef.upload(P0)
+                    ef.nextstep(dt_sim, Uinf, relax=True); ef.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        ef.nextstep(dt_sim, Uinf, relax=True)
+                    ef.synchronize()
+                    t_step = (time.perf_counter() - t0) / 3
+                    fmm[tag] = {"ms_per_evaluation": t_eval * 1e3, "ms_per_step_rk3_dynamic_sfs_pedrizzetti": t_step * 1e3,
+                                "rel_l2_err_U_vs_direct": eU, "rel_l2_err_J_vs_direct": eJ, "tree": ef.fmm_stats()}
+            fmm["settings"] = "vpm.FMM(p=4, ncrit=50, theta=0.4); error on 2048 sampled particles vs the direct kernel"
+        except Exception as exc:   # secondary figure: never fail the headline line
+            fmm = {"error": str(exc)}
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----------------
     e2e = None
     if not args.no_e2e:
@@ -309,7 +349,7 @@ def run_ours(args):
                        "source tiles all-gathered (NCCL)", "l2": "inputs larger than L2 (state 344 MB > 126 MB); state is "
                        "rewritten every substep"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
+            "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "fmm": fmm,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
