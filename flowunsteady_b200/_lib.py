@@ -49,6 +49,8 @@ SYMBOLS = {
     "vpmb200_get_np": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "vpmb200_add_particles": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64]),
     "vpmb200_remove_particle": (C.c_int32, [_H, C.c_int64]),
+    "vpmb200_remove_where": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),
+    "vpmb200_monitors": (C.c_int32, [_H, _dp]),
     "vpmb200_reset_particles": (C.c_int32, [_H]),
     "vpmb200_reset_particles_sfs": (C.c_int32, [_H]),
     "vpmb200_uj": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_int32]),

@@ -674,6 +674,90 @@ int32_t vpmb200_remove_particle(vpmb200_handle e, int64_t i) {
     return VPMB200_OK;
 }
 
+int32_t vpmb200_remove_where(vpmb200_handle e, int32_t criterion, const double* params, int64_t* removed) {
+    CHECK_HANDLE(e);
+    if (!params) return fail(e, VPMB200_EINVAL, "params is NULL");
+    static const int nparams[5] = {0, 2, 2, 9, 4};
+    if (criterion < 1 || criterion > 4) return fail(e, VPMB200_EINVAL, "unknown removal criterion");
+    if (removed) *removed = 0;
+    const int64_t n = e->np;
+    if (n <= 0) return VPMB200_OK;
+    if (n > 2000000000LL) return fail(e, VPMB200_ECAPACITY, "remove_where indexes particles with 32-bit integers");
+    CU_TRY(e, cudaSetDevice(e->device));
+    std::string err;
+    if (fmm_reserve(e->fmm, n, 50, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    FmmWorkspace& w = e->fmm;   // scratch: perm = keep flags, perm_alt = exclusive scan, count_at = removed slots,
+                                //          leaf_flag-sized buffers are too small, so f / g live in keys / keys_alt
+    RemoveCriterion c;
+    c.kind = criterion;
+    for (int k = 0; k < 9; ++k) c.p[k] = k < nparams[criterion] ? params[k] : 0.0;
+    const unsigned nb = blocks_for(n, PK_BT);
+    keep_flags_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, n, c, w.perm);
+    CU_TRY(e, cudaGetLastError());
+    size_t tb = w.cub_bytes;
+    CU_TRY(e, cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.perm, w.perm_alt, (int)n, e->stream));
+    int last_scan = 0, last_flag = 0;
+    CU_TRY(e, cudaMemcpyAsync(&last_scan, w.perm_alt + n - 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaMemcpyAsync(&last_flag, w.perm + n - 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    e->launches += 2;
+    const int64_t K = (int64_t)last_scan + last_flag;
+    if (K < n) {
+        if (K > 0) {
+            int* f = reinterpret_cast<int*>(w.keys);
+            int* g = reinterpret_cast<int*>(w.keys_alt);
+            int* changed = reinterpret_cast<int*>(w.counters);
+            list_removed_kernel<<<nb, PK_BT, 0, e->stream>>>(w.perm, w.perm_alt, n, w.count_at);
+            wrap_map_kernel<<<nb, PK_BT, 0, e->stream>>>(w.perm_alt, n, K, w.count_at, f);
+            e->launches += 2;
+            for (int it = 0; it < 40; ++it) {   // pointer doubling: at most log2(n) + 1 rounds
+                int h = 0;
+                CU_TRY(e, cudaMemcpyAsync(changed, &h, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+                wrap_double_kernel<<<nb, PK_BT, 0, e->stream>>>(f, n, g, changed);
+                e->launches++;
+                CU_TRY(e, cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+                CU_TRY(e, cudaStreamSynchronize(e->stream));
+                std::swap(f, g);
+                if (!h) break;
+            }
+            move_survivors_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, w.perm, n, f);
+            CU_TRY(e, cudaGetLastError());
+            e->launches++;
+        }
+        e->np = K;
+    }
+    if (removed) *removed = n - K;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_monitors(vpmb200_handle e, double* out6) {
+    CHECK_HANDLE(e);
+    if (!out6) return fail(e, VPMB200_EINVAL, "out is NULL");
+    for (int k = 0; k < 6; ++k) out6[k] = 0.0;
+    if (e->np <= 0) return VPMB200_OK;
+    CU_TRY(e, cudaSetDevice(e->device));
+    int32_t rc = ensure_probe(e, 1024);
+    if (rc) return rc;
+    const int nb = 128;
+    monitor_partials_kernel<<<nb, 256, 0, e->stream>>>(e->state, e->ld, e->np, e->probe);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    double hb[nb * 8];
+    CU_TRY(e, cudaMemcpyAsync(hb, e->probe, sizeof(hb), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < nb; ++b)
+        for (int k = 0; k < 6; ++k) acc[k] += hb[b * 8 + k];
+    out6[0] = acc[0];
+    const double cnt = acc[3];
+    out6[1] = cnt > 0 ? acc[1] / cnt : 0.0;
+    out6[2] = cnt > 1 ? std::sqrt(std::max(0.0, (acc[2] - acc[1] * acc[1] / cnt) / (cnt - 1))) : 0.0;
+    out6[3] = cnt;
+    out6[4] = acc[4];
+    out6[5] = acc[5];
+    return VPMB200_OK;
+}
+
 int32_t vpmb200_reset_particles(vpmb200_handle e) {
     CHECK_HANDLE(e);
     CU_TRY(e, cudaSetDevice(e->device));

@@ -482,6 +482,104 @@ __global__ void count_nonfinite_kernel(const double* __restrict__ soa, int64_t l
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);
 }
 
+// ---- wake treatments (FLOWUnsteady's remove_particles_* runtime functions, src/FLOWUnsteady_processing.jl:50-187) as a
+//      stream compaction that reproduces the ORDER the reference's sequential loop leaves behind.  That loop walks
+//      i = np..1 and vpm.remove_particle(i) moves the current last particle into slot i.  Tracking one survivor through
+//      it: its index inside the list of survivors above the cursor grows by one per step and wraps to 0 exactly when it
+//      is the last element and the cursor sits on a removed slot — it then lands in that hole.  With R(p) = removed slots
+//      below p and C(p) = survivors at or above p, a particle (virtually) inserted at p next wraps at the removed slot of
+//      ascending rank R(p) - C(p), or never if that is negative.  The final slot is the fixed point of that map, found by
+//      pointer doubling (tests replay the reference loop line by line).
+struct RemoveCriterion {
+    int kind;          // VPMB200_REMOVE_*
+    double p[9];
+};
+
+__global__ void keep_flags_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, RemoveCriterion c, int* __restrict__ keep) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool k = true;
+    if (c.kind == VPMB200_REMOVE_STRENGTH) {          // keep iff minGamma2 <= |Gamma|^2 <= maxGamma2   (:52-56)
+        double g0 = VPM_P(F_GAMMA), g1 = VPM_P(F_GAMMA + 1), g2 = VPM_P(F_GAMMA + 2);
+        double m = g0 * g0 + g1 * g1 + g2 * g2;
+        k = (c.p[0] <= m) && (m <= c.p[1]);
+    } else if (c.kind == VPMB200_REMOVE_SIGMA) {      // keep iff minsigma <= sigma <= maxsigma        (:98-100)
+        double sg = VPM_P(F_SIGMA);
+        k = (c.p[0] <= sg) && (sg <= c.p[1]);
+    } else if (c.kind == VPMB200_REMOVE_BOX) {        // remove if X - O is outside [Pmin, Pmax]       (:130-138)
+        double x = VPM_P(F_X) - c.p[6], y = VPM_P(F_X + 1) - c.p[7], z = VPM_P(F_X + 2) - c.p[8];
+        k = !((x < c.p[0] || x > c.p[3]) || (y < c.p[1] || y > c.p[4]) || (z < c.p[2] || z > c.p[5]));
+    } else if (c.kind == VPMB200_REMOVE_SPHERE) {     // remove if |X - centre|^2 > Rsphere2            (:171-178)
+        double x = VPM_P(F_X) - c.p[1], y = VPM_P(F_X + 1) - c.p[2], z = VPM_P(F_X + 2) - c.p[3];
+        k = !(x * x + y * y + z * z > c.p[0]);
+    }
+    keep[i] = k ? 1 : 0;
+}
+
+// removed slots listed by ascending rank
+__global__ void list_removed_kernel(const int* __restrict__ keep, const int* __restrict__ kept_before, int64_t n,
+                                    int* __restrict__ removedpos) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !keep[i]) removedpos[i - kept_before[i]] = (int)i;
+}
+
+// f(p): the hole a particle inserted at p falls into next (p itself when it never wraps again)
+__global__ void wrap_map_kernel(const int* __restrict__ kept_before, int64_t n, int64_t K, const int* __restrict__ removedpos,
+                                int* __restrict__ f) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t R = p - kept_before[p], C = K - kept_before[p];
+    f[p] = R - C >= 0 ? removedpos[R - C] : (int)p;
+}
+
+__global__ void wrap_double_kernel(const int* __restrict__ f, int64_t n, int* __restrict__ g, int* __restrict__ changed) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int a = f[p], b = f[a];
+    g[p] = b;
+    if (a != b) *changed = 1;
+}
+
+// survivors move to their final slot (destinations are holes or the particle's own slot: no read/write overlap)
+__global__ void move_survivors_kernel(double* __restrict__ soa, int64_t ld, const int* __restrict__ keep, int64_t n,
+                                      const int* __restrict__ dest) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const int64_t d = dest[i];
+    if (d == i) return;
+    for (int f = 0; f < NFIELDS; ++f) soa[(size_t)f * ld + d] = soa[(size_t)f * ld + i];
+}
+
+// ---- monitors: per-block partial sums (fixed order) of the quantities vpm.monitor_enstrophy / vpm.monitor_Cd report
+//      (src/FLOWUnsteady_monitors.jl:614,697).  out[block * 8 + k]: 0 enstrophy 0.5 sum Gamma.omega, 1 sum C_d over
+//      particles with C_d != 0, 2 sum C_d^2, 3 count C_d != 0, 4 number of static particles, 5 sum |Gamma|, 6, 7 unused.
+__global__ void monitor_partials_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, double* __restrict__ out) {
+    __shared__ double red[8][8];
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double g0 = VPM_P(F_GAMMA), g1 = VPM_P(F_GAMMA + 1), g2 = VPM_P(F_GAMMA + 2);
+        double w0 = VPM_P(F_J + 5) - VPM_P(F_J + 7), w1 = VPM_P(F_J + 6) - VPM_P(F_J + 2), w2 = VPM_P(F_J + 1) - VPM_P(F_J + 3);
+        v[0] += 0.5 * (g0 * w0 + g1 * w1 + g2 * w2);
+        double C = VPM_P(F_C);
+        if (C != 0) { v[1] += C; v[2] += C * C; v[3] += 1.0; }
+        if (VPM_P(F_STATIC) > 0) v[4] += 1.0;
+        v[5] += sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 6; ++c) red[c][threadIdx.x >> 5] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double m = 0.0;
+        if (threadIdx.x < 6)
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m += red[threadIdx.x][k];
+        out[blockIdx.x * 8 + threadIdx.x] = m;
+    }
+}
+
 #undef VPM_P
 
 }  // namespace vpm

@@ -139,6 +139,20 @@ class Engine:
     def remove_particle(self, i: int):
         self._check(self._L.vpmb200_remove_particle(self._h, int(i)))
 
+    REMOVE_STRENGTH, REMOVE_SIGMA, REMOVE_BOX, REMOVE_SPHERE = 1, 2, 3, 4
+
+    def remove_where(self, criterion: int, params) -> int:
+        """Wake treatment on the device (include/vpmb200.h: vpmb200_remove_where); returns the number removed."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        r = C.c_int64()
+        self._check(self._L.vpmb200_remove_where(self._h, int(criterion), p.ctypes.data, C.byref(r)))
+        return r.value
+
+    def monitors(self) -> dict:
+        out = (C.c_double * 6)()
+        self._check(self._L.vpmb200_monitors(self._h, out))
+        return dict(zip(("enstrophy", "Cd_mean", "Cd_std", "Cd_count", "n_static", "sum_abs_Gamma"), [float(v) for v in out]))
+
     # ---- hot path -------------------------------------------------------------------------------------
     def reset_particles(self):
         self._check(self._L.vpmb200_reset_particles(self._h))

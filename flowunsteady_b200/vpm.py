@@ -423,11 +423,35 @@ class ParticleField:
         self._engine.nextstep(dt, tuple(self.Uinf(self.t)), relax)
         self._pulled(_E.FM_ALL & ~(_E.FM_VOL | _E.FM_CIRCULATION | _E.FM_STATIC | _E.FM_VORTICITY))
 
+    # ---- wake treatments / monitors on the device ---------------------------------------------------------------
+    def remove_where(self, criterion: int, params) -> int:
+        """Device-side compaction with the reference's resulting particle order (vpmb200_remove_where)."""
+        if self.np == 0:
+            return 0
+        self._push(_E.FM_ALL)
+        removed = self._engine.remove_where(criterion, params)
+        self.np = self._engine.np
+        if removed:
+            self._pulled(_E.FM_ALL)
+        return removed
+
+    def monitors(self) -> dict:
+        """Enstrophy and C_d statistics reduced on the device (vpm.monitor_enstrophy / vpm.monitor_Cd)."""
+        self._push(_E.FM_ALL)
+        return self._engine.monitors()
+
     # ---- probes: Vvpm_on_Xs without evaluating every target (simulation.jl:494-570) -------------------------------
     def U_at(self, Xs, want_J: bool = False):
         self._engine.set_schemes(self._schemes(_E.UJ_IDS["direct"]))
         self._push(_E.FM_STATE)
         return self._engine.uj_probe(np.asarray(Xs, dtype=np.float64), want_J)
+
+    def fluiddomain(self, Xs):
+        """U and W = curl u at arbitrary nodes (what vpm.computefluiddomain evaluates on its grids,
+        examples/rotorhover/rotorhover_fluiddomain.jl:93-104): probes only, the field's own targets are not touched."""
+        Uo, Jo = self.U_at(Xs, want_J=True)
+        W = np.stack([Jo[:, 5] - Jo[:, 7], Jo[:, 6] - Jo[:, 2], Jo[:, 1] - Jo[:, 3]], -1)
+        return Uo, W
 
     @property
     def engine(self) -> Engine:

@@ -148,6 +148,22 @@ int32_t vpmb200_get_np(vpmb200_handle h, int64_t* np);
 int32_t vpmb200_add_particles(vpmb200_handle h, const double* cols, int64_t ld, int64_t n);
 int32_t vpmb200_remove_particle(vpmb200_handle h, int64_t i);
 
+/* Wake treatments — FLOWUnsteady's remove_particles_strength / _sigma / _box / _sphere runtime functions
+ * (src/FLOWUnsteady_processing.jl:50-187) as one device-side compaction.  The surviving particles end up in exactly the
+ * order the reference's loop (i = np..1, vpm.remove_particle(i) = move the last particle into slot i) produces.
+ *   STRENGTH: params = { minGamma2, maxGamma2 }                      keep iff min <= |Gamma|^2 <= max
+ *   SIGMA   : params = { minsigma, maxsigma }                        keep iff min <= sigma <= max
+ *   BOX     : params = { Pmin[3], Pmax[3], O[3] }                    remove if X - O lies outside the box
+ *   SPHERE  : params = { Rsphere2, centre[3] }                       remove if |X - centre|^2 > Rsphere2
+ * *removed receives the number of particles removed. */
+enum { VPMB200_REMOVE_STRENGTH = 1, VPMB200_REMOVE_SIGMA = 2, VPMB200_REMOVE_BOX = 3, VPMB200_REMOVE_SPHERE = 4 };
+int32_t vpmb200_remove_where(vpmb200_handle h, int32_t criterion, const double* params, int64_t* removed);
+
+/* Monitors (vpm.monitor_enstrophy, vpm.monitor_Cd; src/FLOWUnsteady_monitors.jl:614,697): out[0] = enstrophy
+ * 0.5 sum Gamma.omega (omega = curl u from J), out[1] = mean C_d over particles with C_d != 0, out[2] = its standard
+ * deviation, out[3] = number of particles with C_d != 0, out[4] = number of static particles, out[5] = sum |Gamma|. */
+int32_t vpmb200_monitors(vpmb200_handle h, double* out6);
+
 /* vpm._reset_particles: U, J, PSE <- 0.   _reset_particles_sfs: SFS <- 0. */
 int32_t vpmb200_reset_particles(vpmb200_handle h);
 int32_t vpmb200_reset_particles_sfs(vpmb200_handle h);

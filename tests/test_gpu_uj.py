@@ -137,3 +137,53 @@ def test_empty_field_and_errors():
         assert ei.value.code == -4       # VPMB200_ECAPACITY
         with pytest.raises(fb.EngineError):
             eng.set_schemes(fb.default_schemes(kernel=7))
+
+
+@pytest.mark.parametrize("rows", [100, 400])
+def test_config1_wing_wake_full_parity(rows):
+    """BASELINE configs[0] (examples/wing stand-in, N = 10,100 and 40,400): every target against the oracle."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    from oracle import oracle as o
+    x, g, s = fields.wing_wake(rows=rows)
+    U, J, _ = _run_uj(fb.new_particles(x, g, s), "gaussianerf")
+    Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x, accum=1)
+    assert relmax(U, Uo) < TOL64
+    assert relmax(J, Jo) < TOL64
+
+
+def test_config2_rotor_wake_sampled_parity():
+    """BASELINE configs[1] (examples/rotorhover stand-in, N = 70k mid-low): 2048 sampled targets against the oracle,
+    with and without the engine's internal Morton ordering (both must agree with the oracle and with each other)."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import engine as E, fields
+    from oracle import oracle as o
+    x, g, s = fields.rotor_wake(70_000)
+    P = fb.new_particles(x, g, s)
+    idx = np.random.default_rng(1234).choice(x.shape[0], 2048, replace=False)
+    Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x[idx], accum=1)
+    outs = []
+    for srt in (1, 0):
+        with fb.Engine(P.shape[0], schemes=fb.default_schemes()) as eng:
+            eng.set_option("direct_sort", srt)
+            eng.upload(P)
+            eng.uj()
+            out = eng.download(np.zeros_like(P))
+        assert relmax(out[idx, E.U:E.U + 3], Uo) < TOL64
+        assert relmax(out[idx, E.J:E.J + 9], Jo) < TOL64
+        outs.append(out)
+    assert relmax(outs[0][:, E.U:E.U + 12], outs[1][:, E.U:E.U + 12]) < 1e-13
+
+
+def test_probe_set_uses_split_geometry():
+    """A handful of probes against 100k sources (Vvpm_on_Xs, simulation.jl:494-570): one target block, many chunks."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    from oracle import oracle as o
+    x, g, s = fields.vortex_rings(100_000)
+    probes = np.random.default_rng(5).random((37, 3)) * 2 - 0.5
+    with fb.Engine(x.shape[0], schemes=fb.default_schemes()) as eng:
+        eng.upload(fb.new_particles(x, g, s))
+        Up, Jp = eng.uj_probe(probes, want_J=True)
+    Uo, Jo = o.uj_direct("gaussianerf", x, g, s, probes, accum=1)
+    assert relmax(Up, Uo) < TOL64 and relmax(Jp, Jo) < TOL64
