@@ -61,6 +61,7 @@ SYMBOLS = {
     "vpmb200_device_field": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "vpmb200_stream": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
     "vpmb200_synchronize": (C.c_int32, [_H]),
+    "vpmb200_fmm_global": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "vpmb200_set_option": (C.c_int32, [_H, C.c_char_p, C.c_int64]),
     "vpmb200_fmm_stats": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "vpmb200_launch_count": (C.c_int32, [_H, C.POINTER(C.c_uint64)]),

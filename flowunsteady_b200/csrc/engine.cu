@@ -319,6 +319,57 @@ int32_t do_uj_direct_sorted(vpmb200_engine* e, int reset, int sfs) {
     return VPMB200_OK;
 }
 
+int32_t check_fmm_settings(vpmb200_engine* e) {
+    const vpmb200_schemes& s = e->sch;
+    if (s.fmm_p < 2 || s.fmm_p > 6) return fail(e, VPMB200_ENOTSUP, "FMM expansion order p must be in 2..6");
+    if (s.fmm_ncrit < 1 || s.fmm_ncrit > FMM_MAX_NCRIT) return fail(e, VPMB200_EINVAL, "FMM ncrit must be in 1..256");
+    if (!(s.fmm_theta > 0.0 && s.fmm_theta < 1.0)) return fail(e, VPMB200_EINVAL, "FMM theta must be in (0, 1)");
+    if (e->float_bits != 64) return fail(e, VPMB200_ENOTSUP, "UJ_fmm runs in FP64 only");
+    return VPMB200_OK;
+}
+
+// Multi-GPU FMM building block: G is a 24-row mini-state (rows as in the particle record: X 0:3, Gamma 3:6, sigma 6, U 9:12,
+// J 15:24; rows 12:15 double as E_str scratch) holding ALL ntot particles of the job.  Every rank builds the same tree
+// (deterministic) and evaluates only its share of the leaves; rows outside its share are written as zeros so the ranks'
+// results combine with one all-reduce.  pass 0: tree + U, J.   pass 1: near-field E_str from the (reduced) J rows.
+int32_t do_fmm_global(vpmb200_engine* e, double* G, int64_t ldg, int64_t ntot, int part, int nparts, int pass) {
+    const vpmb200_schemes& s = e->sch;
+    int32_t rc = check_fmm_settings(e);
+    if (rc) return rc;
+    if (ntot <= 0) return VPMB200_OK;
+    if (ntot > 2000000000LL) return fail(e, VPMB200_ECAPACITY, "UJ_fmm indexes particles with 32-bit integers");
+    std::string err;
+    if (fmm_reserve(e->fmm, ntot, s.fmm_ncrit, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    FmmWorkspace& w = e->fmm;
+    const int block = 32;
+    const unsigned nb = blocks_for(ntot, PK_BT);
+    if (pass == 0) {
+        cudaError_t st = fmm_build(w, G, ldg, ntot, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream,
+                                   e->launches, err);
+        if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
+        w.leaf_lo = (int)((int64_t)w.nleaves * part / nparts);
+        w.leaf_hi = (int)((int64_t)w.nleaves * (part + 1) / nparts);
+        CU_TRY(e, cudaMemsetAsync(w.sU, 0, sizeof(double) * 3 * w.lds, e->stream));
+        CU_TRY(e, cudaMemsetAsync(w.sJ, 0, sizeof(double) * 9 * w.lds, e->stream));
+        CU_TRY(e, fmm_evaluate(w, s.fmm_p, s.kernel, block, e->gh_table, e->fmm_lvl, e->stream, e->launches));
+        fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sU, w.lds, 3, ntot, w.perm, G + (size_t)F_U * ldg, ldg, 0);
+        fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sJ, w.lds, 9, ntot, w.perm, G + (size_t)F_J * ldg, ldg, 0);
+        CU_TRY(e, cudaGetLastError());
+        e->launches += 2;
+    } else {
+        if (w.ncells <= 0 || w.nleaves <= 0) return fail(e, VPMB200_EINVAL, "fmm_global pass 1 needs pass 0 first");
+        fmm_gather_estr_kernel<<<nb, PK_BT, 0, e->stream>>>(G, ldg, ntot, w.perm, w.sJ, w.lds, s.transposed, zeta0_of(s.kernel), w.rec);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        CU_TRY(e, cudaMemsetAsync(w.sE, 0, sizeof(double) * 3 * w.lds, e->stream));
+        CU_TRY(e, fmm_estr(w, s.kernel, block, s.transposed, e->z_table, e->stream, e->launches));
+        fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sE, w.lds, 3, ntot, w.perm, G + (size_t)F_W * ldg, ldg, 0);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
+    return VPMB200_OK;
+}
+
 // pfield.UJ(pfield; reset, reset_sfs, sfs)
 int32_t do_uj(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     if (e->sch.uj == VPMB200_UJ_FMM) return do_uj_fmm(e, reset, reset_sfs, sfs);
@@ -874,6 +925,14 @@ int32_t vpmb200_stream(vpmb200_handle e, void** stream) {
     if (!stream) return fail(e, VPMB200_EINVAL, "stream is NULL");
     *stream = (void*)e->stream;
     return VPMB200_OK;
+}
+
+int32_t vpmb200_fmm_global(vpmb200_handle e, double* G, int64_t ldg, int64_t ntot, int32_t part, int32_t nparts, int32_t pass) {
+    CHECK_HANDLE(e);
+    if (!G || ldg < ntot || nparts < 1 || part < 0 || part >= nparts || pass < 0 || pass > 1)
+        return fail(e, VPMB200_EINVAL, "bad fmm_global arguments");
+    CU_TRY(e, cudaSetDevice(e->device));
+    return do_fmm_global(e, G, ldg, ntot, part, nparts, pass);
 }
 
 int32_t vpmb200_set_option(vpmb200_handle e, const char* name, int64_t value) {

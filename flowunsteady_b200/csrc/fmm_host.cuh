@@ -32,6 +32,7 @@ struct FmmWorkspace {
     size_t cub_bytes = 0;
     // statistics of the last evaluation
     int ncells = 0, nleaves = 0, nlevels = 0;
+    int leaf_lo = 0, leaf_hi = 0;   // leaves [leaf_lo, leaf_hi) are evaluated by the near-field / L2P kernels (multi-GPU split)
     unsigned int n_m2l = 0, n_p2p = 0;
 };
 
@@ -167,8 +168,10 @@ struct FmmPasses {
         auto kfn = fmm_leaf_uj_kernel<KERNEL, P>;
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kfn<<<(w.nleaves + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(
-            w.cells, w.leaves, w.nleaves, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
+        const int nl = w.leaf_hi - w.leaf_lo;
+        if (nl <= 0) return cudaSuccess;
+        kfn<<<(nl + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(
+            w.cells, w.leaves + w.leaf_lo, nl, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
         ++launches;
         return cudaGetLastError();
     }
@@ -285,6 +288,8 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     FMM_TRY(cudaMemcpyAsync(&lf, w.leaf_flag + ncells - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     FMM_TRY(cudaStreamSynchronize(st));
     w.nleaves = lp + lf;
+    w.leaf_lo = 0;
+    w.leaf_hi = w.nleaves;
     if (nzs_factor > 0.0) {   // largest core size per cell, leaves first then level by level upward
         fmm_smax_leaf_kernel<<<(ncells + 127) / 128, 128, 0, st>>>(w.cells, ncells, w.rec);
         ++launches;
@@ -375,9 +380,11 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
                             uint64_t& launches) {
     (void)block;
     const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)LEAF_BATCH * REC_REALS;
+    const int nl = w.leaf_hi - w.leaf_lo;
+    if (nl <= 0) return cudaSuccess;
 #define FMM_ESTR_CASE(K)                                                                                                   \
-    fmm_leaf_estr_kernel<K><<<(w.nleaves + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(                     \
-        w.cells, w.leaves, w.nleaves, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
+    fmm_leaf_estr_kernel<K><<<(nl + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(                            \
+        w.cells, w.leaves + w.leaf_lo, nl, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
     switch (kernel) {
     case K_GAUSSIANERF: FMM_ESTR_CASE(K_GAUSSIANERF); break;
     case K_WINCKELMANS: FMM_ESTR_CASE(K_WINCKELMANS); break;

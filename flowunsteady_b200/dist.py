@@ -23,6 +23,13 @@ from . import engine as _E
 RK3 = ((0.0, 1.0 / 3.0), (-5.0 / 9.0, 15.0 / 16.0), (-153.0 / 128.0, 8.0 / 15.0))
 
 
+class _DevArray:
+    """Raw CUDA pointer -> torch (via __cuda_array_interface__); the engine keeps ownership."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
 def partition(n: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous index ranges, sizes differing by at most one particle."""
     base, rem = divmod(int(n), int(world))
@@ -103,9 +110,64 @@ class ShardedField:
                     if r != self.rank and self._ntiles[r] > 0:
                         apply_rest(self._slot_ptr(r), self._ntiles[r])
 
+    # ---- UJ_fmm over the sharded field: replicated tree, leaves split over the ranks ---------------------------------
+    def _uj_fmm(self, reset: bool, reset_sfs: bool, sfs: bool):
+        """All ranks gather (X, Gamma, sigma) of every particle (56 B each), build the SAME tree, evaluate 1/world of the
+        leaves (near field + L2P are > 85 % of the evaluation), and combine with one all-reduce of the U, J rows (the
+        rows of particles outside a rank's share are zeros).  E_str: a second near-field pass + all-reduce."""
+        if sfs and not reset:
+            raise NotImplementedError("sharded UJ_fmm with sfs=True needs reset=True (what every SFS scheme calls)")
+        b, dev = self.b, self.device
+        n_loc = int(b.np)
+        cnt = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        cnt[self.rank] = n_loc
+        if self.world > 1:
+            dist.all_reduce(cnt, group=self.group)
+        counts = [int(v) for v in cnt.tolist()]
+        ntot, slot = sum(counts), max(max(counts), 1)
+        off = sum(counts[:self.rank])
+        ptr, ld = b.device_field(0)
+        with self._stream_ctx():
+            state = torch.as_tensor(_DevArray(ptr, (43, ld)), device=dev)
+            ldg = (ntot + 31) // 32 * 32
+            if getattr(self, "_G", None) is None or self._G.shape[1] < ldg:
+                self._G = torch.zeros((24, ldg), dtype=torch.float64, device=dev)
+            G = self._G
+            send = torch.zeros((7, slot), dtype=torch.float64, device=dev)
+            send[:, :n_loc] = state[0:7, :n_loc]
+            if self.world > 1:
+                recv = torch.empty((self.world, 7, slot), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+                o = 0
+                for r, c in enumerate(counts):
+                    G[0:7, o:o + c] = recv[r, :, :c]
+                    o += c
+            else:
+                G[0:7, :n_loc] = send[:, :n_loc]
+            b.fmm_global(G.data_ptr(), G.shape[1], ntot, self.rank, self.world, 0)
+            if self.world > 1:
+                dist.all_reduce(G[9:24], group=self.group)
+            mine = slice(off, off + n_loc)
+            if reset:
+                state[9:12, :n_loc] = G[9:12, mine]
+                state[15:24, :n_loc] = G[15:24, mine]
+                state[24:27, :n_loc] = 0.0
+            else:
+                state[9:12, :n_loc] += G[9:12, mine]
+                state[15:24, :n_loc] += G[15:24, mine]
+            if reset_sfs:
+                state[39:42, :n_loc] = 0.0
+            if sfs:
+                b.fmm_global(G.data_ptr(), G.shape[1], ntot, self.rank, self.world, 1)
+                if self.world > 1:
+                    dist.all_reduce(G[12:15], group=self.group)
+                state[39:42, :n_loc] += G[12:15, mine]
+
     # ---- pfield.UJ(pfield; reset, reset_sfs, sfs) -------------------------------------------------------------------
     def uj(self, reset: bool = True, reset_sfs: bool = False, sfs: bool = False):
         b = self.b
+        if b.get_schemes().uj == _E.UJ_IDS["fmm"]:
+            return self._uj_fmm(reset, reset_sfs, sfs)
         if reset:
             b.reset_particles()        # U, J, PSE <- 0 (the pair kernel then accumulates chunk by chunk)
         if reset_sfs:

@@ -200,6 +200,9 @@ class Engine:
         self._check(self._L.vpmb200_stream(self._h, C.byref(s)))
         return s.value or 0
 
+    def fmm_global(self, G_ptr: int, ldg: int, ntot: int, part: int, nparts: int, pass_: int):
+        self._check(self._L.vpmb200_fmm_global(self._h, C.c_void_p(G_ptr), int(ldg), int(ntot), int(part), int(nparts), int(pass_)))
+
     def set_option(self, name: str, value: int):
         self._check(self._L.vpmb200_set_option(self._h, name.encode(), int(value)))
 

@@ -215,6 +215,13 @@ int32_t vpmb200_pack_estr_records(vpmb200_handle h, double* dst);
  * adds to the current U, J.  The E_str variant always accumulates into SFS. */
 int32_t vpmb200_uj_from_records(vpmb200_handle h, const double* tiles, int64_t ntiles, int32_t accumulate);
 int32_t vpmb200_estr_from_records(vpmb200_handle h, const double* tiles, int64_t ntiles);
+/* Multi-GPU UJ_fmm building block.  G (device) is a 24-row "mini-state" of ALL ntot particles of the job, row r of
+ * particle i at G[r * ldg + i] with the particle record's row numbering (X 0:3, Gamma 3:6, sigma 6 filled by the caller;
+ * U 9:12 and J 15:24 written by pass 0; rows 12:15 receive E_str in pass 1, which reads the J rows).  Every rank builds
+ * the same tree and evaluates leaves [part, part+1) / nparts; rows of particles outside its share are written as zeros,
+ * so the ranks' outputs combine with one all-reduce (flowunsteady_b200/dist.py). */
+int32_t vpmb200_fmm_global(vpmb200_handle h, double* G, int64_t ldg, int64_t ntot, int32_t part, int32_t nparts, int32_t pass);
+
 /* The per-particle stages of pfield.SFS / nextstep, exposed so a sharded driver can interleave its exchange:
  * stage ids in vpmb200_stage. */
 enum {
