@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", dest="n", type=int, default=1_000_000, help="particles (BASELINE config: 1M)")
     ap.add_argument("--sfs", default="none", choices=["none", "dynamic"], help="SFS scheme of the timed step")
+    ap.add_argument("--uj", default="direct", choices=["direct", "fmm"],
+                    help="direct = headline (BASELINE configs[2]); fmm = secondary mode (configs[1]/[3]): UJ_fmm p=4 ncrit=50 theta=0.4")
+    ap.add_argument("--field", default="rings", choices=["rings", "rotor", "random"], help="synthetic field generator")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fmm", action="store_true", help="skip the secondary UJ_fmm figures")
@@ -93,8 +96,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_field(n: int):
+def make_field(n: int, kind: str = "rings"):
     from flowunsteady_b200 import fields
+    if kind == "rotor":
+        return fields.rotor_wake(n, nfil=101, nsteps_per_rev=72)
+    if kind == "random":
+        return fields.random_field(n)
     return fields.vortex_rings(n)
 
 
@@ -106,8 +113,8 @@ def run_reference(args):
         return
     from oracle import oracle as o
     o.build()
-    n = args.n
-    x, g, s = make_field(n)
+    x, g, s = make_field(args.n, args.field)
+    n = x.shape[0]
     m = 1024                                                   # bounded sample: targets per evaluation
     idx = np.random.default_rng(1234).choice(n, m, replace=False)
     xt = np.ascontiguousarray(x[idx])
@@ -173,12 +180,13 @@ def run_ours(args):
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
 
     n = args.n
-    x, g, s = make_field(n)
+    x, g, s = make_field(n, args.field)
+    n = x.shape[0]
     lo, hi = partition(n, world)[rank]
     P_local = fb.new_particles(x[lo:hi], g[lo:hi], s[lo:hi])
-    sch = fb.default_schemes(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti", uj="direct")
+    sch = fb.default_schemes(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti", uj=args.uj)
     if args.sfs == "dynamic":   # SFS_Cd_twolevel_nobackscatter (rotorhover high fidelity, rotorhover.jl:53-55)
-        sch = fb.default_schemes(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti", uj="direct",
+        sch = fb.default_schemes(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti", uj=args.uj,
                                  sfs="dynamic", alpha=0.999, force_positive=1, clippings=1)
     evals = EVALS_PER_STEP[args.sfs]
     dt_sim, Uinf = 1.0e-3, (0.0, 0.0, 0.0)
@@ -229,6 +237,23 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = evals * float(n) * float(n) / (ms_per_step * 1e-3)
+    if args.uj == "fmm":
+        # secondary mode: an O(N) method has no pair count; report particle-evaluations per second and stop here
+        if rank == 0:
+            print(json.dumps({
+                "metric": "particle U/J evaluations per second (UJ_fmm step: RK3 + pedrizzetti%s)" % (
+                    " + dynamic SFS" if args.sfs == "dynamic" else ""),
+                "value": evals * float(n) / (ms_per_step * 1e-3), "unit": "particle-evaluations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "s_per_timestep": ms_per_step * 1e-3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.field} field, UJ_fmm p=4 ncrit=50 theta=0.4 nonzero_sigma=false, gaussianerf, rVPM",
+                           "particles": n, "sfs": args.sfs, "evaluations_per_step": evals,
+                           "parallelism": f"replicated tree, leaves split over {world} GPU(s)"},
+                "gpu_launches": int(launches), "clocks": clocks, "fmm_tree": eng.fmm_stats()}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- dominant kernel alone: one U/J evaluation (K1 + its pack kernel) ---------------------------------------------
     k1_reps = 3

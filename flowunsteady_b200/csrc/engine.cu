@@ -345,10 +345,8 @@ int32_t do_fmm_global(vpmb200_engine* e, double* G, int64_t ldg, int64_t ntot, i
     const unsigned nb = blocks_for(ntot, PK_BT);
     if (pass == 0) {
         cudaError_t st = fmm_build(w, G, ldg, ntot, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream,
-                                   e->launches, err);
+                                   e->launches, err, part, nparts);
         if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
-        w.leaf_lo = (int)((int64_t)w.nleaves * part / nparts);
-        w.leaf_hi = (int)((int64_t)w.nleaves * (part + 1) / nparts);
         CU_TRY(e, cudaMemsetAsync(w.sU, 0, sizeof(double) * 3 * w.lds, e->stream));
         CU_TRY(e, cudaMemsetAsync(w.sJ, 0, sizeof(double) * 9 * w.lds, e->stream));
         CU_TRY(e, fmm_evaluate(w, s.fmm_p, s.kernel, block, e->gh_table, e->fmm_lvl, e->stream, e->launches));

@@ -311,7 +311,7 @@ __device__ __forceinline__ void push_pair(uint64_t* __restrict__ list, unsigned 
 __global__ void fmm_traverse_kernel(const FmmCell* __restrict__ cells, const uint64_t* __restrict__ frontier, unsigned int nfront,
                                     double theta, double nzs_factor, uint64_t* __restrict__ next, unsigned int cap_next, uint64_t* __restrict__ m2l,
                                     unsigned int cap_m2l, uint64_t* __restrict__ p2p, unsigned int cap_p2p,
-                                    FmmCounters* __restrict__ cnt) {
+                                    FmmCounters* __restrict__ cnt, const int* __restrict__ mine) {
     unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nfront) return;
     const int pi = (int)(frontier[t] >> 32), pj = (int)(frontier[t] & 0xffffffffu);
@@ -328,7 +328,9 @@ __global__ void fmm_traverse_kernel(const FmmCell* __restrict__ cells, const uin
     } else if (ci.nchild == 0 && cj.nchild == 0) {
         push_pair(p2p, &cnt->p2p, cap_p2p, &cnt->overflow, pi, cj.start);   // low word: first particle of the source leaf
     } else if (cj.nchild == 0 || (ci.nchild != 0 && ci.R >= cj.R)) {
-        for (int k = 0; k < ci.nchild; ++k) push_pair(next, &cnt->next, cap_next, &cnt->overflow, ci.child0 + k, pj);
+        // multi-GPU: only target cells with one of this rank's leaves below them are followed (`mine`, nullptr = all)
+        for (int k = 0; k < ci.nchild; ++k)
+            if (!mine || mine[ci.child0 + k]) push_pair(next, &cnt->next, cap_next, &cnt->overflow, ci.child0 + k, pj);
     } else {
         for (int k = 0; k < cj.nchild; ++k) push_pair(next, &cnt->next, cap_next, &cnt->overflow, pi, cj.child0 + k);
     }
@@ -567,6 +569,36 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
             sE[1 * lds + i] = e1 - a.b1;
             sE[2 * lds + i] = e2 - a.b2;
         }
+    }
+}
+
+// Leaves in Morton order: key = first particle of the leaf.
+__global__ void fmm_leaf_starts_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves,
+                                       int* __restrict__ starts) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nleaves) starts[k] = cells[leaves[k]].start;
+}
+
+// First leaf (Morton order) whose first particle is >= target, for the two ends of a rank's share.
+__global__ void fmm_leaf_range_kernel(const int* __restrict__ starts, int nleaves, int p_lo, int p_hi, int* __restrict__ out) {
+    if (threadIdx.x >= 2) return;
+    const int v = threadIdx.x == 0 ? p_lo : p_hi;
+    int lo = 0, hi = nleaves;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (starts[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    out[threadIdx.x] = lo;
+}
+
+// mine[c] = 1 for every cell that is one of the given leaves or an ancestor of one
+__global__ void fmm_flag_owned_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nl, int* __restrict__ mine) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nl) return;
+    int c = leaves[k];
+    while (c >= 0 && !mine[c]) {   // benign race: several leaves may mark the same ancestor
+        mine[c] = 1;
+        c = cells[c].parent;
     }
 }
 

@@ -26,6 +26,7 @@ struct FmmWorkspace {
     unsigned int *m2l_off = nullptr, *p2p_off = nullptr;
     int2* runs = nullptr;          // particle range of every sorted P2P entry
     int* count_at = nullptr;       // leaf particle count, indexed by the leaf's first particle
+    int *mine = nullptr, *leaf_keys = nullptr, *leaf_keys_alt = nullptr, *leaves_alt = nullptr;  // multi-GPU ownership
     FmmCounters* counters = nullptr;
     double* bounds = nullptr;
     void* cub_tmp = nullptr;
@@ -39,7 +40,8 @@ struct FmmWorkspace {
 inline void fmm_free(FmmWorkspace& w) {
     void* ptrs[] = {w.keys, w.keys_alt, w.perm, w.perm_alt, w.sx, w.sy, w.sz, w.rec, w.sU, w.sJ, w.sE, w.cells, w.nchild,
                     w.child_off, w.leaf_flag, w.leaf_pos, w.leaves, w.M, w.L, w.front_a, w.front_b, w.m2l, w.m2l_sorted,
-                    w.p2p, w.p2p_sorted, w.m2l_off, w.p2p_off, w.counters, w.bounds, w.cub_tmp, w.runs, w.count_at};
+                    w.p2p, w.p2p_sorted, w.m2l_off, w.p2p_off, w.counters, w.bounds, w.cub_tmp, w.runs, w.count_at, w.mine,
+                    w.leaf_keys, w.leaf_keys_alt, w.leaves_alt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     w = FmmWorkspace();
@@ -76,12 +78,13 @@ inline cudaError_t fmm_alloc_pairs(FmmWorkspace& w, std::string& err) {
 inline cudaError_t fmm_alloc_cub(FmmWorkspace& w, std::string& err) {
     if (w.cub_tmp) cudaFree(w.cub_tmp);
     w.cub_tmp = nullptr;
-    size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+    size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b5, w.leaf_keys, w.leaf_keys_alt, w.leaves, w.leaves_alt, w.cap_cells);
     cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_alt, w.perm, w.perm_alt, (int)w.cap_n);
     cub::DeviceRadixSort::SortKeys(nullptr, b2, w.m2l, w.m2l_sorted, (int)w.cap_pairs);
     cub::DeviceRadixSort::SortKeys(nullptr, b3, w.p2p, w.p2p_sorted, (int)w.cap_p2p);
     cub::DeviceScan::ExclusiveSum(nullptr, b4, w.nchild, w.child_off, w.cap_cells);
-    w.cub_bytes = std::max(std::max(b1, b2), std::max(b3, b4));
+    w.cub_bytes = std::max(std::max(std::max(b1, b2), std::max(b3, b4)), b5);
     FMM_TRY(cudaMalloc(&w.cub_tmp, w.cub_bytes));
     return cudaSuccess;
 }
@@ -114,6 +117,10 @@ inline cudaError_t fmm_reserve(FmmWorkspace& w, int64_t n, int ncrit, int PLmax_
     FMM_TRY(cudaMalloc(&w.leaf_flag, sizeof(int) * cells));
     FMM_TRY(cudaMalloc(&w.leaf_pos, sizeof(int) * cells));
     FMM_TRY(cudaMalloc(&w.leaves, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.leaves_alt, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.leaf_keys, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.leaf_keys_alt, sizeof(int) * cells));
+    FMM_TRY(cudaMalloc(&w.mine, sizeof(int) * cells));
     w.ml_doubles_M = (size_t)cells * 3 * PLmax_terms_NM;
     w.ml_doubles_L = (size_t)cells * 3 * PLmax_terms_NL;
     FMM_TRY(cudaMalloc(&w.M, sizeof(double) * w.ml_doubles_M));
@@ -233,7 +240,8 @@ inline cudaError_t fmm_sort(FmmWorkspace& w, const double* soa, int64_t ld, int6
 
 // Build the adaptive octree and the interaction lists for the particles of the field.
 inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, int ncrit, double theta,
-                             double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err) {
+                             double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err,
+                             int part = 0, int nparts = 1) {
     FmmRoot rt;
     {
         cudaError_t e0 = fmm_sort(w, soa, ld, n, st, launches, err, &rt);
@@ -290,6 +298,28 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     w.nleaves = lp + lf;
     w.leaf_lo = 0;
     w.leaf_hi = w.nleaves;
+    const int* mine = nullptr;
+    if (nparts > 1) {
+        // leaves in Morton order; this rank takes the leaves covering particles [part, part + 1) * n / nparts of that order
+        // and marks them and their ancestors: only those target cells are traversed / receive M2L, L2L, L2P, P2P
+        fmm_leaf_starts_kernel<<<(w.nleaves + 255) / 256, 256, 0, st>>>(w.cells, w.leaves, w.nleaves, w.leaf_keys);
+        tb = w.cub_bytes;
+        FMM_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.leaf_keys, w.leaf_keys_alt, w.leaves, w.leaves_alt, w.nleaves, 0, 32, st));
+        std::swap(w.leaf_keys, w.leaf_keys_alt);
+        std::swap(w.leaves, w.leaves_alt);
+        const int p_lo = (int)(n * part / nparts), p_hi = (int)(n * (part + 1) / nparts);
+        fmm_leaf_range_kernel<<<1, 32, 0, st>>>(w.leaf_keys, w.nleaves, p_lo, p_hi, w.leaf_flag);
+        int range[2] = {0, 0};
+        FMM_TRY(cudaMemcpyAsync(range, w.leaf_flag, sizeof(range), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaStreamSynchronize(st));
+        w.leaf_lo = range[0];
+        w.leaf_hi = part == nparts - 1 ? w.nleaves : range[1];
+        FMM_TRY(cudaMemsetAsync(w.mine, 0, sizeof(int) * ncells, st));
+        if (w.leaf_hi > w.leaf_lo)
+            fmm_flag_owned_kernel<<<(w.leaf_hi - w.leaf_lo + 255) / 256, 256, 0, st>>>(w.cells, w.leaves + w.leaf_lo, w.leaf_hi - w.leaf_lo, w.mine);
+        launches += 4;
+        mine = w.mine;
+    }
     if (nzs_factor > 0.0) {   // largest core size per cell, leaves first then level by level upward
         fmm_smax_leaf_kernel<<<(ncells + 127) / 128, 128, 0, st>>>(w.cells, ncells, w.rec);
         ++launches;
@@ -310,7 +340,7 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
         hc = zero;
         while (nfront > 0) {
             fmm_traverse_kernel<<<(nfront + 255) / 256, 256, 0, st>>>(w.cells, fa, nfront, theta, nzs_factor, fb, w.cap_pairs, w.m2l,
-                                                                     w.cap_pairs, w.p2p, w.cap_p2p, w.counters);
+                                                                     w.cap_pairs, w.p2p, w.cap_p2p, w.counters, mine);
             ++launches;
             FMM_TRY(cudaMemcpyAsync(&hc, w.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
             FMM_TRY(cudaStreamSynchronize(st));
