@@ -743,7 +743,10 @@ int32_t vpmb200_remove_where(vpmb200_handle e, int32_t criterion, const double* 
     const unsigned nb = blocks_for(n, PK_BT);
     keep_flags_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, n, c, w.perm);
     CU_TRY(e, cudaGetLastError());
-    size_t tb = w.cub_bytes;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, w.perm, w.perm_alt, (int)n, e->stream);
+    if (fmm_cub(w, tb, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    tb = w.cub_bytes;
     CU_TRY(e, cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.perm, w.perm_alt, (int)n, e->stream));
     int last_scan = 0, last_flag = 0;
     CU_TRY(e, cudaMemcpyAsync(&last_scan, w.perm_alt + n - 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));

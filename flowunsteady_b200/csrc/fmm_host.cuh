@@ -56,6 +56,28 @@ inline void fmm_free(FmmWorkspace& w) {
         }                                                    \
     } while (0)
 
+template <typename T>
+inline cudaError_t fmm_grow(T*& ptr, size_t& have, size_t need, std::string& err) {
+    if (need <= have && ptr) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    have = 0;
+    FMM_TRY(cudaMalloc(&ptr, sizeof(T) * need));
+    have = need;
+    return cudaSuccess;
+}
+
+// CUB scratch grows on demand (each CUB call is first asked for its requirement).
+inline cudaError_t fmm_cub(FmmWorkspace& w, size_t bytes, std::string& err) {
+    if (bytes <= w.cub_bytes && w.cub_tmp) return cudaSuccess;
+    if (w.cub_tmp) cudaFree(w.cub_tmp);
+    w.cub_tmp = nullptr;
+    w.cub_bytes = 0;
+    FMM_TRY(cudaMalloc(&w.cub_tmp, bytes + 256));
+    w.cub_bytes = bytes + 256;
+    return cudaSuccess;
+}
+
 // (Re)allocate the pair-list buffers for the current cap_pairs / cap_p2p.
 inline cudaError_t fmm_alloc_pairs(FmmWorkspace& w, std::string& err) {
     void** ptrs[] = {(void**)&w.front_a, (void**)&w.front_b, (void**)&w.m2l, (void**)&w.m2l_sorted, (void**)&w.p2p,
@@ -74,31 +96,17 @@ inline cudaError_t fmm_alloc_pairs(FmmWorkspace& w, std::string& err) {
     return cudaSuccess;
 }
 
-// CUB scratch: the largest of the particle sort, the pair-key sorts and the scans
-inline cudaError_t fmm_alloc_cub(FmmWorkspace& w, std::string& err) {
-    if (w.cub_tmp) cudaFree(w.cub_tmp);
-    w.cub_tmp = nullptr;
-    size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b5, w.leaf_keys, w.leaf_keys_alt, w.leaves, w.leaves_alt, w.cap_cells);
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_alt, w.perm, w.perm_alt, (int)w.cap_n);
-    cub::DeviceRadixSort::SortKeys(nullptr, b2, w.m2l, w.m2l_sorted, (int)w.cap_pairs);
-    cub::DeviceRadixSort::SortKeys(nullptr, b3, w.p2p, w.p2p_sorted, (int)w.cap_p2p);
-    cub::DeviceScan::ExclusiveSum(nullptr, b4, w.nchild, w.child_off, w.cap_cells);
-    w.cub_bytes = std::max(std::max(std::max(b1, b2), std::max(b3, b4)), b5);
-    FMM_TRY(cudaMalloc(&w.cub_tmp, w.cub_bytes));
-    return cudaSuccess;
-}
-
-inline cudaError_t fmm_reserve(FmmWorkspace& w, int64_t n, int ncrit, int PLmax_terms_NM, int PLmax_terms_NL, std::string& err) {
-    if (n <= w.cap_n && w.cap_cells > 0 && (size_t)w.cap_cells * 3 * PLmax_terms_NL <= w.ml_doubles_L) return cudaSuccess;
-    fmm_free(w);
-    const int64_t cap_n = std::max<int64_t>(n, 1024);
-    int64_t cells = std::max<int64_t>(8192, 24 * cap_n / std::max(ncrit, 1));
-    cells = std::min<int64_t>(cells, 2 * cap_n + 16);
-    w.cap_n = cap_n;
-    w.cap_cells = (int)cells;
-    w.cap_pairs = (unsigned int)std::min<int64_t>(160 * cells, 1500000000LL);
-    w.cap_p2p = (unsigned int)std::min<int64_t>(96 * cells, 1500000000LL);
+// Particle-sized scratch (sort keys, Morton-ordered copies).  Used by the FMM, the sorted direct path and remove_where.
+inline cudaError_t fmm_reserve_particles(FmmWorkspace& w, int64_t n, std::string& err) {
+    if (n <= w.cap_n && w.keys) return cudaSuccess;
+    void* ptrs[] = {w.keys, w.keys_alt, w.perm, w.perm_alt, w.sx, w.sy, w.sz, w.rec, w.sU, w.sJ, w.sE, w.count_at};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    w.keys = w.keys_alt = nullptr;
+    w.perm = w.perm_alt = w.count_at = nullptr;
+    w.sx = w.sy = w.sz = w.rec = w.sU = w.sJ = w.sE = nullptr;
+    const int64_t cap_n = std::max<int64_t>(n + n / 8, 4096);
+    w.cap_n = 0;
     w.lds = (cap_n + 31) / 32 * 32;
     FMM_TRY(cudaMalloc(&w.keys, sizeof(uint64_t) * cap_n));
     FMM_TRY(cudaMalloc(&w.keys_alt, sizeof(uint64_t) * cap_n));
@@ -111,6 +119,24 @@ inline cudaError_t fmm_reserve(FmmWorkspace& w, int64_t n, int ncrit, int PLmax_
     FMM_TRY(cudaMalloc(&w.sU, sizeof(double) * 3 * w.lds));
     FMM_TRY(cudaMalloc(&w.sJ, sizeof(double) * 9 * w.lds));
     FMM_TRY(cudaMalloc(&w.sE, sizeof(double) * 3 * w.lds));
+    FMM_TRY(cudaMalloc(&w.count_at, sizeof(int) * cap_n));
+    if (!w.counters) FMM_TRY(cudaMalloc(&w.counters, sizeof(FmmCounters)));
+    if (!w.bounds) FMM_TRY(cudaMalloc(&w.bounds, sizeof(double) * 6 * 256));
+    w.cap_n = cap_n;
+    return cudaSuccess;
+}
+
+// Cell-sized arrays; `cells` is a capacity (the tree build restarts with a larger one if it is exceeded).
+inline cudaError_t fmm_reserve_cells(FmmWorkspace& w, int64_t cells, std::string& err) {
+    if (cells <= w.cap_cells && w.cells) return cudaSuccess;
+    void* ptrs[] = {w.cells, w.nchild, w.child_off, w.leaf_flag, w.leaf_pos, w.leaves, w.leaves_alt, w.leaf_keys,
+                    w.leaf_keys_alt, w.mine, w.m2l_off, w.p2p_off};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    w.cells = nullptr;
+    w.nchild = w.child_off = w.leaf_flag = w.leaf_pos = w.leaves = w.leaves_alt = w.leaf_keys = w.leaf_keys_alt = w.mine = nullptr;
+    w.m2l_off = w.p2p_off = nullptr;
+    w.cap_cells = 0;
     FMM_TRY(cudaMalloc(&w.cells, sizeof(FmmCell) * cells));
     FMM_TRY(cudaMalloc(&w.nchild, sizeof(int) * cells));
     FMM_TRY(cudaMalloc(&w.child_off, sizeof(int) * cells));
@@ -121,17 +147,15 @@ inline cudaError_t fmm_reserve(FmmWorkspace& w, int64_t n, int ncrit, int PLmax_
     FMM_TRY(cudaMalloc(&w.leaf_keys, sizeof(int) * cells));
     FMM_TRY(cudaMalloc(&w.leaf_keys_alt, sizeof(int) * cells));
     FMM_TRY(cudaMalloc(&w.mine, sizeof(int) * cells));
-    w.ml_doubles_M = (size_t)cells * 3 * PLmax_terms_NM;
-    w.ml_doubles_L = (size_t)cells * 3 * PLmax_terms_NL;
-    FMM_TRY(cudaMalloc(&w.M, sizeof(double) * w.ml_doubles_M));
-    FMM_TRY(cudaMalloc(&w.L, sizeof(double) * w.ml_doubles_L));
-    FMM_TRY(fmm_alloc_pairs(w, err));
     FMM_TRY(cudaMalloc(&w.m2l_off, sizeof(unsigned int) * (cells + 1)));
     FMM_TRY(cudaMalloc(&w.p2p_off, sizeof(unsigned int) * (cells + 1)));
-    FMM_TRY(cudaMalloc(&w.counters, sizeof(FmmCounters)));
-    FMM_TRY(cudaMalloc(&w.bounds, sizeof(double) * 6 * 256));
-    FMM_TRY(cudaMalloc(&w.count_at, sizeof(int) * cap_n));
-    return fmm_alloc_cub(w, err);
+    w.cap_cells = (int)cells;
+    return cudaSuccess;
+}
+
+// Back-compat entry used by the sort-only callers: particle scratch only.
+inline cudaError_t fmm_reserve(FmmWorkspace& w, int64_t n, int, int, int, std::string& err) {
+    return fmm_reserve_particles(w, n, err);
 }
 
 template <int P>
@@ -140,6 +164,9 @@ struct FmmPasses {
 
     static cudaError_t upward(FmmWorkspace& w, const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches) {
         cudaError_t e;
+        std::string err;
+        if ((e = fmm_grow(w.M, w.ml_doubles_M, (size_t)w.ncells * 3 * Ops::NM, err)) != cudaSuccess) return e;
+        if ((e = fmm_grow(w.L, w.ml_doubles_L, (size_t)w.ncells * 3 * Ops::NL, err)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(w.M, 0, sizeof(double) * (size_t)w.ncells * 3 * Ops::NM, st)) != cudaSuccess) return e;
         fmm_p2m_kernel<P><<<(w.ncells + 3) / 4, 128, 0, st>>>(w.cells, w.ncells, w.rec, w.M);
         ++launches;
@@ -229,7 +256,10 @@ inline cudaError_t fmm_sort(FmmWorkspace& w, const double* soa, int64_t ld, int6
     const unsigned nbk = (unsigned)((n + 255) / 256);
     fmm_keys_kernel<<<nbk, 256, 0, st>>>(X, Y, Z, n, x0, y0, z0, 2097152.0 / side, w.keys, w.perm);
     ++launches;
-    size_t tb = w.cub_bytes;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, w.keys, w.keys_alt, w.perm, w.perm_alt, (int)n, 0, 63, st);
+    FMM_TRY(fmm_cub(w, tb, err));
+    tb = w.cub_bytes;
     FMM_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys_alt, w.perm, w.perm_alt, (int)n, 0, 63, st));
     ++launches;
     std::swap(w.keys, w.keys_alt);
@@ -238,10 +268,22 @@ inline cudaError_t fmm_sort(FmmWorkspace& w, const double* soa, int64_t ld, int6
     return cudaSuccess;
 }
 
+#define FMM_CUB(call_with_tmp)                                              \
+    do {                                                                     \
+        size_t tb = 0;                                                       \
+        void* tmp = nullptr;                                                 \
+        (void)(call_with_tmp);                                               \
+        FMM_TRY(fmm_cub(w, tb, err));                                        \
+        tmp = w.cub_tmp;                                                     \
+        tb = w.cub_bytes;                                                    \
+        FMM_TRY(call_with_tmp);                                              \
+    } while (0)
+
 // Build the adaptive octree and the interaction lists for the particles of the field.
 inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, int ncrit, double theta,
                              double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err,
                              int part = 0, int nparts = 1) {
+    FMM_TRY(fmm_reserve_particles(w, n, err));
     FmmRoot rt;
     {
         cudaError_t e0 = fmm_sort(w, soa, ld, n, st, launches, err, &rt);
@@ -249,46 +291,54 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     }
     const double cx = rt.cx, cy = rt.cy, cz = rt.cz, side = rt.side;
     const unsigned nbk = (unsigned)((n + 255) / 256);
-    size_t tb = w.cub_bytes;
     fmm_gather_kernel<<<nbk, 256, 0, st>>>(soa, ld, n, w.perm, w.sx, w.sy, w.sz, w.rec);
     ++launches;
-    // ---- tree, level by level
-    FmmCell root;
-    root.start = 0; root.count = (int)n; root.parent = -1; root.child0 = -1; root.nchild = 0; root.level = 0;
-    root.cx = cx; root.cy = cy; root.cz = cz; root.R = 0.5 * side; root.smax = 0.0; root.pad_ = 0.0;
-    FMM_TRY(cudaMemcpyAsync(w.cells, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-    lvl.clear();
-    lvl.push_back(0);
-    lvl.push_back(1);
+    // ---- tree, level by level; the cell arrays start from an estimate and the build restarts if they are too small
+    if (w.cap_cells == 0) FMM_TRY(fmm_reserve_cells(w, std::max<int64_t>(8192, 6 * n / std::max(ncrit, 1)), err));
     int ncells = 1;
-    while (true) {
-        const int c0 = lvl[lvl.size() - 2], c1 = lvl.back();
-        const int nc = c1 - c0;
-        fmm_split_count_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.nchild);
-        tb = w.cub_bytes;
-        FMM_TRY(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.nchild, w.child_off, nc, st));
-        int last_off = 0, last_n = 0;
-        FMM_TRY(cudaMemcpyAsync(&last_off, w.child_off + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        FMM_TRY(cudaMemcpyAsync(&last_n, w.nchild + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        FMM_TRY(cudaStreamSynchronize(st));
-        const int nnew = last_off + last_n;
-        launches += 2;
-        if (ncells + nnew > w.cap_cells) {
-            err = "FMM: octree needs more cells than the workspace holds (extremely clustered particles?)";
+    for (int attempt = 0;; ++attempt) {
+        FmmCell root;
+        root.start = 0; root.count = (int)n; root.parent = -1; root.child0 = -1; root.nchild = 0; root.level = 0;
+        root.cx = cx; root.cy = cy; root.cz = cz; root.R = 0.5 * side; root.smax = 0.0; root.pad_ = 0.0;
+        FMM_TRY(cudaMemcpyAsync(w.cells, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+        lvl.clear();
+        lvl.push_back(0);
+        lvl.push_back(1);
+        ncells = 1;
+        bool overflow = false;
+        while (true) {
+            const int c0 = lvl[lvl.size() - 2], c1 = lvl.back();
+            const int nc = c1 - c0;
+            fmm_split_count_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.nchild);
+            FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, w.nchild, w.child_off, nc, st));
+            int last_off = 0, last_n = 0;
+            FMM_TRY(cudaMemcpyAsync(&last_off, w.child_off + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            FMM_TRY(cudaMemcpyAsync(&last_n, w.nchild + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            FMM_TRY(cudaStreamSynchronize(st));
+            const int nnew = last_off + last_n;
+            launches += 2;
+            if ((int64_t)ncells + nnew > w.cap_cells) {
+                overflow = true;
+                break;
+            }
+            fmm_split_emit_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.child_off, ncells);
+            ++launches;
+            if (nnew == 0) break;
+            ncells += nnew;
+            lvl.push_back(ncells);
+        }
+        if (!overflow) break;
+        if (attempt >= 8 || (int64_t)w.cap_cells * 2 > 2 * n + 64 * FMM_MAXLEVEL) {
+            err = "FMM: octree needs more cells than particles allow (corrupt positions?)";
             return cudaErrorMemoryAllocation;
         }
-        fmm_split_emit_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.child_off, ncells);
-        ++launches;
-        if (nnew == 0) break;
-        ncells += nnew;
-        lvl.push_back(ncells);
+        FMM_TRY(fmm_reserve_cells(w, (int64_t)w.cap_cells * 2, err));
     }
     w.ncells = ncells;
     w.nlevels = (int)lvl.size() - 1;
     // ---- leaves
     fmm_mark_leaves_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(w.cells, ncells, w.leaf_flag);
-    tb = w.cub_bytes;
-    FMM_TRY(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.leaf_flag, w.leaf_pos, ncells, st));
+    FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, w.leaf_flag, w.leaf_pos, ncells, st));
     fmm_collect_leaves_kernel<<<(ncells + 255) / 256, 256, 0, st>>>(w.leaf_flag, w.leaf_pos, ncells, w.leaves);
     launches += 3;
     int lp = 0, lf = 0;
@@ -303,8 +353,7 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
         // leaves in Morton order; this rank takes the leaves covering particles [part, part + 1) * n / nparts of that order
         // and marks them and their ancestors: only those target cells are traversed / receive M2L, L2L, L2P, P2P
         fmm_leaf_starts_kernel<<<(w.nleaves + 255) / 256, 256, 0, st>>>(w.cells, w.leaves, w.nleaves, w.leaf_keys);
-        tb = w.cub_bytes;
-        FMM_TRY(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.leaf_keys, w.leaf_keys_alt, w.leaves, w.leaves_alt, w.nleaves, 0, 32, st));
+        FMM_CUB(cub::DeviceRadixSort::SortPairs(tmp, tb, w.leaf_keys, w.leaf_keys_alt, w.leaves, w.leaves_alt, w.nleaves, 0, 32, st));
         std::swap(w.leaf_keys, w.leaf_keys_alt);
         std::swap(w.leaves, w.leaves_alt);
         const int p_lo = (int)(n * part / nparts), p_hi = (int)(n * (part + 1) / nparts);
@@ -328,7 +377,12 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
             ++launches;
         }
     }
-    // ---- dual tree traversal (grows the pair buffers and starts over if a list overflows)
+    // ---- dual tree traversal (pair buffers start from an estimate, grow and start over if a list overflows)
+    if (!w.front_a) {
+        w.cap_pairs = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 192LL * ncells / nparts), 1500000000LL);
+        w.cap_p2p = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 96LL * ncells / nparts), 1500000000LL);
+        FMM_TRY(fmm_alloc_pairs(w, err));
+    }
     FmmCounters zero = {0, 0, 0, 0};
     FmmCounters hc = zero;
     for (int attempt = 0;; ++attempt) {
@@ -351,15 +405,15 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
             std::swap(fa, fb);
         }
         if (!hc.overflow) break;
-        if (attempt >= 6 || w.cap_pairs > 1000000000u || w.cap_p2p > 1000000000u) {
+        if (attempt >= 8 || w.cap_pairs > 1400000000u || w.cap_p2p > 1400000000u) {
             err = "FMM: interaction lists overflowed the workspace";
             return cudaErrorMemoryAllocation;
         }
         // counters keep counting past the capacity, so they say which list to grow
-        if (hc.p2p >= w.cap_p2p) w.cap_p2p = std::max(w.cap_p2p * 2, hc.p2p + hc.p2p / 2);
-        if (hc.m2l >= w.cap_pairs || hc.next >= w.cap_pairs) w.cap_pairs *= 2;
+        if (hc.p2p >= w.cap_p2p) w.cap_p2p = (unsigned int)std::min<uint64_t>(std::max<uint64_t>((uint64_t)w.cap_p2p * 2, (uint64_t)hc.p2p * 3 / 2), 1500000000ULL);
+        if (hc.m2l >= w.cap_pairs || hc.next >= w.cap_pairs)
+            w.cap_pairs = (unsigned int)std::min<uint64_t>((uint64_t)w.cap_pairs * 2, 1500000000ULL);
         FMM_TRY(fmm_alloc_pairs(w, err));
-        FMM_TRY(fmm_alloc_cub(w, err));
     }
     w.n_m2l = hc.m2l;
     w.n_p2p = hc.p2p;
@@ -367,13 +421,11 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     int bits = 1;
     while ((1 << bits) < ncells) ++bits;
     if (w.n_m2l > 0) {
-        tb = w.cub_bytes;
-        FMM_TRY(cub::DeviceRadixSort::SortKeys(w.cub_tmp, tb, w.m2l, w.m2l_sorted, (int)w.n_m2l, 0, 32 + bits, st));
+        FMM_CUB(cub::DeviceRadixSort::SortKeys(tmp, tb, w.m2l, w.m2l_sorted, (int)w.n_m2l, 0, 32 + bits, st));
         ++launches;
     }
     if (w.n_p2p > 0) {
-        tb = w.cub_bytes;
-        FMM_TRY(cub::DeviceRadixSort::SortKeys(w.cub_tmp, tb, w.p2p, w.p2p_sorted, (int)w.n_p2p, 0, 32 + bits, st));
+        FMM_CUB(cub::DeviceRadixSort::SortKeys(tmp, tb, w.p2p, w.p2p_sorted, (int)w.n_p2p, 0, 32 + bits, st));
         ++launches;
     }
     fmm_list_offsets_kernel<<<(ncells + 256) / 256, 256, 0, st>>>(w.m2l_sorted, w.n_m2l, ncells, w.m2l_off);
