@@ -26,6 +26,7 @@ class Schemes(C.Structure):
         ("sfs_rlxf", C.c_double), ("minC", C.c_double), ("maxC", C.c_double), ("Cs", C.c_double),
         ("force_positive", C.c_int32), ("clippings", C.c_int32), ("controls", C.c_int32),
         ("viscous", C.c_int32), ("nu", C.c_double), ("integration", C.c_int32),
+        ("cs_sgm0", C.c_double), ("cs_beta", C.c_double), ("cs_itmax", C.c_int32), ("cs_tol", C.c_double),
         ("uj", C.c_int32), ("fmm_p", C.c_int32), ("fmm_ncrit", C.c_int32), ("fmm_theta", C.c_double),
         ("fmm_nonzero_sigma", C.c_int32),
     ]
@@ -50,6 +51,8 @@ SYMBOLS = {
     "vpmb200_add_particles": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64]),
     "vpmb200_remove_particle": (C.c_int32, [_H, C.c_int64]),
     "vpmb200_remove_where": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),
+    "vpmb200_zeta": (C.c_int32, [_H]),
+    "vpmb200_corespreading_reset": (C.c_int32, [_H, C.POINTER(C.c_int32), _dp]),
     "vpmb200_monitors": (C.c_int32, [_H, _dp]),
     "vpmb200_reset_particles": (C.c_int32, [_H]),
     "vpmb200_reset_particles_sfs": (C.c_int32, [_H]),

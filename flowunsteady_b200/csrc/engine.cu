@@ -69,6 +69,9 @@ int32_t fail(vpmb200_engine* e, int32_t code, const std::string& msg) {
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline unsigned blocks_for(int64_t n, int bt) { return (unsigned)((n + bt - 1) / bt); }
 
+int32_t ensure_probe(vpmb200_engine* e, int64_t m);
+inline int32_t ensure_probe_scratch(vpmb200_engine* e) { return ensure_probe(e, 1024); }
+
 double zeta0_of(int kernel) {
     switch (kernel) {
     case K_GAUSSIANERF: return CONST1;
@@ -168,7 +171,7 @@ cudaError_t dispatch_uj(vpmb200_engine* e, const double* rec, int ntiles, const 
 
 template <int K>
 cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty, const double* tz,
-                        const double* Jt, int64_t ldj, double* sfs, int64_t ldo, int accumulate) {
+                        const double* Jt, int64_t ldj, double* sfs, int64_t ldo, int accumulate, int raw = 0) {
     if (e->np <= 0) return cudaSuccess;
     Geometry g;
     cudaError_t st = make_geometry(e, e->np, ntiles, 3, &g);
@@ -178,7 +181,7 @@ cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles, const 
     st = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st != cudaSuccess) return st;
     kfn<<<g.grid, UJ_BT, smem, e->stream>>>(rec, ntiles, tx, ty, tz, e->np, Jt, ldj, e->sch.transposed, sfs, ldo, e->z_table,
-                                          g.split, accumulate);
+                                          g.split, accumulate, raw);
     e->launches++;
     st = cudaGetLastError();
     if (st != cudaSuccess) return st;
@@ -186,13 +189,107 @@ cudaError_t launch_estr(vpmb200_engine* e, const double* rec, int ntiles, const 
 }
 
 cudaError_t dispatch_estr_at(vpmb200_engine* e, const double* rec, int ntiles, const double* tx, const double* ty,
-                             const double* tz, const double* Jt, int64_t ldj, double* sfs, int64_t ldo, int accumulate) {
+                             const double* tz, const double* Jt, int64_t ldj, double* sfs, int64_t ldo, int accumulate,
+                             int raw = 0) {
     switch (e->sch.kernel) {
-    case K_GAUSSIANERF: return launch_estr<K_GAUSSIANERF>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
-    case K_WINCKELMANS: return launch_estr<K_WINCKELMANS>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
-    case K_GAUSSIAN: return launch_estr<K_GAUSSIAN>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
-    default: return launch_estr<K_SINGULAR>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate);
+    case K_GAUSSIANERF: return launch_estr<K_GAUSSIANERF>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate, raw);
+    case K_WINCKELMANS: return launch_estr<K_WINCKELMANS>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate, raw);
+    case K_GAUSSIAN: return launch_estr<K_GAUSSIAN>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate, raw);
+    default: return launch_estr<K_SINGULAR>(e, rec, ntiles, tx, ty, tz, Jt, ldj, sfs, ldo, accumulate, raw);
     }
+}
+
+// out (3 rows, particle order) = sum_q zeta_sigma_q(x_p - x_q) vec_q : the zeta pass (vpm.zeta_direct) on the K2 kernel
+int32_t zeta_apply(vpmb200_engine* e, const double* vec, int64_t ldv, double* out, int64_t ldo) {
+    if (e->np <= 0) return VPMB200_OK;
+    const double* S = e->state;
+    const int64_t ld = e->ld;
+    pack_zeta_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(
+        e->state, ld, e->np, vec, ldv, zeta0_of(e->sch.kernel), e->sch.kernel == K_GAUSSIANERF ? 1 : 0, e->rec);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    CU_TRY(e, dispatch_estr_at(e, e->rec, (int)vpmb200_tiles_for(e->np), S + (size_t)F_X * ld, S + (size_t)(F_X + 1) * ld,
+                               S + (size_t)(F_X + 2) * ld, S + (size_t)F_J * ld, ld, out, ldo, 0, 1));
+    return VPMB200_OK;
+}
+
+// host-side sum of per-block partials (fixed order)
+int32_t dot3(vpmb200_engine* e, const double* a, const double* b, double out[3]) {
+    int32_t rc = ensure_probe_scratch(e);
+    if (rc) return rc;
+    const int nb = 128;
+    dot3_partials_kernel<<<nb, 256, 0, e->stream>>>(a, e->ld, b, e->ld, e->state + (size_t)F_STATIC * e->ld, e->np, e->probe);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    double hb[nb * 4];
+    CU_TRY(e, cudaMemcpyAsync(hb, e->probe, sizeof(hb), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    out[0] = out[1] = out[2] = 0.0;
+    for (int k = 0; k < nb; ++k)
+        for (int c = 0; c < 3; ++c) out[c] += hb[k * 4 + c];
+    return VPMB200_OK;
+}
+
+// CoreSpreading spatial adaptation: see include/vpmb200.h
+int32_t do_corespreading_reset(vpmb200_engine* e, int32_t* iters, double* residual3) {
+    const vpmb200_schemes& s = e->sch;
+    if (iters) *iters = 0;
+    if (residual3) residual3[0] = residual3[1] = residual3[2] = 0.0;
+    if (e->np <= 0 || !(s.cs_sgm0 > 0)) return VPMB200_OK;
+    int32_t rc = ensure_probe_scratch(e);
+    if (rc) return rc;
+    const int64_t ld = e->ld, n = e->np;
+    const unsigned nb = blocks_for(n, PK_BT);
+    {   // is any spread core beyond beta sgm0?
+        const int nbk = 128;
+        sigma_max_partials_kernel<<<nbk, 256, 0, e->stream>>>(e->state, ld, n, e->probe);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        double hb[nbk];
+        CU_TRY(e, cudaMemcpyAsync(hb, e->probe, sizeof(hb), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(e, cudaStreamSynchronize(e->stream));
+        double m = 0.0;
+        for (int k = 0; k < nbk; ++k) m = std::max(m, hb[k]);
+        if (!(m / s.cs_sgm0 > s.cs_beta)) return VPMB200_OK;
+    }
+    double* G = e->state + (size_t)F_GAMMA * ld;
+    double* b = e->state + (size_t)F_W * ld;         // target vorticity (also the W output rows)
+    double* r = e->state + (size_t)F_M * ld;         // M[:,1]
+    double* d = e->state + (size_t)(F_M + 3) * ld;   // M[:,2]
+    double* Ad = e->state + (size_t)(F_M + 6) * ld;  // M[:,3]
+    const double* stat = e->state + (size_t)F_STATIC * ld;
+    if ((rc = zeta_apply(e, G, ld, b, ld))) return rc;                       // omega with the spread cores
+    set_sigma_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, ld, n, s.cs_sgm0);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    if ((rc = zeta_apply(e, G, ld, Ad, ld))) return rc;                      // A Gamma with the reset cores
+    cg_init_kernel<<<nb, PK_BT, 0, e->stream>>>(b, Ad, r, d, ld, stat, n);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    double rr[3];
+    if ((rc = dot3(e, r, r, rr))) return rc;
+    int32_t it = 0;
+    for (; it < s.cs_itmax; ++it) {
+        if (std::sqrt(rr[0]) < s.cs_tol && std::sqrt(rr[1]) < s.cs_tol && std::sqrt(rr[2]) < s.cs_tol) break;
+        if ((rc = zeta_apply(e, d, ld, Ad, ld))) return rc;
+        double dAd[3], rrn[3];
+        if ((rc = dot3(e, d, Ad, dAd))) return rc;
+        Vec3 alpha, beta;
+        for (int k = 0; k < 3; ++k) alpha.v[k] = dAd[k] != 0 ? rr[k] / dAd[k] : 0.0;
+        cg_update_kernel<<<nb, PK_BT, 0, e->stream>>>(G, r, d, Ad, ld, stat, n, alpha);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        if ((rc = dot3(e, r, r, rrn))) return rc;
+        for (int k = 0; k < 3; ++k) beta.v[k] = rr[k] != 0 ? rrn[k] / rr[k] : 0.0;
+        cg_direction_kernel<<<nb, PK_BT, 0, e->stream>>>(d, r, ld, stat, n, beta);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        for (int k = 0; k < 3; ++k) rr[k] = rrn[k];
+    }
+    if (iters) *iters = it;
+    if (residual3)
+        for (int k = 0; k < 3; ++k) residual3[k] = std::sqrt(rr[k]);
+    return VPMB200_OK;
 }
 
 // E_str of the local particles (state rows as targets), accumulated into the state's SFS rows
@@ -483,6 +580,8 @@ int32_t check_schemes(vpmb200_engine* e, const vpmb200_schemes* s) {
     if (s->sfs == VPMB200_SFS_DYNAMIC && !(s->alpha > 0)) return fail(e, VPMB200_EINVAL, "DynamicSFS needs alpha > 0");
     if (s->controls & ~(VPMB200_CTRL_DIRECTIONAL | VPMB200_CTRL_MAGNITUDE))
         return fail(e, VPMB200_ENOTSUP, "control_sigmasensor is not implemented (upstream form unverified)");
+    if (s->viscous == VPMB200_VISCOUS_CORESPREADING && s->cs_sgm0 > 0 && (s->cs_itmax < 0 || !(s->cs_beta > 0) || !(s->cs_tol >= 0)))
+        return fail(e, VPMB200_EINVAL, "CoreSpreading needs beta > 0, itmax >= 0, tol >= 0");
     if (s->viscous == VPMB200_VISCOUS_CORESPREADING && s->kernel != VPMB200_KERNEL_GAUSSIANERF)
         return fail(e, VPMB200_EINVAL, "CoreSpreading requires the gaussianerf kernel (vpm._kernel_compatibility)");
     return VPMB200_OK;
@@ -535,6 +634,10 @@ int32_t vpmb200_default_schemes(vpmb200_schemes* s) {
     s->Cs = 1.0;
     s->viscous = VPMB200_VISCOUS_INVISCID;
     s->integration = VPMB200_INTEGRATION_RK3;
+    s->cs_sgm0 = 0.0;
+    s->cs_beta = 1.5;
+    s->cs_itmax = 15;
+    s->cs_tol = 1e-3;
     s->uj = VPMB200_UJ_DIRECT;
     s->fmm_p = 4;
     s->fmm_ncrit = 50;
@@ -782,6 +885,18 @@ int32_t vpmb200_remove_where(vpmb200_handle e, int32_t criterion, const double* 
     return VPMB200_OK;
 }
 
+int32_t vpmb200_zeta(vpmb200_handle e) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    return zeta_apply(e, e->state + (size_t)F_GAMMA * e->ld, e->ld, e->state + (size_t)F_W * e->ld, e->ld);
+}
+
+int32_t vpmb200_corespreading_reset(vpmb200_handle e, int32_t* iters, double* residual3) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    return do_corespreading_reset(e, iters, residual3);
+}
+
 int32_t vpmb200_monitors(vpmb200_handle e, double* out6) {
     CHECK_HANDLE(e);
     if (!out6) return fail(e, VPMB200_EINVAL, "out is NULL");
@@ -878,6 +993,7 @@ int32_t vpmb200_nextstep(vpmb200_handle e, double dt, const double* Uinf, int32_
         if (e->sch.integration == VPMB200_INTEGRATION_EULER) {
             if ((rc = do_sfs(e, 1.0, 1.0))) return rc;
             if ((rc = do_stage(e, VPMB200_STAGE_UPDATE, 0.0, 1.0, dt, Uinf, relax ? 1 : 0))) return rc;
+            if (e->sch.viscous == VPMB200_VISCOUS_CORESPREADING && (rc = do_corespreading_reset(e, nullptr, nullptr))) return rc;
         } else {
             static const double AB[3][2] = {{0.0, 1.0 / 3.0}, {-5.0 / 9.0, 15.0 / 16.0}, {-153.0 / 128.0, 8.0 / 15.0}};
             if ((rc = do_stage(e, VPMB200_STAGE_ZERO_M, 0, 0, 0, nullptr, 0))) return rc;
@@ -885,6 +1001,8 @@ int32_t vpmb200_nextstep(vpmb200_handle e, double dt, const double* Uinf, int32_
                 if ((rc = do_sfs(e, AB[st][0], AB[st][1]))) return rc;
                 if ((rc = do_stage(e, VPMB200_STAGE_UPDATE, AB[st][0], AB[st][1], dt, Uinf, 0))) return rc;
             }
+            // spatial adaptation is checked once the last substep is done
+            if (e->sch.viscous == VPMB200_VISCOUS_CORESPREADING && (rc = do_corespreading_reset(e, nullptr, nullptr))) return rc;
             if (relax && e->sch.relaxation != VPMB200_RELAX_NONE) {
                 if ((rc = do_uj(e, 1, 0, 0))) return rc;
                 if ((rc = do_stage(e, VPMB200_STAGE_RELAX, 0, 0, 0, nullptr, 0))) return rc;

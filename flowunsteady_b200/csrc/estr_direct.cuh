@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(UJ_BT, 2)
 estr_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* __restrict__ tx,
                        const double* __restrict__ ty, const double* __restrict__ tz, int64_t nt,
                        const double* __restrict__ Jt, int64_t ldj, int transposed, double* __restrict__ SFS,
-                       int64_t ldo, const double* __restrict__ z_table, SplitArgs split, int accumulate) {
+                       int64_t ldo, const double* __restrict__ z_table, SplitArgs split, int accumulate, int raw) {
     if (split.partial != nullptr) {
         const int t0 = blockIdx.y * split.tiles_per_chunk;
         srec += (size_t)t0 * TILE_DOUBLES;
@@ -129,7 +129,13 @@ estr_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double
         __syncthreads();
     }
 
-    if (live) {
+    if (live && raw) {
+        // zeta pass (vpm.zeta_direct): the plain kernel sum  sum_q zeta_sigma_q(x_p - x_q) v_q  (records carry c v in the
+        // Gamma slots); used for the vorticity and as the matrix-vector product of the RBF conjugate gradient
+        SFS[0 * ldo + i] = (accumulate ? SFS[0 * ldo + i] : 0.0) + tot.a0;
+        SFS[1 * ldo + i] = (accumulate ? SFS[1 * ldo + i] : 0.0) + tot.a1;
+        SFS[2 * ldo + i] = (accumulate ? SFS[2 * ldo + i] : 0.0) + tot.a2;
+    } else if (live) {
         double Jp[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) Jp[c] = Jt[(size_t)c * ldj + i];

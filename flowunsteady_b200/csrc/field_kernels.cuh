@@ -196,6 +196,119 @@ pack_estr_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, 
     write_tile_header(tile + TILE_HDR, real, x, y, z, rfar2, (int)(nreal > TILE_SRC ? TILE_SRC : nreal));
 }
 
+// zeta-pass source tiles: { x, y | z, 1/sigma^2 | c v0, c v1 | c v2, 0 | 0, 0 }, c = zeta_norm / sigma^3, v = 3 rows at `vec`
+__global__ void __launch_bounds__(TILE_SRC)
+pack_zeta_records_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, const double* __restrict__ vec, int64_t ldv,
+                         double zeta_norm, int cutoff, double* __restrict__ rec) {
+    const int64_t t0 = (int64_t)blockIdx.x * TILE_SRC;
+    const int64_t i = t0 + threadIdx.x;
+    const bool real = i < n;
+    const int64_t isrc = real ? i : t0;
+    double* tile = rec + (size_t)blockIdx.x * TILE_DOUBLES;
+    double2* r = reinterpret_cast<double2*>(tile + (size_t)threadIdx.x * REC_REALS);
+    double x = soa[(size_t)(F_X + 0) * ld + isrc], y = soa[(size_t)(F_X + 1) * ld + isrc], z = soa[(size_t)(F_X + 2) * ld + isrc];
+    double rfar2 = 0.0;
+    if (real) {
+        double sg = soa[(size_t)F_SIGMA * ld + i];
+        double si = 1.0 / sg, si2 = si * si;
+        double c = zeta_norm * (si2 * si);
+        rfar2 = cutoff ? VPM_GT_TFAR * (sg * sg) : 1.0e300;
+        r[0] = make_double2(x, y);
+        r[1] = make_double2(z, si2);
+        r[2] = make_double2(c * vec[i], c * vec[ldv + i]);
+        r[3] = make_double2(c * vec[2 * ldv + i], 0.0);
+        r[4] = make_double2(0.0, 0.0);
+    } else {
+        r[0] = make_double2(x, y);
+        r[1] = make_double2(z, 1.0);
+        r[2] = make_double2(0.0, 0.0);
+        r[3] = make_double2(0.0, 0.0);
+        r[4] = make_double2(0.0, 0.0);
+    }
+    int64_t nreal = n - t0;
+    write_tile_header(tile + TILE_HDR, real, x, y, z, rfar2, (int)(nreal > TILE_SRC ? TILE_SRC : nreal));
+}
+
+// ---- RBF conjugate gradient helpers (CoreSpreading spatial adaptation).  Vectors are 3 SoA rows; static
+//      particles are fixed (their residual / direction entries are kept at zero). ---------------------------------------
+// out[block * 4 + k] = sum over non-static i of a_k[i] * b_k[i]
+__global__ void dot3_partials_kernel(const double* __restrict__ a, int64_t lda, const double* __restrict__ b, int64_t ldb,
+                                     const double* __restrict__ stat, int64_t n, double* __restrict__ out) {
+    __shared__ double red[3][8];
+    double v[3] = {0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!(stat[i] > 0))
+            for (int k = 0; k < 3; ++k) v[k] += a[(size_t)k * lda + i] * b[(size_t)k * ldb + i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 3; ++c) red[c][threadIdx.x >> 5] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double m = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m += red[threadIdx.x][k];
+        out[blockIdx.x * 4 + threadIdx.x] = m;
+    }
+}
+
+// r = b - Ad (0 for statics), d = r
+__global__ void cg_init_kernel(const double* __restrict__ b, const double* __restrict__ Ad, double* __restrict__ r,
+                               double* __restrict__ d, int64_t ld, const double* __restrict__ stat, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool st = stat[i] > 0;
+    for (int k = 0; k < 3; ++k) {
+        double v = st ? 0.0 : b[(size_t)k * ld + i] - Ad[(size_t)k * ld + i];
+        r[(size_t)k * ld + i] = v;
+        d[(size_t)k * ld + i] = v;
+    }
+}
+
+struct Vec3 {
+    double v[3];
+};
+
+// x += alpha d ; r -= alpha Ad   (non-static)
+__global__ void cg_update_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d,
+                                 const double* __restrict__ Ad, int64_t ld, const double* __restrict__ stat, int64_t n, Vec3 alpha) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || stat[i] > 0) return;
+    for (int k = 0; k < 3; ++k) {
+        x[(size_t)k * ld + i] += alpha.v[k] * d[(size_t)k * ld + i];
+        r[(size_t)k * ld + i] -= alpha.v[k] * Ad[(size_t)k * ld + i];
+    }
+}
+
+// d = r + beta d   (non-static)
+__global__ void cg_direction_kernel(double* __restrict__ d, const double* __restrict__ r, int64_t ld,
+                                    const double* __restrict__ stat, int64_t n, Vec3 beta) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || stat[i] > 0) return;
+    for (int k = 0; k < 3; ++k) d[(size_t)k * ld + i] = r[(size_t)k * ld + i] + beta.v[k] * d[(size_t)k * ld + i];
+}
+
+// max over non-static particles of sigma (block partials), and sigma <- sgm0 for them
+__global__ void sigma_max_partials_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, double* __restrict__ out) {
+    __shared__ double red[8];
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!(soa[(size_t)F_STATIC * ld + i] > 0)) m = fmax(m, soa[(size_t)F_SIGMA * ld + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmax(m, red[k]);
+        out[blockIdx.x] = m;
+    }
+}
+__global__ void set_sigma_kernel(double* __restrict__ soa, int64_t ld, int64_t n, double sgm0) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !(soa[(size_t)F_STATIC * ld + i] > 0)) soa[(size_t)F_SIGMA * ld + i] = sgm0;
+}
+
 // dst[k * ldd + i] = src[(row0 + k) * ld + perm[i]]  — SoA rows into Morton order
 __global__ void gather_rows_kernel(const double* __restrict__ soa, int64_t ld, int row0, int nrows, int64_t n,
                                    const int* __restrict__ perm, double* __restrict__ dst, int64_t ldd) {

@@ -206,6 +206,8 @@ class ShardedField:
     def nextstep(self, dt: float, Uinf: Sequence[float] = (0.0, 0.0, 0.0), relax: bool = True):
         s = self.b.get_schemes()
         st = self.b.stage
+        if s.viscous == _E.VISCOUS_IDS["corespreading"] and getattr(s, "cs_sgm0", 0.0) > 0:
+            raise NotImplementedError("CoreSpreading's RBF re-fit is single-GPU; run it with cs_sgm0 = 0 on a sharded field")
         if sum(self._ntiles) > 0:
             if s.integration == _E.INTEGRATION_IDS["euler"]:
                 self.sfs(1.0, 1.0)

@@ -148,6 +148,18 @@ class Engine:
         self._check(self._L.vpmb200_remove_where(self._h, int(criterion), p.ctypes.data, C.byref(r)))
         return r.value
 
+    def zeta(self):
+        """W rows <- sum_q Gamma_q zeta_sigma_q(x_p - x_q)  (vpm.zeta_direct / zeta_fmm)."""
+        self._check(self._L.vpmb200_zeta(self._h))
+
+    def corespreading_reset(self):
+        """CoreSpreading's spatial adaptation (sigma <- sgm0 + RBF conjugate-gradient re-fit of Gamma); returns
+        (CG iterations, residual per component).  0 iterations = no particle had sigma/sgm0 > beta."""
+        it = C.c_int32()
+        res = (C.c_double * 3)()
+        self._check(self._L.vpmb200_corespreading_reset(self._h, C.byref(it), res))
+        return it.value, np.array(res[:])
+
     def monitors(self) -> dict:
         out = (C.c_double * 6)()
         self._check(self._L.vpmb200_monitors(self._h, out))

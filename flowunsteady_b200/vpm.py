@@ -103,8 +103,9 @@ class Inviscid(ViscousScheme):
 @dataclass
 class CoreSpreading(ViscousScheme):
     """vpm.CoreSpreading(nu, sgm0, zeta; beta, itmax, tol) (examples/rotorhover/rotorhover.jl:170).  The engine applies
-    the sigma update of SURVEY.md A.8; the RBF re-fit on sigma/sgm0 > beta is not built yet (all shipped examples run
-    Inviscid)."""
+    the sigma update of SURVEY.md A.8 every substep and, once the last substep is done, the spatial adaptation: when any
+    sigma/sgm0 > beta the cores are reset to sgm0 and Gamma is re-fitted by RBF conjugate gradients (itmax, tol) so the
+    particle-approximated vorticity is preserved."""
     nu: float
     sgm0: float
     zeta: object = None
@@ -121,8 +122,13 @@ def iscorespreading(v) -> bool:
     return isinstance(v, CoreSpreading)
 
 
-def zeta_fmm(pfield):  # placeholder object passed as CoreSpreading's `zeta` (simulation.jl:232)
-    raise NotImplementedError("zeta_fmm (RBF vorticity evaluation) is not built yet")
+def zeta_fmm(pfield):
+    """vpm.zeta_fmm (passed as CoreSpreading's `zeta`, simulation.jl:232): vorticity sum_q Gamma_q zeta_sigma_q(x_p - x_q) at every
+    particle, stored in the W rows.  Runs the near-field zeta pass of the engine."""
+    pfield._call_zeta()
+
+
+zeta_direct = zeta_fmm
 
 
 def _kernel_compatibility(viscous) -> tuple:
@@ -364,7 +370,8 @@ class ParticleField:
             kw.update(alpha=sfs.alpha, sfs_rlxf=sfs.rlxf, minC=sfs.minC, maxC=sfs.maxC,
                       force_positive=int(sfs.procedure is pseudo3level_positive))
         if iscorespreading(self.viscous):
-            kw.update(viscous=1, nu=self.viscous.nu)
+            kw.update(viscous=1, nu=self.viscous.nu, cs_sgm0=self.viscous.sgm0, cs_beta=self.viscous.beta,
+                      cs_itmax=self.viscous.itmax, cs_tol=self.viscous.tol)
         if integration_id is not None:
             kw.update(integration=integration_id)
         return _E.default_schemes(**kw)
@@ -409,6 +416,12 @@ class ParticleField:
         self._engine.uj(reset, reset_sfs, sfs)
         self._pulled(_E.FM_U | _E.FM_J | _E.FM_PSE | (_E.FM_SFS if (sfs or reset_sfs) else 0))
 
+    def _call_zeta(self):
+        self._engine.set_schemes(self._schemes(_E.UJ_IDS["direct"]))
+        self._push(_E.FM_STATE)
+        self._engine.zeta()
+        self._pulled(_E.FM_VORTICITY)
+
     def _call_sfs(self, a: float, b: float):
         self._engine.set_schemes(self._schemes(self._uj_id()))
         self._push(_E.FM_ALL)
@@ -421,7 +434,7 @@ class ParticleField:
         self._engine.set_schemes(self._schemes(self._uj_id(), integration_id))
         self._push(_E.FM_STATE | _E.FM_M)
         self._engine.nextstep(dt, tuple(self.Uinf(self.t)), relax)
-        self._pulled(_E.FM_ALL & ~(_E.FM_VOL | _E.FM_CIRCULATION | _E.FM_STATIC | _E.FM_VORTICITY))
+        self._pulled(_E.FM_ALL & ~(_E.FM_VOL | _E.FM_CIRCULATION | _E.FM_STATIC))
 
     # ---- wake treatments / monitors on the device ---------------------------------------------------------------
     def remove_where(self, criterion: int, params) -> int:

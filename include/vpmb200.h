@@ -90,7 +90,7 @@ enum { VPMB200_INTEGRATION_EULER = 0, VPMB200_INTEGRATION_RK3 = 1 };
 enum { VPMB200_UJ_DIRECT = 0, VPMB200_UJ_FMM = 1 };
 
 /* Mirrors the scheme fields of vpm.ParticleField (simulation.jl:239-244).  Same layout as oracle's vpmo_schemes
- * for the first 18 members so tests can drive both from one description. */
+ * for the first 22 members so tests can drive both from one description. */
 typedef struct {
     int32_t kernel;         /* vpm_kernel: gaussianerf | winckelmans | gaussian | singular                */
     double f, g;            /* vpm_formulation: rVPM (0, 1/5) | cVPM (0, 0)                                */
@@ -105,9 +105,13 @@ typedef struct {
     int32_t force_positive; /*   pseudo3level_positive                                                     */
     int32_t clippings;      /*   VPMB200_CLIP_* mask                                                       */
     int32_t controls;       /*   VPMB200_CTRL_* mask                                                       */
-    int32_t viscous;        /* vpm_viscous: Inviscid | CoreSpreading (sigma update; RBF re-fit not included) */
+    int32_t viscous;        /* vpm_viscous: Inviscid | CoreSpreading                                            */
     double nu;              /*   kinematic viscosity                                                       */
     int32_t integration;    /* vpm_integration: euler | rungekutta3                                        */
+    double cs_sgm0;         /* CoreSpreading(nu, sgm0, zeta; beta, itmax, tol): reset core size, <= 0 = never reset */
+    double cs_beta;         /*   reset when sigma/sgm0 > beta (1.5)                                        */
+    int32_t cs_itmax;       /*   RBF conjugate-gradient iterations (15)                                    */
+    double cs_tol;          /*   RBF residual tolerance (1e-3)                                             */
     /* --- beyond the oracle's struct --- */
     int32_t uj;             /* vpm_UJ: direct | fmm                                                        */
     int32_t fmm_p;          /* vpm_fmm = vpm.FMM(; p=4, ncrit=50, theta=0.4, nonzero_sigma) simulation.jl:43 */
@@ -158,6 +162,14 @@ int32_t vpmb200_remove_particle(vpmb200_handle h, int64_t i);
  * *removed receives the number of particles removed. */
 enum { VPMB200_REMOVE_STRENGTH = 1, VPMB200_REMOVE_SIGMA = 2, VPMB200_REMOVE_BOX = 3, VPMB200_REMOVE_SPHERE = 4 };
 int32_t vpmb200_remove_where(vpmb200_handle h, int32_t criterion, const double* params, int64_t* removed);
+
+/* vpm.zeta_direct / zeta_fmm: W (rows 12:15) <- sum_q Gamma_q zeta_sigma_q(x_p - x_q), the particle-approximated vorticity. */
+int32_t vpmb200_zeta(vpmb200_handle h);
+/* CoreSpreading's spatial adaptation: if any non-static sigma/sgm0 > beta, store omega (spread cores) in
+ * W, set sigma <- sgm0 and re-fit Gamma by conjugate gradients.  *iters: CG iterations done (0 = no reset was needed);
+ * residual3: final residual 2-norm per component (may be NULL).  vpmb200_nextstep calls this itself when
+ * viscous = CoreSpreading and cs_sgm0 > 0. */
+int32_t vpmb200_corespreading_reset(vpmb200_handle h, int32_t* iters, double* residual3);
 
 /* Monitors (vpm.monitor_enstrophy, vpm.monitor_Cd; src/FLOWUnsteady_monitors.jl:614,697): out[0] = enstrophy
  * 0.5 sum Gamma.omega (omega = curl u from J), out[1] = mean C_d over particles with C_d != 0, out[2] = its standard

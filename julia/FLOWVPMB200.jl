@@ -34,6 +34,7 @@ mutable struct Schemes
     sfs_rlxf::Float64; minC::Float64; maxC::Float64; Cs::Float64
     force_positive::Int32; clippings::Int32; controls::Int32
     viscous::Int32; nu::Float64; integration::Int32
+    cs_sgm0::Float64; cs_beta::Float64; cs_itmax::Int32; cs_tol::Float64
     uj::Int32; fmm_p::Int32; fmm_ncrit::Int32; fmm_theta::Float64; fmm_nonzero_sigma::Int32
     Schemes() = new()
 end
@@ -83,6 +84,8 @@ function _schemes(pfield; uj::Integer=0, integration::Integer=1)
     end
     if vpm.iscorespreading(pfield.viscous)
         s.viscous = 1; s.nu = pfield.viscous.nu
+        s.cs_sgm0 = pfield.viscous.sgm0; s.cs_beta = pfield.viscous.beta
+        s.cs_itmax = pfield.viscous.itmax; s.cs_tol = pfield.viscous.tol
     end
     s.integration = integration
     s.uj = uj

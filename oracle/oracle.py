@@ -33,6 +33,7 @@ class Schemes(C.Structure):
         ("sfs_rlxf", C.c_double), ("minC", C.c_double), ("maxC", C.c_double), ("Cs", C.c_double),
         ("force_positive", C.c_int32), ("clippings", C.c_int32), ("controls", C.c_int32),
         ("viscous", C.c_int32), ("nu", C.c_double), ("integration", C.c_int32),
+        ("cs_sgm0", C.c_double), ("cs_beta", C.c_double), ("cs_itmax", C.c_int32), ("cs_tol", C.c_double),
     ]
 
 
@@ -72,6 +73,9 @@ def lib():
         L.vpmo_relax_particle.argtypes = [_dp, C.c_int32, C.c_double]
         L.vpmo_update_particle.argtypes = [_dp, C.POINTER(Schemes), C.c_double, C.c_double, C.c_double, _dp,
                                            C.c_double]
+        L.vpmo_zeta_direct.argtypes = [C.c_int32, C.c_int64, _dp, _dp, _dp, C.c_int64, _dp, _dp]
+        L.vpmo_corespreading_reset.argtypes = [_dp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, _dp]
+        L.vpmo_corespreading_reset.restype = C.c_int32
         L.vpmo_num_threads.restype = C.c_int32
         L.vpmo_set_num_threads.argtypes = [C.c_int32]
         _lib = L
@@ -173,6 +177,19 @@ def nextstep(P, schemes, dt, Uinf=(0.0, 0.0, 0.0), relax=True, t=0.0, nt=0):
     tt, nn = C.c_double(t), C.c_int64(nt)
     lib().vpmo_nextstep(P, P.shape[0], C.byref(schemes), dt, _c(Uinf), int(relax), C.byref(tt), C.byref(nn))
     return tt.value, nn.value
+
+
+def zeta_direct(kernel, xs, vs, sig, xt):
+    xs, vs, sig, xt = _c(xs), _c(vs), _c(sig), _c(xt)
+    out = np.zeros((xt.shape[0], 3))
+    lib().vpmo_zeta_direct(_kid(kernel), xs.shape[0], xs, vs, sig, xt.shape[0], xt, out)
+    return out
+
+
+def corespreading_reset(P, kernel, sgm0, beta=1.5, itmax=15, tol=1e-3):
+    res = np.zeros(3)
+    it = lib().vpmo_corespreading_reset(P, P.shape[0], _kid(kernel), sgm0, beta, itmax, tol, res)
+    return it, res
 
 
 def num_threads() -> int:

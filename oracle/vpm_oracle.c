@@ -63,6 +63,10 @@ void vpmo_default_schemes(vpmo_schemes *s) {
     s->viscous = VPMO_VISCOUS_INVISCID;
     s->nu = 0.0;
     s->integration = VPMO_INTEGRATION_RK3;
+    s->cs_sgm0 = 0.0;
+    s->cs_beta = 1.5;
+    s->cs_itmax = 15;
+    s->cs_tol = 1e-3;
 }
 
 /* ------------------------------------------------------------------ kernels (A.3) ------------ */
@@ -226,6 +230,27 @@ void vpmo_estr_direct(int32_t kernel, int32_t transposed, int64_t ns, const doub
             }
             for (int k = 0; k < 3; ++k) SFS[3 * i + k] = (double)e[k];
         }
+    }
+}
+
+/* ------------------------------------------------------------------ zeta pass / RBF (A.8) ---- */
+
+void vpmo_zeta_direct(int32_t kernel, int64_t ns, const double *xs, const double *vs, const double *sig, int64_t nt,
+                      const double *xt, double *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nt; ++i) {
+        long double a[3] = {out[3 * i], out[3 * i + 1], out[3 * i + 2]};
+        for (int64_t j = 0; j < ns; ++j) {
+            double dX1 = xt[3 * i + 0] - xs[3 * j + 0];
+            double dX2 = xt[3 * i + 1] - xs[3 * j + 1];
+            double dX3 = xt[3 * i + 2] - xs[3 * j + 2];
+            double r = sqrt(dX1 * dX1 + dX2 * dX2 + dX3 * dX3);
+            double z = 1 / (sig[j] * sig[j] * sig[j]) * vpmo_zeta(kernel, r / sig[j]);
+            a[0] += z * vs[3 * j + 0];
+            a[1] += z * vs[3 * j + 1];
+            a[2] += z * vs[3 * j + 2];
+        }
+        for (int k = 0; k < 3; ++k) out[3 * i + k] = (double)a[k];
     }
 }
 
@@ -540,6 +565,77 @@ void vpmo_update_particle(double *p, const vpmo_schemes *s, double a, double b, 
     }
 }
 
+int32_t vpmo_corespreading_reset(double *P, int64_t np, int32_t kernel, double sgm0, double beta, int32_t itmax, double tol,
+                                 double *residual3) {
+    int need = 0;
+    for (int64_t i = 0; i < np; ++i) {
+        const double *p = PCOL(P, i);
+        if (!is_static(p) && p[VPMO_SIGMA] / sgm0 > beta) need = 1;
+    }
+    if (residual3) residual3[0] = residual3[1] = residual3[2] = 0;
+    if (!need || np <= 0) return 0;
+    double *x = (double *)malloc(sizeof(double) * 3 * np), *v = (double *)malloc(sizeof(double) * 3 * np);
+    double *sg = (double *)malloc(sizeof(double) * np), *b = (double *)calloc(3 * np, sizeof(double));
+    double *r = (double *)malloc(sizeof(double) * 3 * np), *d = (double *)malloc(sizeof(double) * 3 * np);
+    double *Ad = (double *)malloc(sizeof(double) * 3 * np);
+    for (int64_t i = 0; i < np; ++i) {
+        const double *p = PCOL(P, i);
+        for (int k = 0; k < 3; ++k) { x[3 * i + k] = p[VPMO_X + k]; v[3 * i + k] = p[VPMO_GAMMA + k]; }
+        sg[i] = p[VPMO_SIGMA];
+    }
+    /* target vorticity with the spread cores */
+    vpmo_zeta_direct(kernel, np, x, v, sg, np, x, b);
+    for (int64_t i = 0; i < np; ++i) {
+        double *p = PCOL(P, i);
+        for (int k = 0; k < 3; ++k) p[VPMO_W + k] = b[3 * i + k];
+        if (!is_static(p)) { p[VPMO_SIGMA] = sgm0; sg[i] = sgm0; }
+    }
+    /* CG on the non-static unknowns; statics contribute A_static Gamma_static to both sides (kept inside A v below and
+     * never updated because their search direction is zero) */
+    memset(Ad, 0, sizeof(double) * 3 * np);
+    vpmo_zeta_direct(kernel, np, x, v, sg, np, x, Ad);
+    double rr[3] = {0, 0, 0};
+    for (int64_t i = 0; i < np; ++i) {
+        int st = is_static(PCOL(P, i));
+        for (int k = 0; k < 3; ++k) {
+            r[3 * i + k] = st ? 0.0 : b[3 * i + k] - Ad[3 * i + k];
+            d[3 * i + k] = r[3 * i + k];
+            rr[k] += r[3 * i + k] * r[3 * i + k];
+        }
+    }
+    int32_t it = 0;
+    for (; it < itmax; ++it) {
+        if (sqrt(rr[0]) < tol && sqrt(rr[1]) < tol && sqrt(rr[2]) < tol) break;
+        memset(Ad, 0, sizeof(double) * 3 * np);
+        vpmo_zeta_direct(kernel, np, x, d, sg, np, x, Ad);
+        double dAd[3] = {0, 0, 0};
+        for (int64_t i = 0; i < np; ++i)
+            if (!is_static(PCOL(P, i)))
+                for (int k = 0; k < 3; ++k) dAd[k] += d[3 * i + k] * Ad[3 * i + k];
+        double alpha[3], rrn[3] = {0, 0, 0};
+        for (int k = 0; k < 3; ++k) alpha[k] = dAd[k] != 0 ? rr[k] / dAd[k] : 0.0;
+        for (int64_t i = 0; i < np; ++i) {
+            if (is_static(PCOL(P, i))) continue;
+            for (int k = 0; k < 3; ++k) {
+                v[3 * i + k] += alpha[k] * d[3 * i + k];
+                r[3 * i + k] -= alpha[k] * Ad[3 * i + k];
+                rrn[k] += r[3 * i + k] * r[3 * i + k];
+            }
+        }
+        for (int64_t i = 0; i < np; ++i) {
+            if (is_static(PCOL(P, i))) continue;
+            for (int k = 0; k < 3; ++k) d[3 * i + k] = r[3 * i + k] + (rr[k] != 0 ? rrn[k] / rr[k] : 0.0) * d[3 * i + k];
+        }
+        for (int k = 0; k < 3; ++k) rr[k] = rrn[k];
+    }
+    for (int64_t i = 0; i < np; ++i)
+        for (int k = 0; k < 3; ++k) PCOL(P, i)[VPMO_GAMMA + k] = v[3 * i + k];
+    if (residual3)
+        for (int k = 0; k < 3; ++k) residual3[k] = sqrt(rr[k]);
+    free(x); free(v); free(sg); free(b); free(r); free(d); free(Ad);
+    return it;
+}
+
 void vpmo_nextstep(double *P, int64_t np, const vpmo_schemes *s, double dt, const double *Uinf,
                    int32_t relax, double *t, int64_t *nt) {
     const double zeta0 = vpmo_zeta(s->kernel, 0.0);
@@ -561,6 +657,8 @@ void vpmo_nextstep(double *P, int64_t np, const vpmo_schemes *s, double dt, cons
                     p[VPMO_SIGMA] = sqrt(p[VPMO_SIGMA] * p[VPMO_SIGMA] + 2 * s->nu * dt);
                 memcpy(p + VPMO_M, Msave, sizeof(Msave));
             }
+            if (s->viscous == VPMO_VISCOUS_CORESPREADING && s->cs_sgm0 > 0)
+                vpmo_corespreading_reset(P, np, s->kernel, s->cs_sgm0, s->cs_beta, s->cs_itmax, s->cs_tol, NULL);
         } else {
             static const double AB[3][2] = {
                 {0.0, 1.0 / 3.0}, {-5.0 / 9.0, 15.0 / 16.0}, {-153.0 / 128.0, 8.0 / 15.0}};
@@ -577,6 +675,9 @@ void vpmo_nextstep(double *P, int64_t np, const vpmo_schemes *s, double dt, cons
                     if (!is_static(p)) vpmo_update_particle(p, s, a, b, dt, Uinf, zeta0);
                 }
             }
+            /* spatial adaptation is checked once the last substep is done (A.8), before the relaxation evaluation */
+            if (s->viscous == VPMO_VISCOUS_CORESPREADING && s->cs_sgm0 > 0)
+                vpmo_corespreading_reset(P, np, s->kernel, s->cs_sgm0, s->cs_beta, s->cs_itmax, s->cs_tol, NULL);
             if (relax && s->relaxation != VPMO_RELAX_NONE) {
                 vpmo_field_uj(P, np, s, 1, 0, 0);
                 for (int64_t i = 0; i < np; ++i) {

@@ -78,6 +78,10 @@ typedef struct {
     int32_t viscous;       /* VPMO_VISCOUS_*                                                    */
     double nu;             /* kinematic viscosity for core spreading                            */
     int32_t integration;   /* VPMO_INTEGRATION_*                                                */
+    double cs_sgm0;        /* CoreSpreading: reset core size (<= 0: never reset)   rotorhover.jl:170     */
+    double cs_beta;        /*   reset when sigma/sgm0 > beta (1.5)                                       */
+    int32_t cs_itmax;      /*   RBF conjugate-gradient iterations (15)                                   */
+    double cs_tol;         /*   RBF residual tolerance (1e-3)                                            */
 } vpmo_schemes;
 
 /* Sets `s` to FLOWUnsteady's defaults (src/FLOWUnsteady_simulation.jl:36-44): rVPM, gaussianerf,
@@ -127,6 +131,19 @@ void vpmo_field_sfs(double *P, int64_t np, const vpmo_schemes *s, double a, doub
  * Advances *t and *nt.                                                                          */
 void vpmo_nextstep(double *P, int64_t np, const vpmo_schemes *s, double dt, const double *Uinf,
                    int32_t relax, double *t, int64_t *nt);
+
+/* zeta pass (vpm.zeta_direct / zeta_fmm): out[3*i..] (+)= sum_q v_q zeta_sigma_q(x_i - x_q), v = vs[3*q..].  With v = Gamma
+ * this is the particle-approximated vorticity omega(x_i) (rvpm.md:80-86). */
+void vpmo_zeta_direct(int32_t kernel, int64_t ns, const double *xs, const double *vs, const double *sig, int64_t nt,
+                      const double *xt, double *out);
+
+/* Core-spreading spatial adaptation (DOC rvpm.md:367; ctor examples/rotorhover/rotorhover.jl:170):
+ * if any non-static sigma/sgm0 > beta: omega_p = sum_q Gamma_q zeta_sigma_q(x_p - x_q) with the SPREAD cores, then every
+ * non-static sigma <- sgm0 and Gamma is re-fitted by conjugate gradients (per component, at most itmax iterations, stop when
+ * every component's residual 2-norm < tol) so that sum_q Gamma_q zeta_sgm0(x_p - x_q) = omega_p.  Static particles keep
+ * sigma and Gamma and act as fixed sources on both sides.  Returns the number of CG iterations (0: no reset needed). */
+int32_t vpmo_corespreading_reset(double *P, int64_t np, int32_t kernel, double sgm0, double beta, int32_t itmax, double tol,
+                                 double *residual3);
 
 /* Per-particle pieces, exported so the tests can pin each one separately. */
 void vpmo_relax_particle(double *p, int32_t relaxation, double rlxf);

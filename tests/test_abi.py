@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from flowunsteady_b200 import _lib
     from oracle import oracle as o
-    # first 18 members are shared with the oracle's struct (same order, same types)
-    assert [f[0] for f in _lib.Schemes._fields_[:18]] == [f[0] for f in o.Schemes._fields_]
+    # first 22 members are shared with the oracle's struct (same order, same types)
+    assert [f[0] for f in _lib.Schemes._fields_[:22]] == [f[0] for f in o.Schemes._fields_]
     s = _lib.Schemes()
     assert _lib.lib().vpmb200_default_schemes(C.byref(s)) == 0
     assert (s.kernel, s.f, s.g, s.transposed, s.relaxation, s.rlxf, s.integration) == (0, 0.0, 0.2, 1, 1, 0.3, 1)
