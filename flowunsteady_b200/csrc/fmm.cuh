@@ -422,28 +422,47 @@ __global__ void fmm_p2p_runs_kernel(const uint64_t* __restrict__ keys, unsigned 
 }
 
 constexpr int LEAF_WARPS = 8;     // leaves per CTA (one warp each)
-constexpr int LEAF_BATCH = 64;    // source records staged per warp and pass (5 KB)
+constexpr int LEAF_BATCH = 48;    // source records per staged batch (3.84 KB); two batches per warp (double buffer)
 
-// Stage up to LEAF_BATCH source records of the run list [k, b1) into this warp's shared-memory slice.  (run, off) is
-// the cursor: `off` records of run k are already consumed.  Returns the number of records staged.
-__device__ __forceinline__ int stage_batch(const int2* __restrict__ runs, unsigned int& k, unsigned int b1, int& off,
-                                           const double* __restrict__ rec, double* __restrict__ slice, int lane) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Issue the asynchronous copy (LDGSTS) of up to LEAF_BATCH source records of the run list [k, b1) into `slice`.
+// (k, off) is the cursor: `off` records of run k are already consumed.  Returns the number of records in flight.
+__device__ __forceinline__ int stage_batch_async(const int2* __restrict__ runs, unsigned int& k, unsigned int b1, int& off,
+                                                 const double* __restrict__ rec, double* __restrict__ slice, int lane) {
     int n = 0;
     while (k < b1 && n < LEAF_BATCH) {
         const int2 r = runs[k];
         const int take = min(r.y - off, LEAF_BATCH - n);
         const double2* g2 = reinterpret_cast<const double2*>(rec + (size_t)(r.x + off) * REC_REALS);
         double2* s2 = reinterpret_cast<double2*>(slice + (size_t)n * REC_REALS);
-        for (int q = lane; q < take * (REC_REALS / 2); q += 32) s2[q] = g2[q];
+        for (int q = lane; q < take * (REC_REALS / 2); q += 32) cp_async16(s2 + q, g2 + q);
         n += take;
         off += take;
         if (off == r.y) { ++k; off = 0; }
     }
+    cp_async_commit();
     return n;
 }
 
-// L2P + near-field P2P: one warp per leaf, one target per lane (leaves with more than 32 particles take several passes).
-// Outputs in Morton order: sU[k * lds + i], sJ[k * lds + i].
+// Lane mapping of one pass over `rem` (<= 32) targets: T = next power of two >= rem targets per pass and S = 32 / T
+// "ways" that split the source loop (lane = way * T + t).  Small leaves therefore still keep all 32 lanes busy; the ways'
+// partial sums are combined with xor-shuffles in a fixed order.
+__device__ __forceinline__ int pow2ceil32(int v) {
+    int t = 1;
+    while (t < v) t <<= 1;
+    return t;
+}
+__device__ __forceinline__ double xor_sum(double v, int T) {
+    for (int o = 16; o >= T; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// L2P + near-field P2P: one warp per leaf.  Outputs in Morton order: sU[k * lds + i], sJ[k * lds + i].
 template <int KERNEL, int P>
 __global__ void __launch_bounds__(32 * LEAF_WARPS)
 fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves,
@@ -452,27 +471,40 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
                    const double* __restrict__ L, const double* __restrict__ gh_table, double* __restrict__ sU,
                    double* __restrict__ sJ, int64_t lds) {
     using Ops = FmmOps<P>;
-    extern __shared__ __align__(16) double smem[];  // per warp: [3 * NL (padded even)] local expansion + [LEAF_BATCH * 10] records
+    // shared: [G/H table (gaussianerf)] then per warp { [3 * NL padded even] local expansion, 2 x [LEAF_BATCH * 10] records }
+    extern __shared__ __align__(16) double smem[];
     constexpr int LPAD = (3 * Ops::NL + 1) & ~1;
+    constexpr int TABD = KERNEL == K_GAUSSIANERF ? 2 * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0;
+    constexpr int WARPD = LPAD + 2 * LEAF_BATCH * REC_REALS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* sL = smem + (size_t)warp * (LPAD + LEAF_BATCH * REC_REALS);
-    double* slice = sL + LPAD;
+    if (KERNEL == K_GAUSSIANERF) {
+        const double2* g2 = reinterpret_cast<const double2*>(gh_table);
+        double2* t2 = reinterpret_cast<double2*>(smem);
+        for (int k = threadIdx.x; k < TABD / 2; k += blockDim.x) t2[k] = g2[k];
+    }
+    __syncthreads();
+    const double2* tab = reinterpret_cast<const double2*>(smem);
+    double* sL = smem + TABD + (size_t)warp * WARPD;
+    double* buf0 = sL + LPAD;
+    double* buf1 = buf0 + LEAF_BATCH * REC_REALS;
     const int leaf = blockIdx.x * LEAF_WARPS + warp;
-    if (leaf >= nleaves) return;   // whole warp exits together
+    if (leaf >= nleaves) return;   // whole warp exits together (after the only block-wide barrier)
     const int c = leaves[leaf];
     const FmmCell cell = cells[c];
     for (int k = lane; k < 3 * Ops::NL; k += 32) sL[k] = L[(size_t)c * 3 * Ops::NL + k];
     __syncwarp();
-    const double2* tab = reinterpret_cast<const double2*>(gh_table);  // read through L1 (23 KB, hot)
     const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
 
     for (int t0 = 0; t0 < cell.count; t0 += 32) {
-        const bool live = t0 + lane < cell.count;
-        const int i = cell.start + (live ? t0 + lane : 0);
+        const int rem = min(32, cell.count - t0);
+        const int T = pow2ceil32(rem), S = 32 / T;
+        const int t = lane & (T - 1), way = lane / T;
+        const bool live = t < rem;
+        const int i = cell.start + t0 + (live ? t : 0);
         const double px = sx[i], py = sy[i], pz = sz[i];
         UJAcc a;
         acc_zero(a);
-        {   // far field: psi_n = local expansion n; U = curl psi, J = grad U
+        if (way == 0) {   // far field: psi_n = local expansion n; U = curl psi, J = grad U
             double g[3][3], h[3][6];
 #pragma unroll
             for (int n = 0; n < 3; ++n) Ops::l2p(px - cell.cx, py - cell.cy, pz - cell.cz, sL + n * Ops::NL, g[n], h[n]);
@@ -484,15 +516,19 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
             a.j3 = h[2][3] - h[1][4]; a.j4 = h[0][4] - h[2][1]; a.j5 = h[1][1] - h[0][3];   // l = y: (yx, yy, yz) = 1, 3, 4
             a.j6 = h[2][4] - h[1][5]; a.j7 = h[0][5] - h[2][2]; a.j8 = h[1][2] - h[0][4];   // l = z: (zx, zy, zz) = 2, 4, 5
         }
+        // near field: double-buffered batches of source records, each way takes every S-th record
         unsigned int k = b0;
-        int off = 0;
-        while (k < b1) {
+        int off = 0, pb = 0;
+        __syncwarp();
+        int n_next = stage_batch_async(runs, k, b1, off, rec, buf0, lane);
+        while (true) {
+            cp_async_wait_all();
             __syncwarp();
-            const int ns = stage_batch(runs, k, b1, off, rec, slice, lane);
-            __syncwarp();
-            const double2* r2p = reinterpret_cast<const double2*>(slice);
-#pragma unroll 2
-            for (int s = 0; s < ns; ++s) {
+            const int ns = n_next;
+            if (ns == 0) break;
+            n_next = stage_batch_async(runs, k, b1, off, rec, pb ? buf0 : buf1, lane);
+            const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0);
+            for (int s = way; s < ns; s += S) {
                 const double2* r = r2p + s * (REC_REALS / 2);
                 const SrcCore sc = load_core(r);
                 double dx = px - sc.x, dy = py - sc.y, dz = pz - sc.z;
@@ -506,8 +542,16 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
                     uj_pair_general<KERNEL>(a, dx, dy, dz, r2, sc, r, tab);
                 }
             }
+            pb ^= 1;
         }
-        if (live) {
+        if (S > 1) {
+            a.u0 = xor_sum(a.u0, T); a.u1 = xor_sum(a.u1, T); a.u2 = xor_sum(a.u2, T);
+            a.j0 = xor_sum(a.j0, T); a.j1 = xor_sum(a.j1, T); a.j2 = xor_sum(a.j2, T);
+            a.j3 = xor_sum(a.j3, T); a.j4 = xor_sum(a.j4, T); a.j5 = xor_sum(a.j5, T);
+            a.j6 = xor_sum(a.j6, T); a.j7 = xor_sum(a.j7, T); a.j8 = xor_sum(a.j8, T);
+            a.w0 = xor_sum(a.w0, T); a.w1 = xor_sum(a.w1, T); a.w2 = xor_sum(a.w2, T);
+        }
+        if (live && way == 0) {
             a.j1 -= a.w2; a.j2 += a.w1;
             a.j3 += a.w2; a.j5 -= a.w0;
             a.j6 -= a.w1; a.j7 += a.w0;
@@ -528,30 +572,52 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
                      const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                      const double* __restrict__ sJ, int64_t lds, int transposed, const double* __restrict__ z_table,
                      double* __restrict__ sE) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(16) double smem[];   // [Z table (gaussianerf)] then per warp 2 x [LEAF_BATCH * 10] records
+    constexpr int TABD = KERNEL == K_GAUSSIANERF ? (VPM_GT_DEG + 1) * VPM_GT_NINT : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* slice = smem + (size_t)warp * (LEAF_BATCH * REC_REALS);
+    if (KERNEL == K_GAUSSIANERF)
+        for (int k = threadIdx.x; k < TABD; k += blockDim.x) smem[k] = z_table[k];
+    __syncthreads();
+    const double* ztab = smem;
+    double* buf0 = smem + TABD + (size_t)warp * (2 * LEAF_BATCH * REC_REALS);
+    double* buf1 = buf0 + LEAF_BATCH * REC_REALS;
     const int leaf = blockIdx.x * LEAF_WARPS + warp;
     if (leaf >= nleaves) return;
     const int c = leaves[leaf];
     const FmmCell cell = cells[c];
     const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
     for (int t0 = 0; t0 < cell.count; t0 += 32) {
-        const bool live = t0 + lane < cell.count;
-        const int i = cell.start + (live ? t0 + lane : 0);
+        const int rem = min(32, cell.count - t0);
+        const int T = pow2ceil32(rem), S = 32 / T;
+        const int t = lane & (T - 1), way = lane / T;
+        const bool live = t < rem;
+        const int i = cell.start + t0 + (live ? t : 0);
         const double px = sx[i], py = sy[i], pz = sz[i];
         EAcc a = {0, 0, 0, 0, 0, 0};
         unsigned int k = b0;
-        int off = 0;
-        while (k < b1) {
+        int off = 0, pb = 0;
+        __syncwarp();
+        int n_next = stage_batch_async(runs, k, b1, off, rec, buf0, lane);
+        while (true) {
+            cp_async_wait_all();
             __syncwarp();
-            const int ns = stage_batch(runs, k, b1, off, rec, slice, lane);
-            __syncwarp();
-            const double2* r2p = reinterpret_cast<const double2*>(slice);
-#pragma unroll 2
-            for (int s = 0; s < ns; ++s) estr_pair<KERNEL>(a, px, py, pz, r2p + s * (REC_REALS / 2), z_table);
+            const int ns = n_next;
+            if (ns == 0) break;
+            n_next = stage_batch_async(runs, k, b1, off, rec, pb ? buf0 : buf1, lane);
+            const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0);
+            // every lane runs the same number of iterations (estr_pair votes across the warp); out-of-range ways are masked
+            for (int s0 = 0; s0 < ns; s0 += S) {
+                const int sidx = s0 + way;
+                EAcc tmp = {0, 0, 0, 0, 0, 0};
+                estr_pair<KERNEL>(sidx < ns ? a : tmp, px, py, pz, r2p + (sidx < ns ? sidx : 0) * (REC_REALS / 2), ztab);
+            }
+            pb ^= 1;
         }
-        if (live) {
+        if (S > 1) {
+            a.a0 = xor_sum(a.a0, T); a.a1 = xor_sum(a.a1, T); a.a2 = xor_sum(a.a2, T);
+            a.b0 = xor_sum(a.b0, T); a.b1 = xor_sum(a.b1, T); a.b2 = xor_sum(a.b2, T);
+        }
+        if (live && way == 0) {
             double Jp[9];
 #pragma unroll
             for (int q = 0; q < 9; ++q) Jp[q] = sJ[(size_t)q * lds + i];

@@ -198,7 +198,8 @@ struct FmmPasses {
     template <int KERNEL>
     static cudaError_t leaves_uj(FmmWorkspace& w, int block, const double* gh_table, cudaStream_t st, uint64_t& launches) {
         (void)block;
-        const size_t smem = sizeof(double) * LEAF_WARPS * (((3 * Ops::NL + 1) & ~1) + (size_t)LEAF_BATCH * REC_REALS);
+        const size_t smem = sizeof(double) * ((KERNEL == K_GAUSSIANERF ? 2 * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0) +
+                                              LEAF_WARPS * (((3 * Ops::NL + 1) & ~1) + (size_t)2 * LEAF_BATCH * REC_REALS));
         auto kfn = fmm_leaf_uj_kernel<KERNEL, P>;
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -461,10 +462,12 @@ inline cudaError_t fmm_evaluate(FmmWorkspace& w, int p, int kernel, int block, c
 inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transposed, const double* z_table, cudaStream_t st,
                             uint64_t& launches) {
     (void)block;
-    const size_t smem = sizeof(double) * LEAF_WARPS * (size_t)LEAF_BATCH * REC_REALS;
     const int nl = w.leaf_hi - w.leaf_lo;
     if (nl <= 0) return cudaSuccess;
+    const size_t smem = sizeof(double) * ((kernel == K_GAUSSIANERF ? (VPM_GT_DEG + 1) * VPM_GT_NINT : 0) +
+                                          LEAF_WARPS * (size_t)2 * LEAF_BATCH * REC_REALS);
 #define FMM_ESTR_CASE(K)                                                                                                   \
+    cudaFuncSetAttribute(fmm_leaf_estr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
     fmm_leaf_estr_kernel<K><<<(nl + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(                            \
         w.cells, w.leaves + w.leaf_lo, nl, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
     switch (kernel) {
