@@ -1,0 +1,140 @@
+"""The drop-in boundary exercised in FLOWUnsteady's call order (/root/reference/src/FLOWUnsteady_simulation.jl:339-447):
+static particles appended -> vpm.nextstep -> statics removed from the end -> wake shed -> probes evaluated by appending
+zero-strength particles, calling pfield.UJ(pfield) and reading get_U (Vvpm_on_Xs, :494-570) -> wake treatment.
+The same loop is replayed on a plain numpy matrix with the CPU oracle; the particle matrices must agree."""
+import types
+
+import numpy as np
+import pytest
+
+from tests.util import relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _script(rng, nsteps=3, nshed=40, nstatic=12, nprobe=9):
+    """Deterministic inputs of a run: per step the static (bound) particles, the shed particles and the probe points."""
+    steps = []
+    for k in range(nsteps):
+        steps.append(dict(
+            statics=(rng.random((nstatic, 3)) * 0.2 + [0.0, 0.4, 0.4], rng.standard_normal((nstatic, 3)) * 0.02, np.full(nstatic, 0.06)),
+            shed=(rng.random((nshed, 3)) * [0.1, 1.0, 0.2] + [0.1 * k, 0.0, 0.4], rng.standard_normal((nshed, 3)) * 0.05,
+                  np.full(nshed, 0.08)),
+            probes=rng.random((nprobe, 3))))
+    return steps
+
+
+def _run_engine(steps, dt, Uinf, sfs, integration):
+    from flowunsteady_b200 import vpm, wake
+    pf = vpm.ParticleField(2000, Uinf=lambda t: Uinf, UJ=vpm.UJ_direct, SFS=sfs, integration=integration,
+                           relaxation=vpm.pedrizzetti)
+    sim = types.SimpleNamespace(nt=0, vehicle=types.SimpleNamespace(system=types.SimpleNamespace(O=np.zeros(3))))
+    treatment = wake.remove_particles_sphere(1.2 ** 2, 1, Xoff=[0.3, 0.5, 0.5])
+    V = []
+    for k, st in enumerate(steps):
+        org_np = vpm.get_np(pf)
+        if k > 0:
+            for X, G, s in zip(*st["statics"]):
+                vpm.add_particle(pf, X, G, s, vol=0, circulation=np.linalg.norm(G), static=True)
+            vpm.nextstep(pf, dt, relax=True)
+            for i in range(vpm.get_np(pf) - 1, org_np - 1, -1):        # simulation.jl:361-365
+                vpm.remove_particle(pf, i)
+        for X, G, s in zip(*st["shed"]):
+            vpm.add_particle(pf, X, G, s, vol=1e-3, circulation=np.linalg.norm(G))
+        # Vvpm_on_Xs the reference way: probes are particles
+        sta_np = vpm.get_np(pf)
+        for X in st["probes"]:
+            vpm.add_particle(pf, X, np.zeros(3), 1e-6, vol=0)
+        pf.UJ(pf)
+        Vref = np.array([vpm.get_U(P).copy() for P in vpm.iterator(pf, start_i=sta_np, include_static=True)])
+        for i in range(vpm.get_np(pf) - 1, sta_np - 1, -1):
+            vpm.remove_particle(pf, i)
+        Vfast = pf.U_at(st["probes"])                                  # the probe fast path must give the same numbers
+        assert relmax(Vfast, Vref) < 1e-13
+        V.append(Vref)
+        sim.nt = k
+        treatment(sim, pf, pf.t, dt)
+    return pf.particles[:pf.np].copy(), np.array(V), pf.t, pf.nt
+
+
+def _run_oracle(steps, dt, Uinf, kw):
+    from oracle import oracle as o
+    sch = o.default_schemes(**kw)
+    P = np.zeros((0, 43))
+    t, nt = 0.0, 0
+    V = []
+
+    def cols(X, G, s, vol, circ, static):
+        c = np.zeros((X.shape[0], 43))
+        c[:, 0:3], c[:, 3:6], c[:, 6], c[:, 7], c[:, 8], c[:, 42] = X, G, s, vol, circ, static
+        return c
+
+    for k, st in enumerate(steps):
+        org_np = P.shape[0]
+        if k > 0:
+            X, G, s = st["statics"]
+            P = np.ascontiguousarray(np.concatenate([P, cols(X, G, s, 0.0, np.linalg.norm(G, axis=1), 1.0)]))
+            t, nt = o.nextstep(P, sch, dt, Uinf, relax=True, t=t, nt=nt)
+            P = P[:org_np]
+        X, G, s = st["shed"]
+        P = np.ascontiguousarray(np.concatenate([P, cols(X, G, s, 1e-3, np.linalg.norm(G, axis=1), 0.0)]))
+        U, _ = o.uj_direct(sch.kernel, P[:, 0:3], P[:, 3:6], P[:, 6], st["probes"], accum=1)
+        V.append(U)
+        # pfield.UJ(pfield) also refreshed U, J of the field itself (probes contribute nothing: Gamma = 0)
+        Pq = np.ascontiguousarray(np.concatenate([P, cols(st["probes"], np.zeros_like(st["probes"]), np.full(len(st["probes"]), 1e-6), 0, 1.0, 0)]))
+        o.field_uj(Pq, sch)
+        P = np.ascontiguousarray(Pq[:P.shape[0]])
+        # remove_particles_sphere, replayed literally
+        n = P.shape[0]
+        c = np.array([0.3, 0.5, 0.5])
+        for i in range(n - 1, -1, -1):
+            if ((P[i, 0:3] - c) ** 2).sum() > 1.2 ** 2:
+                if i != n - 1:
+                    P[i] = P[n - 1]
+                n -= 1
+        P = np.ascontiguousarray(P[:n])
+    return P, np.array(V), t, nt
+
+
+@pytest.mark.parametrize("variant", ["rk3_nosfs", "euler_dynamic"])
+def test_simulation_loop_matches_oracle(variant):
+    from flowunsteady_b200 import vpm
+    steps = _script(np.random.default_rng(11))
+    dt, Uinf = 0.02, (1.0, 0.0, 0.1)
+    if variant == "rk3_nosfs":
+        got = _run_engine(steps, dt, Uinf, vpm.SFS_none, vpm.rungekutta3)
+        exp = _run_oracle(steps, dt, Uinf, dict(integration="rungekutta3"))
+        tol = 1e-11
+    else:
+        got = _run_engine(steps, dt, Uinf, vpm.SFS_Cd_twolevel_nobackscatter, vpm.euler)
+        exp = _run_oracle(steps, dt, Uinf, dict(integration="euler", sfs="dynamic", alpha=0.999, force_positive=1, clippings=1))
+        tol = 1e-8
+    Pg, Vg, tg, ntg = got
+    Po, Vo, to, nto = exp
+    assert Pg.shape == Po.shape and (tg, ntg) == (pytest.approx(to), nto)
+    assert relmax(Vg, Vo) < 1e-11
+    for sl in (slice(0, 3), slice(3, 6), slice(6, 7), slice(9, 12), slice(15, 24)):
+        assert relmax(Pg[:, sl], Po[:, sl]) < tol
+    assert np.allclose(Pg[:, 7:9], Po[:, 7:9], rtol=1e-14) and np.array_equal(Pg[:, 42], Po[:, 42])
+
+
+def test_lazy_sync_keeps_field_on_device():
+    """sync='lazy': no host traffic between calls until pull(); results equal the always-synchronised field."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import vpm
+    from tests.util import mixed_field
+    x, g, s, static = mixed_field(800, seed=2)
+    static = np.where(np.all(g == 0, axis=1), 1.0, static)
+    P = fb.new_particles(x, 50 * g, s, static=static)
+    outs = []
+    for mode in ("always", "lazy"):
+        pf = vpm.ParticleField(800, UJ=vpm.UJ_direct, sync=mode)
+        pf.particles[:800] = P
+        pf.np = 800
+        for _ in range(3):
+            vpm.nextstep(pf, 1e-3, relax=True)
+        if mode == "lazy":
+            assert pf.d2h_bytes == 0 and pf.h2d_bytes == 800 * 8 * 22   # ONE upload (state + M rows), nothing downloaded yet
+            pf.pull()
+        outs.append(pf.particles[:800].copy())
+    assert np.array_equal(outs[0], outs[1])
