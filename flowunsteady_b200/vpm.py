@@ -553,6 +553,89 @@ def nextstep(pfield: ParticleField, dt: float, relax: bool = False, custom_UJ=No
     pfield.nt += 1
 
 
+# ---- on-disk format: <file_name>[.<num>].h5 + .xmf  (vpm.save / vpm.read!, simulation.jl:263-265,436-440) ----------------
+_XMF = """<?xml version="1.0" ?>
+<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>
+<Xdmf Version="3.0">
+  <Domain>
+    <Grid Name="particles" GridType="Uniform">
+      <Time Value="{t}" />
+      <Geometry GeometryType="XYZ">
+        <DataItem DataType="Float" Dimensions="{np} 3" Format="HDF" Precision="8">{h5}:X</DataItem>
+      </Geometry>
+      <Topology Dimensions="{np}" Type="Polyvertex"/>
+{attrs}    </Grid>
+  </Domain>
+</Xdmf>
+"""
+_XMF_ATTR = """      <Attribute Center="Node" ElementCell="" ElementDegree="0" ElementFamily="" ItemType="" Name="{name}" Type="{kind}">
+        <DataItem DataType="{dtype}" Dimensions="{dims}" Format="HDF" Precision="8">{h5}:{name}</DataItem>
+      </Attribute>
+"""
+
+
+def save(pfield, file_name: str, path: str = "", add_num: bool = True, num: Optional[int] = None,
+         overwrite_time: Optional[float] = None) -> str:
+    """vpm.save(pfield, file_name; path, add_num, num, overwrite_time): writes `<file_name>.<num>.h5` (np, nt, t, X, Gamma,
+    sigma, circulation, vol, static, i) and the XDMF wrapper ParaView opens.  Returns the name of the .xmf file."""
+    import os
+
+    from . import h5min
+    if getattr(pfield, "_dev_dirty", 0):
+        pfield.pull()
+    n = int(pfield.np)
+    P = pfield.particles[:n]
+    fname = file_name + (f".{pfield.nt if num is None else num}" if add_num else "")
+    h5name = fname + ".h5"
+    t = pfield.t if overwrite_time is None else overwrite_time
+    data = {
+        "np": np.int64(n), "nt": np.int64(pfield.nt), "t": np.float64(t),
+        "X": P[:, X_INDEX], "Gamma": P[:, GAMMA_INDEX], "sigma": P[:, SIGMA_INDEX], "circulation": P[:, CIRCULATION_INDEX],
+        "vol": P[:, VOL_INDEX], "static": P[:, STATIC_INDEX], "i": np.arange(1, n + 1, dtype=np.int64),
+    }
+    h5min.write(os.path.join(path, h5name), data)
+    attrs = ""
+    for name, kind, dtype, dims in (("Gamma", "Vector", "Float", f"{n} 3"), ("sigma", "Scalar", "Float", f"{n}"),
+                                    ("circulation", "Scalar", "Float", f"{n}"), ("vol", "Scalar", "Float", f"{n}"),
+                                    ("static", "Scalar", "Float", f"{n}"), ("i", "Scalar", "Int", f"{n}")):
+        attrs += _XMF_ATTR.format(name=name, kind=kind, dtype=dtype, dims=dims, h5=h5name)
+    with open(os.path.join(path, fname + ".xmf"), "w") as f:
+        f.write(_XMF.format(t=repr(float(t)), np=n, h5=h5name, attrs=attrs))
+    return fname + ".xmf;"
+
+
+def read_(pfield, h5_fname: str, path: str = "", overwrite: bool = True, load_time: bool = True):
+    """vpm.read!(pfield, h5_fname; path, overwrite, load_time) — restart from a saved field (simulation.jl:263-265 calls it
+    with overwrite=true, load_time=false)."""
+    import os
+
+    from . import h5min
+    d = h5min.read(os.path.join(path, h5_fname))
+    n = int(d["np"])
+    if overwrite:
+        pfield.np = 0
+    if pfield.np + n > pfield.maxparticles:
+        raise RuntimeError(f"PARTICLE OVERFLOW. Max number of particles {pfield.maxparticles} has been reached")
+    cols = pfield.particles[pfield.np:pfield.np + n]
+    cols[:] = 0.0
+    cols[:, X_INDEX] = np.asarray(d["X"]).reshape(n, 3)
+    cols[:, GAMMA_INDEX] = np.asarray(d["Gamma"]).reshape(n, 3)
+    cols[:, SIGMA_INDEX] = np.asarray(d["sigma"]).reshape(n)
+    for key, row in (("circulation", CIRCULATION_INDEX), ("vol", VOL_INDEX), ("static", STATIC_INDEX)):
+        if key in d:
+            cols[:, row] = np.asarray(d[key]).reshape(n)
+    pfield.np += n
+    if load_time:
+        pfield.t = float(d["t"])
+        pfield.nt = int(d["nt"])
+    if hasattr(pfield, "mark_dirty"):
+        pfield.mark_dirty()
+    return pfield
+
+
+read = read_   # `read!` in Julia
+
+
 def monitor_enstrophy_value(pfield: ParticleField) -> float:
     """0.5 sum Gamma_p . omega(x_p) with omega = curl u from J (vpm.monitor_enstrophy, monitors.jl:614)."""
     P = pfield.particles[:pfield.np]
