@@ -459,10 +459,31 @@ class ParticleField:
         self._push(_E.FM_STATE)
         return self._engine.uj_probe(np.asarray(Xs, dtype=np.float64), want_J)
 
-    def fluiddomain(self, Xs):
+    def fluiddomain(self, Xs, method: str = "direct"):
         """U and W = curl u at arbitrary nodes (what vpm.computefluiddomain evaluates on its grids,
-        examples/rotorhover/rotorhover_fluiddomain.jl:93-104): probes only, the field's own targets are not touched."""
-        Uo, Jo = self.U_at(Xs, want_J=True)
+        examples/rotorhover/rotorhover_fluiddomain.jl:93-104).
+        method="direct": m probes x np sources with the pair kernel (exact; right for m up to ~1e5 or small fields);
+        method="fmm":    the reference's own way — the nodes join a scratch field as zero-strength particles (add_probe:
+                         Gamma = 0, sigma = 1e-6, simulation.jl:572), UJ_fmm runs once on np + m particles, and U, J are
+                         read at the nodes.  O(np + m): grids of 1e6..1e7 nodes (examples/vahana: 2.4e7) stay cheap."""
+        Xs = np.ascontiguousarray(Xs, dtype=np.float64).reshape(-1, 3)
+        if method == "direct":
+            Uo, Jo = self.U_at(Xs, want_J=True)
+        elif method == "fmm":
+            if self._dev_dirty:
+                self.pull()
+            m, n = Xs.shape[0], self.np
+            cols = np.zeros((n + m, NFIELDS))
+            cols[:n] = self.particles[:n]
+            cols[n:, X_INDEX] = Xs
+            cols[n:, SIGMA_INDEX] = 1e-6
+            with Engine(n + m, device=self._engine.device, schemes=self._schemes(_E.UJ_IDS["fmm"])) as scratch:
+                scratch.upload(cols)
+                scratch.uj()
+                scratch.download(cols, field_mask=_E.FM_U | _E.FM_J)
+            Uo, Jo = cols[n:, U_INDEX].copy(), cols[n:, J_INDEX].copy()
+        else:
+            raise ValueError("method must be 'direct' or 'fmm'")
         W = np.stack([Jo[:, 5] - Jo[:, 7], Jo[:, 6] - Jo[:, 2], Jo[:, 1] - Jo[:, 3]], -1)
         return Uo, W
 

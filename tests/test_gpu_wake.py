@@ -102,3 +102,39 @@ def test_fluiddomain_probes():
     Wo = np.stack([Jo[:, 5] - Jo[:, 7], Jo[:, 6] - Jo[:, 2], Jo[:, 1] - Jo[:, 3]], -1)
     assert np.abs(U - Uo).max() < 1e-12 * np.abs(Uo).max()
     assert np.abs(W - Wo).max() < 1e-12 * np.abs(Wo).max()
+
+
+def test_fluiddomain_through_fmm():
+    """Grid nodes evaluated the reference's way (zero-strength probe particles + UJ_fmm) agree with the direct probes to
+    the FMM's truncation error."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields, vpm
+    x, g, s = fields.vortex_rings(40_000)
+    pf = vpm.ParticleField(x.shape[0], UJ=vpm.UJ_fmm, fmm=vpm.FMM(p=4, ncrit=50, theta=0.4, nonzero_sigma=True))
+    pf.particles[:] = fb.new_particles(x, g, s)
+    pf.np = x.shape[0]
+    gx = np.linspace(-1.5, 1.5, 24)
+    nodes = np.stack(np.meshgrid(gx, gx, np.linspace(-0.5, 1.5, 16), indexing="ij"), -1).reshape(-1, 3)
+    Ud, Wd = pf.fluiddomain(nodes, method="direct")
+    Uf, Wf = pf.fluiddomain(nodes, method="fmm")
+    assert np.linalg.norm(Uf - Ud) / np.linalg.norm(Ud) < 2e-3
+    assert np.linalg.norm(Wf - Wd) / np.linalg.norm(Wd) < 2e-2
+
+
+def test_fp32_engine_runs_a_time_step():
+    """vpm_floattype = Float32 (simulation.jl:137): FP32 pair arithmetic, FP64 state — a whole RK3 step stays within
+    single-precision distance of the FP64 engine."""
+    import flowunsteady_b200 as fb
+    x, g, s, static = mixed_field(4000, seed=9)
+    static = np.where(np.all(g == 0, axis=1), 1.0, static)
+    P = fb.new_particles(x, 50 * g, s, static=static)
+    outs = []
+    for bits in (64, 32):
+        with fb.Engine(4000, float_bits=bits, schemes=fb.default_schemes()) as eng:
+            eng.upload(P)
+            eng.nextstep(2e-3, (1.0, 0.0, 0.0), relax=True)
+            outs.append(eng.download(np.zeros_like(P)))
+    d = outs[1][:, 0:3] - P[:, 0:3]
+    d64 = outs[0][:, 0:3] - P[:, 0:3]
+    assert np.abs(d - d64).max() < 1e-4 * np.abs(d64).max()
+    assert np.abs(outs[1][:, 3:6] - outs[0][:, 3:6]).max() < 1e-4 * np.abs(outs[0][:, 3:6]).max()
