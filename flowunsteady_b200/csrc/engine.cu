@@ -89,8 +89,8 @@ struct Geometry {
     int nchunks;
 };
 
-cudaError_t make_geometry(vpmb200_engine* e, int64_t nt, int ntiles, int ncomp, Geometry* g) {
-    const int nblocks = (int)blocks_for(nt, UJ_BT);
+cudaError_t make_geometry(vpmb200_engine* e, int64_t nt, int ntiles, int ncomp, Geometry* g, int targets_per_block = UJ_BT) {
+    const int nblocks = (int)blocks_for(nt, targets_per_block);
     const int slots = 2 * e->sm_count;
     int nchunks = 1;
     if (nblocks < 24 * slots && ntiles >= 16) {
@@ -138,7 +138,7 @@ cudaError_t launch_uj(vpmb200_engine* e, const double* rec, int ntiles, const do
                       const double* tz, int64_t nt, double* U, double* J, int64_t ldo, int accumulate) {
     if (nt <= 0) return cudaSuccess;
     Geometry g;
-    cudaError_t st = make_geometry(e, nt, ntiles, 12, &g);
+    cudaError_t st = make_geometry(e, nt, ntiles, 12, &g, e->float_bits == 32 ? F32_TPB : UJ_BT);
     if (st != cudaSuccess) return st;
     if (e->float_bits == 32) {
         auto kfn = uj_direct_f32_kernel<K>;
