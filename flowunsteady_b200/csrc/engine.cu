@@ -35,6 +35,8 @@ struct vpmb200_engine {
     size_t partial_doubles = 0;
     int sm_count = 148;
     int direct_sort = 1;        // Morton-order the direct path internally (vpmb200_set_option)
+    int64_t shard_sorted_np = -1;  // >= 0: fmm.perm / sx,sy,sz hold the Morton order of the current local particles
+                                   // (set by vpmb200_pack_uj_records, dropped by anything that moves or re-counts them)
     double* probe = nullptr;    // probe scratch: 3 (X) + 3 (U) + 9 (J) rows of probe_ld, + AoS staging
     int64_t probe_cap = 0;
     unsigned long long* counter = nullptr;
@@ -342,8 +344,54 @@ int32_t uj_local_from(vpmb200_engine* e, const double* rec, int64_t ntiles_, int
     return VPMB200_OK;
 }
 
+// ---- sharded driver with Morton-ordered LOCAL targets: pack_uj_records sorts the shard once per evaluation; every
+//      from_records call then runs the pair kernel on the sorted targets and scatter-adds into the state rows -----------
+int32_t shard_sort(vpmb200_engine* e) {
+    std::string err;
+    if (fmm_reserve_particles(e->fmm, e->np, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    FmmWorkspace& w = e->fmm;
+    if (fmm_sort(w, e->state, e->ld, e->np, e->stream, e->launches, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    const unsigned nb = blocks_for(e->np, PK_BT);
+    gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X, 1, e->np, w.perm, w.sx, w.lds);
+    gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X + 1, 1, e->np, w.perm, w.sy, w.lds);
+    gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X + 2, 1, e->np, w.perm, w.sz, w.lds);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 3;
+    e->shard_sorted_np = e->np;
+    return VPMB200_OK;
+}
+
+bool shard_is_sorted(const vpmb200_engine* e) {
+    return e->direct_sort && e->shard_sorted_np == e->np && e->np >= 4 * TILE_SRC && e->np < 2000000000LL;
+}
+
+int32_t uj_local_from_sorted(vpmb200_engine* e, const double* rec, int64_t ntiles, int accumulate) {
+    FmmWorkspace& w = e->fmm;
+    const unsigned nb = blocks_for(e->np, PK_BT);
+    CU_TRY(e, dispatch_uj(e, rec, (int)ntiles, w.sx, w.sy, w.sz, e->np, w.sU, w.sJ, w.lds, 0));
+    fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sU, w.lds, 3, e->np, w.perm, e->state + (size_t)F_U * e->ld, e->ld, accumulate);
+    fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sJ, w.lds, 9, e->np, w.perm, e->state + (size_t)F_J * e->ld, e->ld, accumulate);
+    CU_TRY(e, cudaGetLastError());
+    e->launches += 2;
+    return VPMB200_OK;
+}
+
+int32_t estr_local_from_sorted(vpmb200_engine* e, const double* rec, int64_t ntiles) {
+    FmmWorkspace& w = e->fmm;
+    const unsigned nb = blocks_for(e->np, PK_BT);
+    gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_J, 9, e->np, w.perm, w.sJ, w.lds);   // current total J
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    CU_TRY(e, dispatch_estr_at(e, rec, (int)ntiles, w.sx, w.sy, w.sz, w.sJ, w.lds, w.sE, w.lds, 0));
+    fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sE, w.lds, 3, e->np, w.perm, e->state + (size_t)F_SFS * e->ld, e->ld, 1);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    return VPMB200_OK;
+}
+
 // pfield.UJ(pfield; ...) through the GPU FMM (fmm.cuh): U, J [and the near-field E_str] of every particle
 int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
+    e->shard_sorted_np = -1;
     const vpmb200_schemes& s = e->sch;
     if (s.fmm_p < 2 || s.fmm_p > 6) return fail(e, VPMB200_ENOTSUP, "FMM expansion order p must be in 2..6");
     if (s.fmm_ncrit < 1 || s.fmm_ncrit > FMM_MAX_NCRIT) return fail(e, VPMB200_EINVAL, "FMM ncrit must be in 1..256");
@@ -383,6 +431,7 @@ int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
 // targets and a tile's 256 sources are compact boxes and the tile-level far/near classification of K1/K2 stays
 // effective for ANY input order (random fields, freshly shed particles...).  Results are scattered back to particle order.
 int32_t do_uj_direct_sorted(vpmb200_engine* e, int reset, int sfs) {
+    e->shard_sorted_np = -1;   // the shared sort scratch is about to be reused
     std::string err;
     if (fmm_reserve(e->fmm, e->np, 50, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
     FmmWorkspace& w = e->fmm;
@@ -430,6 +479,7 @@ int32_t check_fmm_settings(vpmb200_engine* e) {
 // (deterministic) and evaluates only its share of the leaves; rows outside its share are written as zeros so the ranks'
 // results combine with one all-reduce.  pass 0: tree + U, J.   pass 1: near-field E_str from the (reduced) J rows.
 int32_t do_fmm_global(vpmb200_engine* e, double* G, int64_t ldg, int64_t ntot, int part, int nparts, int pass) {
+    e->shard_sorted_np = -1;
     const vpmb200_schemes& s = e->sch;
     int32_t rc = check_fmm_settings(e);
     if (rc) return rc;
@@ -483,6 +533,7 @@ int32_t do_uj(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
 }
 
 int32_t do_stage(vpmb200_engine* e, int stage, double a, double b, double dt, const double* Uinf, int relax_inline) {
+    if (stage == VPMB200_STAGE_UPDATE) e->shard_sorted_np = -1;   // positions move
     if (e->np <= 0) return VPMB200_OK;
     const vpmb200_schemes& s = e->sch;
     const unsigned nb = blocks_for(e->np, PK_BT);
@@ -754,6 +805,7 @@ int32_t vpmb200_get_np(vpmb200_handle e, int64_t* np) {
 }
 
 static int32_t upload_block(vpmb200_engine* e, const double* particles, int64_t ld, int64_t n, int64_t dst0, uint32_t mask) {
+    e->shard_sorted_np = -1;
     if (n <= 0) return VPMB200_OK;
     if (ld < NFIELDS) return fail(e, VPMB200_EINVAL, "ld < 43");
     CU_TRY(e, cudaSetDevice(e->device));
@@ -816,6 +868,7 @@ int32_t vpmb200_add_particles(vpmb200_handle e, const double* cols, int64_t ld, 
 int32_t vpmb200_remove_particle(vpmb200_handle e, int64_t i) {
     CHECK_HANDLE(e);
     if (i < 0 || i >= e->np) return fail(e, VPMB200_EINVAL, "particle index out of range");
+    e->shard_sorted_np = -1;
     CU_TRY(e, cudaSetDevice(e->device));
     if (i != e->np - 1) {
         move_column_kernel<<<1, 64, 0, e->stream>>>(e->state, e->ld, i, e->np - 1);
@@ -831,6 +884,7 @@ int32_t vpmb200_remove_where(vpmb200_handle e, int32_t criterion, const double* 
     if (!params) return fail(e, VPMB200_EINVAL, "params is NULL");
     static const int nparams[5] = {0, 2, 2, 9, 4};
     if (criterion < 1 || criterion > 4) return fail(e, VPMB200_EINVAL, "unknown removal criterion");
+    e->shard_sorted_np = -1;
     if (removed) *removed = 0;
     const int64_t n = e->np;
     if (n <= 0) return VPMB200_OK;
@@ -1097,6 +1151,17 @@ int32_t vpmb200_pack_uj_records(vpmb200_handle e, double* dst) {
     CHECK_HANDLE(e);
     if (!dst) return fail(e, VPMB200_EINVAL, "dst is NULL");
     CU_TRY(e, cudaSetDevice(e->device));
+    if (e->direct_sort && e->np >= 4 * TILE_SRC && e->np < 2000000000LL) {
+        // the shard's tiles go out in Morton order (tight tile boxes for every receiver) and its targets are visited in
+        // the same order by the from_records calls that follow
+        int32_t rc = shard_sort(e);
+        if (rc) return rc;
+        pack_uj_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(e->state, e->ld, e->np, e->fmm.perm, dst);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        return VPMB200_OK;
+    }
+    e->shard_sorted_np = -1;
     return pack_uj(e, dst);
 }
 
@@ -1104,6 +1169,13 @@ int32_t vpmb200_pack_estr_records(vpmb200_handle e, double* dst) {
     CHECK_HANDLE(e);
     if (!dst) return fail(e, VPMB200_EINVAL, "dst is NULL");
     CU_TRY(e, cudaSetDevice(e->device));
+    if (shard_is_sorted(e)) {   // positions have not moved since the UJ pass of this evaluation: reuse its ordering
+        pack_estr_records_kernel<<<blocks_for(e->np, TILE_SRC), TILE_SRC, 0, e->stream>>>(
+            e->state, e->ld, e->np, e->fmm.perm, e->sch.transposed, zeta0_of(e->sch.kernel), e->sch.kernel == K_GAUSSIANERF ? 1 : 0, dst);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        return VPMB200_OK;
+    }
     return pack_estr(e, dst);
 }
 
@@ -1112,6 +1184,7 @@ int32_t vpmb200_uj_from_records(vpmb200_handle e, const double* tiles, int64_t n
     if (ntiles < 0 || (ntiles > 0 && !tiles)) return fail(e, VPMB200_EINVAL, "bad tiles");
     CU_TRY(e, cudaSetDevice(e->device));
     if (e->np <= 0) return VPMB200_OK;
+    if (shard_is_sorted(e)) return uj_local_from_sorted(e, tiles, ntiles, accumulate);
     return uj_local_from(e, tiles, ntiles, accumulate);  // ntiles == 0 writes zeros unless accumulating
 }
 
@@ -1120,6 +1193,7 @@ int32_t vpmb200_estr_from_records(vpmb200_handle e, const double* tiles, int64_t
     if (ntiles < 0 || (ntiles > 0 && !tiles)) return fail(e, VPMB200_EINVAL, "bad tiles");
     CU_TRY(e, cudaSetDevice(e->device));
     if (e->np <= 0 || ntiles == 0) return VPMB200_OK;
+    if (shard_is_sorted(e)) return estr_local_from_sorted(e, tiles, ntiles);
     CU_TRY(e, dispatch_estr(e, tiles, (int)ntiles));
     return VPMB200_OK;
 }
