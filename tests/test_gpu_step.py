@@ -189,3 +189,24 @@ def test_impulse_conserved_large():
     I1 = fields.ring_impulse(Pg[:, 0:3], Pg[:, 3:6])
     assert np.abs(I1 - I0).max() < 1e-4 * np.abs(I0).max()
     assert np.abs(Pg[:, 0:3] - x).max() > 0
+
+
+def test_nextstep_vs_frozen_oracle_fixture():
+    """GPU vs tests/golden/step_oracle.npz — the committed two-step results of every scheme family (96 particles)."""
+    import os
+    import sys
+    import flowunsteady_b200 as fb
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import gen_golden_step as gg
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_oracle.npz"))
+    for name, kw in gg.CASES.items():
+        P = G["P0"].copy()
+        if "corespreading" in name:
+            P[:, 6] = 0.2
+        with fb.Engine(P.shape[0], schemes=fb.default_schemes(**kw)) as eng:
+            eng.upload(P)
+            for _ in range(2):
+                eng.nextstep(5e-3, (1.0, -0.5, 0.25), relax=True)
+            Pg = eng.download(np.zeros_like(P))
+        tol = 1e-8 if ("dynamic" in name or "corespreading" in name) else 1e-11
+        _compare(Pg, G[name], tol, ["X", "Gamma", "sigma", "U", "J"])

@@ -177,3 +177,26 @@ def test_rvpm_sigma_closure():
         assert q[o.SIGMA] == pytest.approx(expect, rel=1e-15)
         # Gamma: dGamma/dt = S - 3 Z Gamma, Z = g * 3  -> z-component 6 - 3 (3 g) 2
         assert q[o.GAMMA + 2] == pytest.approx(2.0 + 1e-3 * (6.0 - 18.0 * g_), rel=1e-15)
+
+
+def _golden_step():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_oracle.npz"))
+
+
+def test_oracle_matches_its_frozen_step_fixture():
+    """tests/golden/step_oracle.npz (tools/gen_golden_step.py) freezes two-step results of every scheme family, so a
+    later edit of the oracle cannot silently move the goal posts of the GPU parity tests."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import gen_golden_step as gg
+    G = _golden_step()
+    assert np.array_equal(G["P0"], gg.field())
+    for name, kw in gg.CASES.items():
+        P = gg.field()
+        if "corespreading" in name:
+            P[:, o.SIGMA] = 0.2
+        t, nt = 0.0, 0
+        for _ in range(2):
+            t, nt = o.nextstep(P, o.default_schemes(**kw), 5e-3, (1.0, -0.5, 0.25), relax=True, t=t, nt=nt)
+        assert np.allclose(P, G[name], rtol=1e-12, atol=1e-14), name
