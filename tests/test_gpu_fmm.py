@@ -130,3 +130,18 @@ def test_fmm_parameter_validation():
             eng.set_schemes(fb.default_schemes(uj="fmm", **bad))
             with pytest.raises(fb.EngineError):
                 eng.uj()
+
+
+def test_fmm_is_deterministic():
+    """Two evaluations of the same field give bit-identical U, J, SFS (sorted pair lists, fixed-order reductions)."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    x, g, s = fields.random_field(30_000)
+    P = fb.new_particles(x, g, s)
+    outs = []
+    for _ in range(2):
+        with fb.Engine(P.shape[0], schemes=fb.default_schemes(uj="fmm")) as eng:
+            eng.upload(P)
+            eng.uj(True, True, True)
+            outs.append(eng.download(np.zeros_like(P)))
+    assert np.array_equal(outs[0], outs[1])

@@ -187,3 +187,26 @@ def test_probe_set_uses_split_geometry():
         Up, Jp = eng.uj_probe(probes, want_J=True)
     Uo, Jo = o.uj_direct("gaussianerf", x, g, s, probes, accum=1)
     assert relmax(Up, Uo) < TOL64 and relmax(Jp, Jo) < TOL64
+
+
+def test_full_size_1m_sampled_parity_and_properties():
+    """BASELINE configs[2] at its full size (N = 1,000,000 vortex rings, direct FP64): 2048 sampled targets against the
+    long-double oracle over all 10^6 sources, tr J = 0 at every particle, and bitwise reproducibility of a second run."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import engine as E, fields
+    from oracle import oracle as o
+    x, g, s = fields.vortex_rings(1_000_000)
+    P = fb.new_particles(x, g, s)
+    with fb.Engine(P.shape[0], schemes=fb.default_schemes()) as eng:
+        eng.upload(P)
+        eng.uj()
+        a = eng.download(np.zeros_like(P), field_mask=E.FM_U | E.FM_J)
+        eng.uj()
+        b = eng.download(np.zeros_like(P), field_mask=E.FM_U | E.FM_J)
+    assert np.array_equal(a, b)                                   # deterministic: fixed summation order, no atomics
+    idx = np.random.default_rng(1234).choice(x.shape[0], 2048, replace=False)
+    Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x[idx], accum=1)
+    assert relmax(a[idx, E.U:E.U + 3], Uo) < TOL64
+    assert relmax(a[idx, E.J:E.J + 9], Jo) < TOL64
+    Jm = a[:, E.J:E.J + 9]
+    assert np.abs(Jm[:, 0] + Jm[:, 4] + Jm[:, 8]).max() < 1e-11 * np.abs(Jm).max()
