@@ -19,15 +19,22 @@ struct EAcc {
     double a0, a1, a2, b0, b1, b2;
 };
 
+// Z(t) = exp(-t/2) = E[i] * exp(-u/2), i = rint(t / WZ), u = t - i WZ: one tabulated double per lookup, the second
+// factor is a degree-7 Taylor polynomial with immediate coefficients (|u/2| <= 1/32).  Requires 0 <= t < T_FAR.
 __device__ __forceinline__ double zeta_gauss_table(const double* __restrict__ ztab, double t) {
-    double m = fma(t, VPM_GT_INVW, MAGIC_RINT);
+    double m = fma(t, VPM_GZ_INVW, MAGIC_RINT);
     int i = __double2loint(m);
-    double u = fma(m - MAGIC_RINT, -VPM_GT_W, t);
-    const double* tp = ztab + i;
-    double z = tp[VPM_GT_DEG * VPM_GT_NINT];
-#pragma unroll
-    for (int k = VPM_GT_DEG - 1; k >= 0; --k) z = fma(z, u, tp[k * VPM_GT_NINT]);
-    return z;
+    double u = fma(m - MAGIC_RINT, -VPM_GZ_W, t);
+    const double e = ztab[i];
+    double z = VPM_GZ_C7;
+    z = fma(z, u, VPM_GZ_C6);
+    z = fma(z, u, VPM_GZ_C5);
+    z = fma(z, u, VPM_GZ_C4);
+    z = fma(z, u, VPM_GZ_C3);
+    z = fma(z, u, VPM_GZ_C2);
+    z = fma(z, u, VPM_GZ_C1);
+    z = fma(z, u, VPM_GZ_C0);
+    return z * e;
 }
 
 template <int KERNEL>
@@ -65,7 +72,7 @@ __device__ __forceinline__ void estr_pair(EAcc& a, double tx, double ty, double 
 }
 
 constexpr size_t estr_smem_bytes(int kernel) {
-    return sizeof(PairSmem) + (kernel == K_GAUSSIANERF ? sizeof(double) * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0);
+    return sizeof(PairSmem) + (kernel == K_GAUSSIANERF ? sizeof(double) * VPM_GZ_NINT : 0);
 }
 
 // Targets: positions tx/ty/tz and their J (component c at Jt[c * ldj + i]).  SFS component k accumulates at
@@ -97,7 +104,7 @@ estr_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double
         fence_mbar_init();
     }
     if (KERNEL == K_GAUSSIANERF)
-        for (int k = tid; k < (VPM_GT_DEG + 1) * VPM_GT_NINT; k += UJ_BT) ztab[k] = z_table[k];
+        for (int k = tid; k < VPM_GZ_NINT; k += UJ_BT) ztab[k] = z_table[k];
     __syncthreads();
     if (tid == 0 && ntiles > 0) {
         mbar_arrive_expect_tx(&sm.full[0], TILE_BYTES);

@@ -423,6 +423,8 @@ __global__ void fmm_p2p_runs_kernel(const uint64_t* __restrict__ keys, unsigned 
 
 constexpr int LEAF_WARPS = 8;     // leaves per CTA (one warp each)
 constexpr int LEAF_BATCH = 48;    // source records per staged batch (3.84 KB); two batches per warp (double buffer)
+constexpr int LEAF_MIN_T = 4;     // fewest targets per pass -> at most 8 ways; LEAF_BATCH is a multiple of 2 * 8
+static_assert(LEAF_BATCH % (2 * (32 / LEAF_MIN_T)) == 0, "a full batch must hold whole groups of 2 * ways records");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -430,13 +432,37 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// The run list [b0, b1) of a leaf, read 32 entries at a time (lane l holds entry base + l, the following 32 are already in
+// flight) and handed out by shuffle, so staging never waits on a dependent global load per run.
+struct RunReader {
+    const int2* runs;
+    unsigned int b1, base;
+    int2 cur, nxt;
+    __device__ __forceinline__ int2 fetch(unsigned int k) const { return k < b1 ? runs[k] : make_int2(0, 0); }
+    __device__ __forceinline__ void init(const int2* __restrict__ r, unsigned int b0, unsigned int b1_, int lane) {
+        runs = r; b1 = b1_; base = b0;
+        cur = fetch(b0 + lane);
+        nxt = fetch(b0 + 32 + lane);
+    }
+    // k is warp-uniform, k < b1, and never decreases or skips between calls
+    __device__ __forceinline__ int2 get(unsigned int k, int lane) {
+        if (k - base >= 32u) {
+            base += 32u;
+            cur = nxt;
+            nxt = fetch(base + 32u + lane);
+        }
+        const int j = (int)(k - base);
+        return make_int2(__shfl_sync(0xffffffffu, cur.x, j), __shfl_sync(0xffffffffu, cur.y, j));
+    }
+};
+
 // Issue the asynchronous copy (LDGSTS) of up to LEAF_BATCH source records of the run list [k, b1) into `slice`.
 // (k, off) is the cursor: `off` records of run k are already consumed.  Returns the number of records in flight.
-__device__ __forceinline__ int stage_batch_async(const int2* __restrict__ runs, unsigned int& k, unsigned int b1, int& off,
+__device__ __forceinline__ int stage_batch_async(RunReader& rr, unsigned int& k, unsigned int b1, int& off,
                                                  const double* __restrict__ rec, double* __restrict__ slice, int lane) {
     int n = 0;
     while (k < b1 && n < LEAF_BATCH) {
-        const int2 r = runs[k];
+        const int2 r = rr.get(k, lane);
         const int take = min(r.y - off, LEAF_BATCH - n);
         const double2* g2 = reinterpret_cast<const double2*>(rec + (size_t)(r.x + off) * REC_REALS);
         double2* s2 = reinterpret_cast<double2*>(slice + (size_t)n * REC_REALS);
@@ -449,17 +475,96 @@ __device__ __forceinline__ int stage_batch_async(const int2* __restrict__ runs, 
     return n;
 }
 
-// Lane mapping of one pass over `rem` (<= 32) targets: T = next power of two >= rem targets per pass and S = 32 / T
-// "ways" that split the source loop (lane = way * T + t).  Small leaves therefore still keep all 32 lanes busy; the ways'
-// partial sums are combined with xor-shuffles in a fixed order.
+// Round a landed batch of `ns` records up to a multiple of `mult` (= 2 * ways, a power of two <= 16) with copies of
+// record 0 whose strength is zero (UJ record: G' in quads 1.y and 2; E_str record: quads 2..4): they contribute exactly 0
+// on every branch and are never closer to a target than a real source, so the pair loop runs the same trip count on
+// every lane (warp votes stay legal) and needs no mask.
+template <bool ESTR>
+__device__ __forceinline__ int pad_batch(double* __restrict__ buf, int ns, int mult, int lane) {
+    const int np = (ns + mult - 1) & ~(mult - 1);
+    if (np != ns) {
+        double2* b2 = reinterpret_cast<double2*>(buf);
+        for (int q = lane; q < (np - ns) * (REC_REALS / 2); q += 32) {
+            const int part = q % (REC_REALS / 2);
+            double2 v = b2[part];
+            if (ESTR) {
+                if (part >= 2) v = make_double2(0.0, 0.0);
+            } else {
+                if (part == 1) v.y = 0.0;
+                if (part == 2) v = make_double2(0.0, 0.0);
+            }
+            b2[(ns + q / (REC_REALS / 2)) * (REC_REALS / 2) + part] = v;
+        }
+        __syncwarp();
+    }
+    return np;
+}
+
+// Lane mapping of one pass over a leaf's targets: T (a power of two) targets per pass and S = 32 / T "ways" that split
+// the source loop (lane = way * T + t); the ways' partial sums are combined with xor-shuffles in a fixed order.  A leaf
+// of `rem` < 32 remaining targets is taken as one pass with T = pow2ceil(rem), unless peeling off T/2 targets first leaves
+// a remainder that fits a strictly smaller pass (18 targets: 16 x 2 ways, then 2 of 4 x 8 ways = 20/32 of the cost
+// of one 32-target pass).  Each pass re-stages the leaf's sources (L2 hits); the split depends only on the count.
 __device__ __forceinline__ int pow2ceil32(int v) {
     int t = 1;
     while (t < v) t <<= 1;
     return t;
 }
+__device__ __forceinline__ void leaf_pass(int rem, int& T, int& take) {
+    if (rem >= 32) { T = 32; take = 32; return; }
+    const int Tc = max(pow2ceil32(rem), LEAF_MIN_T);
+    const int Tf = Tc >> 1;
+    if (rem < Tc && Tf >= LEAF_MIN_T && max(pow2ceil32(rem - Tf), LEAF_MIN_T) < Tf) { T = Tf; take = Tf; }
+    else { T = Tc; take = rem; }
+}
 __device__ __forceinline__ double xor_sum(double v, int T) {
     for (int o = 16; o >= T; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Two sources at a time for a whole warp (every lane must call: warp votes).  Inside an FMM near field nearly every pair
+// is in the regularised range, so the first vote selects a straight-line block with two independent table evaluations.
+template <int KERNEL>
+__device__ __forceinline__ void uj_pair2_leaf(UJAcc& a, double tx, double ty, double tz, const double2* __restrict__ recA,
+                                              const double2* __restrict__ recB, const double2* __restrict__ tab) {
+    const SrcCore sa = load_core(recA), sb = load_core(recB);
+    double dxa = tx - sa.x, dya = ty - sa.y, dza = tz - sa.z;
+    double dxb = tx - sb.x, dyb = ty - sb.y, dzb = tz - sb.z;
+    double r2a = fma(dza, dza, fma(dya, dya, dxa * dxa));
+    double r2b = fma(dzb, dzb, fma(dyb, dyb, dxb * dxb));
+    if (KERNEL == K_SINGULAR) {
+        const bool nza = nonzero_f64(r2a), nzb = nonzero_f64(r2b);
+        double Aa, Ba, Ab, Bb;
+        ab_singular(nza ? r2a : 1.0, Aa, Ba);
+        ab_singular(nzb ? r2b : 1.0, Ab, Bb);
+        uj_accumulate(a, dxa, dya, dza, sa.gx, sa.gy, sa.gz, nza ? Aa : 0.0, Ba);
+        uj_accumulate(a, dxb, dyb, dzb, sb.gx, sb.gy, sb.gz, nzb ? Ab : 0.0, Bb);
+    } else if (KERNEL == K_GAUSSIANERF) {
+        const double2 qa3 = recA[3], qb3 = recB[3];
+        const bool fa = __double2hiint(r2a) > __double2hiint(qa3.x), fb = __double2hiint(r2b) > __double2hiint(qb3.x);
+        if (__all_sync(0xffffffffu, !fa && !fb)) {
+            const double2 qa4 = recA[4], qb4 = recB[4];
+            double Aa, Ba, Ab, Bb;
+            ab_gauss_table(tab, r2a * qa4.y, qa3.y, qa4.x, Aa, Ba);
+            ab_gauss_table(tab, r2b * qb4.y, qb3.y, qb4.x, Ab, Bb);
+            Aa = nonzero_f64(r2a) ? Aa : 0.0;  // r == 0 skip (src/FLOWUnsteady_processing_force.jl:895)
+            Ab = nonzero_f64(r2b) ? Ab : 0.0;
+            uj_accumulate(a, dxa, dya, dza, sa.gx, sa.gy, sa.gz, Aa, Ba);
+            uj_accumulate(a, dxb, dyb, dzb, sb.gx, sb.gy, sb.gz, Ab, Bb);
+        } else if (__all_sync(0xffffffffu, fa && fb)) {
+            double Aa, Ba, Ab, Bb;
+            ab_singular(r2a, Aa, Ba);
+            ab_singular(r2b, Ab, Bb);
+            uj_accumulate(a, dxa, dya, dza, sa.gx, sa.gy, sa.gz, Aa, Ba);
+            uj_accumulate(a, dxb, dyb, dzb, sb.gx, sb.gy, sb.gz, Ab, Bb);
+        } else {
+            uj_pair_general<KERNEL>(a, dxa, dya, dza, r2a, sa, recA, tab);
+            uj_pair_general<KERNEL>(a, dxb, dyb, dzb, r2b, sb, recB, tab);
+        }
+    } else {
+        uj_pair_general<KERNEL>(a, dxa, dya, dza, r2a, sa, recA, tab);
+        uj_pair_general<KERNEL>(a, dxb, dyb, dzb, r2b, sb, recB, tab);
+    }
 }
 
 // L2P + near-field P2P: one warp per leaf.  Outputs in Morton order: sU[k * lds + i], sJ[k * lds + i].
@@ -474,7 +579,7 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
     // shared: [G/H table (gaussianerf)] then per warp { [3 * NL padded even] local expansion, 2 x [LEAF_BATCH * 10] records }
     extern __shared__ __align__(16) double smem[];
     constexpr int LPAD = (3 * Ops::NL + 1) & ~1;
-    constexpr int TABD = KERNEL == K_GAUSSIANERF ? 2 * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0;
+    constexpr int TABD = KERNEL == K_GAUSSIANERF ? VPM_GG_DOUBLES : 0;
     constexpr int WARPD = LPAD + 2 * LEAF_BATCH * REC_REALS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (KERNEL == K_GAUSSIANERF) {
@@ -495,11 +600,12 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
     __syncwarp();
     const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
 
-    for (int t0 = 0; t0 < cell.count; t0 += 32) {
-        const int rem = min(32, cell.count - t0);
-        const int T = pow2ceil32(rem), S = 32 / T;
+    for (int t0 = 0; t0 < cell.count;) {
+        int T, take;
+        leaf_pass(cell.count - t0, T, take);
+        const int S = 32 / T;
         const int t = lane & (T - 1), way = lane / T;
-        const bool live = t < rem;
+        const bool live = t < take;
         const int i = cell.start + t0 + (live ? t : 0);
         const double px = sx[i], py = sy[i], pz = sz[i];
         UJAcc a;
@@ -516,31 +622,24 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
             a.j3 = h[2][3] - h[1][4]; a.j4 = h[0][4] - h[2][1]; a.j5 = h[1][1] - h[0][3];   // l = y: (yx, yy, yz) = 1, 3, 4
             a.j6 = h[2][4] - h[1][5]; a.j7 = h[0][5] - h[2][2]; a.j8 = h[1][2] - h[0][4];   // l = z: (zx, zy, zz) = 2, 4, 5
         }
-        // near field: double-buffered batches of source records, each way takes every S-th record
+        // near field: double-buffered batches of source records; way w takes records w, w + S, ... two at a time
+        RunReader rr;
+        rr.init(runs, b0, b1, lane);
         unsigned int k = b0;
         int off = 0, pb = 0;
         __syncwarp();
-        int n_next = stage_batch_async(runs, k, b1, off, rec, buf0, lane);
+        int n_next = stage_batch_async(rr, k, b1, off, rec, buf0, lane);
         while (true) {
             cp_async_wait_all();
             __syncwarp();
-            const int ns = n_next;
+            int ns = n_next;
             if (ns == 0) break;
-            n_next = stage_batch_async(runs, k, b1, off, rec, pb ? buf0 : buf1, lane);
-            const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0);
-            for (int s = way; s < ns; s += S) {
-                const double2* r = r2p + s * (REC_REALS / 2);
-                const SrcCore sc = load_core(r);
-                double dx = px - sc.x, dy = py - sc.y, dz = pz - sc.z;
-                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                if (KERNEL == K_SINGULAR) {
-                    const bool nz = nonzero_f64(r2);
-                    double A, B;
-                    ab_singular(nz ? r2 : 1.0, A, B);
-                    uj_accumulate(a, dx, dy, dz, sc.gx, sc.gy, sc.gz, nz ? A : 0.0, B);
-                } else {
-                    uj_pair_general<KERNEL>(a, dx, dy, dz, r2, sc, r, tab);
-                }
+            n_next = stage_batch_async(rr, k, b1, off, rec, pb ? buf0 : buf1, lane);
+            ns = pad_batch<false>(pb ? buf1 : buf0, ns, 2 * S, lane);
+            const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0) + way * (REC_REALS / 2);
+            for (int s = 0; s < ns; s += 2 * S) {
+                const double2* ra = r2p + s * (REC_REALS / 2);
+                uj_pair2_leaf<KERNEL>(a, px, py, pz, ra, ra + S * (REC_REALS / 2), tab);
             }
             pb ^= 1;
         }
@@ -561,6 +660,35 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
 #pragma unroll
             for (int q = 0; q < 9; ++q) sJ[(size_t)q * lds + i] = o[3 + q];
         }
+        t0 += take;
+    }
+}
+
+// Two E_str sources at a time (every lane must call: warp vote).  gaussianerf: both beyond T_FAR for all lanes -> skip.
+template <int KERNEL>
+__device__ __forceinline__ void estr_pair2_leaf(EAcc& a, double tx, double ty, double tz, const double2* __restrict__ recA,
+                                                const double2* __restrict__ recB, const double* __restrict__ ztab) {
+    if (KERNEL == K_GAUSSIANERF) {
+        const double2 a0 = recA[0], a1 = recA[1], b0 = recB[0], b1 = recB[1];
+        double dxa = tx - a0.x, dya = ty - a0.y, dza = tz - a1.x;
+        double dxb = tx - b0.x, dyb = ty - b0.y, dzb = tz - b1.x;
+        const double ta = fma(dza, dza, fma(dya, dya, dxa * dxa)) * a1.y;
+        const double tb = fma(dzb, dzb, fma(dyb, dyb, dxb * dxb)) * b1.y;
+        const bool fa = ta >= VPM_GT_TFAR, fb = tb >= VPM_GT_TFAR;
+        if (__all_sync(0xffffffffu, fa && fb)) return;
+        double za = zeta_gauss_table(ztab, fa ? 0.0 : ta);
+        double zb = zeta_gauss_table(ztab, fb ? 0.0 : tb);
+        za = fa ? 0.0 : za;
+        zb = fb ? 0.0 : zb;
+        const double2 a2 = recA[2], a3 = recA[3], a4 = recA[4];
+        const double2 b2 = recB[2], b3 = recB[3], b4 = recB[4];
+        a.a0 = fma(za, a2.x, a.a0); a.a1 = fma(za, a2.y, a.a1); a.a2 = fma(za, a3.x, a.a2);
+        a.b0 = fma(za, a3.y, a.b0); a.b1 = fma(za, a4.x, a.b1); a.b2 = fma(za, a4.y, a.b2);
+        a.a0 = fma(zb, b2.x, a.a0); a.a1 = fma(zb, b2.y, a.a1); a.a2 = fma(zb, b3.x, a.a2);
+        a.b0 = fma(zb, b3.y, a.b0); a.b1 = fma(zb, b4.x, a.b1); a.b2 = fma(zb, b4.y, a.b2);
+    } else {
+        estr_pair<KERNEL>(a, tx, ty, tz, recA, ztab);
+        estr_pair<KERNEL>(a, tx, ty, tz, recB, ztab);
     }
 }
 
@@ -573,10 +701,10 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
                      const double* __restrict__ sJ, int64_t lds, int transposed, const double* __restrict__ z_table,
                      double* __restrict__ sE) {
     extern __shared__ __align__(16) double smem[];   // [Z table (gaussianerf)] then per warp 2 x [LEAF_BATCH * 10] records
-    constexpr int TABD = KERNEL == K_GAUSSIANERF ? (VPM_GT_DEG + 1) * VPM_GT_NINT : 0;
+    constexpr int TABD = KERNEL == K_GAUSSIANERF ? ((VPM_GZ_NINT + 1) & ~1) : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (KERNEL == K_GAUSSIANERF)
-        for (int k = threadIdx.x; k < TABD; k += blockDim.x) smem[k] = z_table[k];
+        for (int k = threadIdx.x; k < VPM_GZ_NINT; k += blockDim.x) smem[k] = z_table[k];
     __syncthreads();
     const double* ztab = smem;
     double* buf0 = smem + TABD + (size_t)warp * (2 * LEAF_BATCH * REC_REALS);
@@ -586,30 +714,32 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
     const int c = leaves[leaf];
     const FmmCell cell = cells[c];
     const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
-    for (int t0 = 0; t0 < cell.count; t0 += 32) {
-        const int rem = min(32, cell.count - t0);
-        const int T = pow2ceil32(rem), S = 32 / T;
+    for (int t0 = 0; t0 < cell.count;) {
+        int T, take;
+        leaf_pass(cell.count - t0, T, take);
+        const int S = 32 / T;
         const int t = lane & (T - 1), way = lane / T;
-        const bool live = t < rem;
+        const bool live = t < take;
         const int i = cell.start + t0 + (live ? t : 0);
         const double px = sx[i], py = sy[i], pz = sz[i];
         EAcc a = {0, 0, 0, 0, 0, 0};
+        RunReader rr;
+        rr.init(runs, b0, b1, lane);
         unsigned int k = b0;
         int off = 0, pb = 0;
         __syncwarp();
-        int n_next = stage_batch_async(runs, k, b1, off, rec, buf0, lane);
+        int n_next = stage_batch_async(rr, k, b1, off, rec, buf0, lane);
         while (true) {
             cp_async_wait_all();
             __syncwarp();
-            const int ns = n_next;
+            int ns = n_next;
             if (ns == 0) break;
-            n_next = stage_batch_async(runs, k, b1, off, rec, pb ? buf0 : buf1, lane);
-            const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0);
-            // every lane runs the same number of iterations (estr_pair votes across the warp); out-of-range ways are masked
-            for (int s0 = 0; s0 < ns; s0 += S) {
-                const int sidx = s0 + way;
-                EAcc tmp = {0, 0, 0, 0, 0, 0};
-                estr_pair<KERNEL>(sidx < ns ? a : tmp, px, py, pz, r2p + (sidx < ns ? sidx : 0) * (REC_REALS / 2), ztab);
+            n_next = stage_batch_async(rr, k, b1, off, rec, pb ? buf0 : buf1, lane);
+            ns = pad_batch<true>(pb ? buf1 : buf0, ns, 2 * S, lane);
+            const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0) + way * (REC_REALS / 2);
+            for (int s = 0; s < ns; s += 2 * S) {
+                const double2* ra = r2p + s * (REC_REALS / 2);
+                estr_pair2_leaf<KERNEL>(a, px, py, pz, ra, ra + S * (REC_REALS / 2), ztab);
             }
             pb ^= 1;
         }
@@ -635,6 +765,7 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
             sE[1 * lds + i] = e1 - a.b1;
             sE[2 * lds + i] = e2 - a.b2;
         }
+        t0 += take;
     }
 }
 

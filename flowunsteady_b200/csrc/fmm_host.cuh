@@ -198,7 +198,7 @@ struct FmmPasses {
     template <int KERNEL>
     static cudaError_t leaves_uj(FmmWorkspace& w, int block, const double* gh_table, cudaStream_t st, uint64_t& launches) {
         (void)block;
-        const size_t smem = sizeof(double) * ((KERNEL == K_GAUSSIANERF ? 2 * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0) +
+        const size_t smem = sizeof(double) * ((KERNEL == K_GAUSSIANERF ? VPM_GG_DOUBLES : 0) +
                                               LEAF_WARPS * (((3 * Ops::NL + 1) & ~1) + (size_t)2 * LEAF_BATCH * REC_REALS));
         auto kfn = fmm_leaf_uj_kernel<KERNEL, P>;
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -464,7 +464,7 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
     (void)block;
     const int nl = w.leaf_hi - w.leaf_lo;
     if (nl <= 0) return cudaSuccess;
-    const size_t smem = sizeof(double) * ((kernel == K_GAUSSIANERF ? (VPM_GT_DEG + 1) * VPM_GT_NINT : 0) +
+    const size_t smem = sizeof(double) * ((kernel == K_GAUSSIANERF ? ((VPM_GZ_NINT + 1) & ~1) : 0) +
                                           LEAF_WARPS * (size_t)2 * LEAF_BATCH * REC_REALS);
 #define FMM_ESTR_CASE(K)                                                                                                   \
     cudaFuncSetAttribute(fmm_leaf_estr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \

@@ -14,7 +14,7 @@
 //   * the pair math is re-derived in t = r^2/sigma^2 so the regularised (near) branch needs no sqrt, erf,
 //     exp or division: g/r^3 = G(t)/sigma^3 and (g'/(sigma r) - 3 g/r^2)/r^3 = H(t)/sigma^5 with G, H
 //     entire functions of t evaluated from a shared-memory piecewise-polynomial table
-//     (tools/gen_tables.py, max rel. error 3e-15).  For t >= T_FAR the Gaussian-erf kernel equals the
+//     (tools/gen_tables.py, max rel. error 2e-15; H = 2 dG/dt so one polynomial gives both).  For t >= T_FAR the Gaussian-erf kernel equals the
 //     singular kernel to < 2^-56, and a warp-uniform vote takes the branch with one MUFU.RSQ64H + 5 DFMA;
 //   * -1/(4 pi) is folded into the source's Gamma, the antisymmetric (Kronecker-delta) part of J is
 //     accumulated as a 3-vector and expanded once at the end, and per-tile partial sums are added to the
@@ -76,23 +76,26 @@ __device__ __forceinline__ void ab_singular(double r2, double& A, double& B) {
     B = (-3.0 * ri2) * A;
 }
 
-// Gaussian-erf near field from the table: t < T_FAR.
+// Gaussian-erf near field from the table: t < T_FAR.  H = 2 dG/dt, so one degree-7 polynomial per interval gives both:
+// value and derivative share the Horner recurrence (13 FMAs) and a lookup reads 64 B (four LDS.128) — the pair loops
+// are as much shared-memory-bandwidth bound as FP64 bound, so bytes per lookup matter (tools/gen_tables.py).
 __device__ __forceinline__ void ab_gauss_table(const double2* __restrict__ tab, double t, double sinv3, double sinv5,
                                                double& A, double& B) {
-    double m = fma(t, VPM_GT_INVW, MAGIC_RINT);
+    double m = fma(t, VPM_GG_INVW, MAGIC_RINT);
     int i = __double2loint(m);
-    double u = fma(m - MAGIC_RINT, -VPM_GT_W, t);
+    double u = fma(m - MAGIC_RINT, -VPM_GG_W, t);
     const double2* tp = tab + i;
-    double2 c = tp[VPM_GT_DEG * VPM_GT_NINT];
-    double G = c.x, H = c.y;
-#pragma unroll
-    for (int k = VPM_GT_DEG - 1; k >= 0; --k) {
-        c = tp[k * VPM_GT_NINT];
-        G = fma(G, u, c.x);
-        H = fma(H, u, c.y);
-    }
-    A = G * sinv3;
-    B = H * sinv5;
+    const double2 c67 = tp[3 * VPM_GG_NINT], c45 = tp[2 * VPM_GG_NINT], c23 = tp[VPM_GG_NINT], c01 = tp[0];
+    double d = c67.y;                 // derivative runs one step behind the value
+    double p = fma(d, u, c67.x);
+    d = fma(d, u, p); p = fma(p, u, c45.y);
+    d = fma(d, u, p); p = fma(p, u, c45.x);
+    d = fma(d, u, p); p = fma(p, u, c23.y);
+    d = fma(d, u, p); p = fma(p, u, c23.x);
+    d = fma(d, u, p); p = fma(p, u, c01.y);
+    d = fma(d, u, p); p = fma(p, u, c01.x);
+    A = p * sinv3;
+    B = (d + d) * sinv5;
 }
 
 // Winckelmans: G = (t + 2.5)/(t+1)^2.5, H = -(3 t + 10.5)/(t+1)^3.5   (SURVEY.md A.3 in the variable t)
@@ -282,7 +285,7 @@ __device__ __forceinline__ double box_dist2(const double* __restrict__ tb, const
 }
 
 constexpr size_t uj_smem_bytes(int kernel) {
-    return sizeof(PairSmem) + (kernel == K_GAUSSIANERF ? sizeof(double) * 2 * (VPM_GT_DEG + 1) * VPM_GT_NINT : 0);
+    return sizeof(PairSmem) + (kernel == K_GAUSSIANERF ? sizeof(double) * VPM_GG_DOUBLES : 0);
 }
 
 // Source-split launch geometry: when there are too few target blocks to fill the GPU for many waves (small N, or a
@@ -326,7 +329,7 @@ uj_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* 
     }
     if (KERNEL == K_GAUSSIANERF) {
         const double2* g2 = reinterpret_cast<const double2*>(gh_table);
-        for (int k = tid; k < (VPM_GT_DEG + 1) * VPM_GT_NINT; k += UJ_BT) tab[k] = g2[k];
+        for (int k = tid; k < VPM_GG_DOUBLES / 2; k += UJ_BT) tab[k] = g2[k];
     }
     __syncthreads();
     if (tid == 0 && ntiles > 0) {

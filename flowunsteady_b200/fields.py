@@ -9,6 +9,15 @@ from __future__ import annotations
 import numpy as np
 
 
+def floor_gamma(G: np.ndarray) -> np.ndarray:
+    """FLOWUnsteady's add_particle floors every component of Gamma to 5 eps ("or ExaFMM will blow up",
+    src/FLOWUnsteady_simulation.jl:464-468); without it a zero-strength particle makes the integrator's 1/|Gamma|^2 a 0/0."""
+    tiny = 5 * np.finfo(np.float64).eps
+    G = np.array(G, dtype=np.float64, copy=True)
+    G[np.abs(G) < tiny] = tiny
+    return G
+
+
 def random_field(n: int, seed: int | None = None):
     """Config 5: x ~ U[0,1)^3, Gamma ~ N(0,1)^3 / n, sigma = 2.125 n^(-1/3) (overlap-preserving), rng seed = n."""
     rng = np.random.default_rng(n if seed is None else seed)
@@ -99,7 +108,7 @@ def wing_wake(rows: int = 100, nspan: int = 101, b: float = 2.489, Vinf: float =
     dGdy = Gamma0 * eta / np.sqrt(1 - eta * eta) * (2 / b)
     gx = np.broadcast_to(dGdy * (b / (nspan - 1)) * dx, Xg.shape)
     X = np.stack([Xg.ravel(), Yg.ravel(), 0.02 * np.sin(3 * Xg.ravel())], -1)
-    G = np.stack([gx.ravel(), np.zeros(X.shape[0]), np.zeros(X.shape[0])], -1)
+    G = floor_gamma(np.stack([gx.ravel(), np.zeros(X.shape[0]), np.zeros(X.shape[0])], -1))
     return np.ascontiguousarray(X), np.ascontiguousarray(G), np.full(X.shape[0], sigma)
 
 
@@ -128,6 +137,63 @@ def rotor_wake(n_total: int = 70_000, blades: int = 2, R: float = 0.12, nfil: in
     X = np.concatenate(X)[:n_total]
     G = np.concatenate(G)[:n_total]
     return np.ascontiguousarray(X), np.ascontiguousarray(G), np.full(X.shape[0], sigma)
+
+
+def vahana_wake(n_total: int = 5_000_000, span: float = 5.86, nrotors: int = 8, R: float = 0.75, sigma: float = 0.0366,
+                _oversample: float | None = None):
+    """Config 4 stand-in (examples/vahana): `nrotors` helical rotor wakes trailing two wings plus two planar wing wakes,
+    clipped to the wake-treatment sphere of radius 1.25 b (examples/vahana/vahana.jl:356; b = 5.86 m), with the example's
+    core size sigma = lambda V dt / p_per_step ~ 0.0366 m (vahana.jl:109; lambda = 2.125, dt = 30/21600 s, p_per_step = 5).
+    Each rotor wake takes 1/(nrotors + 2) of the particles; the wing wakes are flat sheets of the same count.  The
+    generator oversamples (pilot run) so that exactly n_total particles remain inside the sphere."""
+    if _oversample is None:
+        pilot = vahana_wake(40_000, span, nrotors, R, sigma, _oversample=1.0)[0].shape[0]
+        _oversample = 1.03 * 40_000 / pilot
+    per = int(n_total * _oversample) // (nrotors + 2)
+    rsph = 1.25 * span
+    length = 1.6 * rsph                                        # wakes leave the sphere before they end
+    X, G = [], []
+    # rotor wakes: helices along -x (cruise), 2 blades x 21 trailing filaments, advance per revolution = 0.6 R
+    nfil, blades, adv = 21, 2, 0.6 * R
+    for r in range(nrotors):
+        wing = r % 2                                           # two wings (tandem): x offset and height differ
+        y0 = (r // 2 - (nrotors // 2 - 1) / 2) * (span / (nrotors // 2))
+        x0, z0 = (0.0 if wing == 0 else -0.45 * span), (0.0 if wing == 0 else 0.25 * span)
+        per_fil = max(2, per // (blades * nfil))
+        psi = np.linspace(0.0, 2 * np.pi * length / adv, per_fil)
+        dpsi = psi[1] - psi[0]
+        rfil = R * np.linspace(0.2, 1.0, nfil)
+        for bl in range(blades):
+            ang = psi[None, :] + 2 * np.pi * bl / blades + 0.37 * r
+            rr = rfil[:, None] * (1 - 0.12 * (1 - np.exp(-psi[None, :] / 6)))
+            x = x0 - adv * psi[None, :] / (2 * np.pi) * np.ones_like(rr)
+            y = y0 + rr * np.cos(ang)
+            z = z0 + rr * np.sin(ang)
+            gam = 2.0 * (rfil[:, None] / R) ** 2
+            tx = -adv / (2 * np.pi) * dpsi * np.ones_like(rr)
+            ty, tz = -rr * np.sin(ang) * dpsi, rr * np.cos(ang) * dpsi
+            X.append(np.stack([x, y, z], -1).reshape(-1, 3))
+            G.append(np.stack([gam * tx, gam * ty, gam * tz], -1).reshape(-1, 3))
+    # wing wakes: flat sheets behind each wing, elliptic loading
+    for wing in range(2):
+        nspan = 401
+        rows = max(2, per // nspan)
+        x0, z0 = (0.0 if wing == 0 else -0.45 * span), (0.0 if wing == 0 else 0.25 * span)
+        y = np.linspace(-span / 2, span / 2, nspan)
+        xs = x0 - length * (np.arange(rows) + 1) / rows
+        Xg, Yg = np.meshgrid(xs, y, indexing="ij")
+        eta = np.clip(2 * y / span, -0.999, 0.999)
+        dG = 8.0 * eta / np.sqrt(1 - eta * eta) * (2 / span) * (span / (nspan - 1)) * (length / rows)
+        X.append(np.stack([Xg.ravel(), Yg.ravel(), z0 + 0.05 * np.sin(2 * Xg.ravel())], -1))
+        G.append(np.stack([np.broadcast_to(dG, Xg.shape).ravel(), np.zeros(Xg.size), np.zeros(Xg.size)], -1))
+    X = np.concatenate(X)
+    G = np.concatenate(G)
+    keep = np.linalg.norm(X - np.array([-0.2 * span, 0.0, 0.1 * span]), axis=1) < rsph   # remove_particles_sphere
+    X, G = X[keep], G[keep]
+    if X.shape[0] > n_total:                                   # thin uniformly down to n_total
+        sel = np.linspace(0, X.shape[0] - 1, n_total).astype(np.int64)
+        X, G = X[sel], G[sel]
+    return np.ascontiguousarray(X), np.ascontiguousarray(floor_gamma(G)), np.full(X.shape[0], sigma)
 
 
 def ring_impulse(X: np.ndarray, G: np.ndarray) -> np.ndarray:

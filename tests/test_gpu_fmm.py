@@ -48,6 +48,23 @@ def test_theta_to_zero_is_the_direct_sum(kernel, n):
         assert relmax(F[:, 39:42], D[:, 39:42]) < 1e-11
 
 
+@pytest.mark.parametrize("kernel", ["gaussianerf", "winckelmans"])
+@pytest.mark.parametrize("ncrit", [5, 18, 33, 128])
+def test_near_field_lane_mapping_every_leaf_size(kernel, ncrit):
+    """The near-field kernel splits a leaf's targets into passes of T = 4..32 targets x 32/T ways and pads the last source
+    batch to whole groups of 2 x ways records (fmm.cuh: leaf_pass, pad_batch).  ncrit = 5 / 18 / 33 / 128 on a field with a
+    dense cluster produces leaves of every count from 1 to ncrit, i.e. every (T, ways) pair, multi-pass leaves and leaves
+    larger than a warp; theta -> 0 makes all of it near field, which must equal the direct sum to round-off."""
+    P = _field(1500, seed=5)
+    P[:400, 0:3] = P[0, 0:3] + 0.02 * (P[:400, 0:3] - P[0, 0:3])     # cluster: deep, unevenly filled leaves
+    D, _ = _eval(P, kernel=kernel, uj="direct", sfs=True)
+    F, st = _eval(P, kernel=kernel, uj="fmm", fmm_theta=1e-6, fmm_ncrit=ncrit, sfs=True)
+    assert st["m2l_pairs"] == 0
+    assert relmax(F[:, 9:12], D[:, 9:12]) < 1e-12
+    assert relmax(F[:, 15:24], D[:, 15:24]) < 1e-12
+    assert relmax(F[:, 39:42], D[:, 39:42]) < 1e-11
+
+
 def test_reference_defaults_error_vs_direct():
     """p = 4, ncrit = 50, theta = 0.4, nonzero_sigma = false (src/FLOWUnsteady_simulation.jl:43): the far field is the
     SINGULAR kernel wherever the acceptance criterion holds, even inside the regularised range, so the error against the

@@ -12,6 +12,14 @@ src/FLOWUnsteady_simulation.jl:37).  All three are entire functions of t.  Inter
 centred at i*W (i = rint(t/W)); coefficients are monomials in u = t - i*W, fitted at Chebyshev nodes in
 60-digit arithmetic.  Beyond T_FAR the kernel is singular to double precision (|1 - g| < 2^-56).
 
+The pair kernels are bound by shared-memory bandwidth on the table lookups as much as by the FP64 pipe, so the FP64
+tables are laid out for the fewest bytes per lookup:
+  * H = 2 dG/dt identically (differentiate g/s^3 with respect to t = s^2), so ONE polynomial serves both: the kernel
+    evaluates G and its derivative in the same Horner recurrence (value + derivative = 13 FMAs) from 8 coefficients
+    = 64 B per lookup (four LDS.128) instead of 16 coefficients.  Width 3/16 keeps the derivative exact to ~2e-15.
+  * Z(t) = exp(-c_i/2) * exp(-u/2): one tabulated double per interval (width 1/8), the second factor is a degree-7
+    Taylor polynomial with constant coefficients (|u/2| <= 1/32: truncation 2e-17) — 8 B per lookup instead of 64 B.
+
 Run:  python tools/gen_tables.py [--check]
 """
 import argparse
@@ -21,8 +29,10 @@ import mpmath as mp
 import numpy as np
 
 mp.mp.dps = 60
-W = mp.mpf("0.5")        # interval width
-DEG = 7                  # polynomial degree
+W = mp.mpf("0.5")        # interval width of the FP32 tables
+DEG = 7                  # polynomial degree (FP64 tables)
+WG = mp.mpf("0.1875")    # FP64 G table: interval width (exact in binary), value + derivative from one polynomial
+WZ = mp.mpf("0.125")     # FP64 Z table: interval width; Z = E[i] * taylor(exp(-u/2))
 T_FAR = 88.0             # |1 - g(sqrt(t))| < 1.2e-17 beyond this
 # FP32 variant of the pair kernel: lower degree, shorter range (|1 - g| < 3e-8 beyond T_FAR32)
 DEG32 = 4
@@ -85,30 +95,35 @@ def main():
     ap.add_argument("--check", action="store_true", help="also measure the double-precision error")
     args = ap.parse_args()
 
-    nint = int(mp.ceil(mp.mpf(T_FAR) / W)) + 2   # centres 0 .. nint-1 (rint can round up at T_FAR)
-    half = W / 2
-    tabs = {"G": [], "H": [], "Z": []}
-    for i in range(nint):
-        c = i * W
-        lo = c - half
-        # the first interval only needs [0, W/2]; fit it on [-W/2, W/2] anyway (functions are entire)
-        for name, fn in (("G", G), ("H", H), ("Z", Z)):
-            tabs[name].append([float(v) for v in fit(fn, c, half, DEG)])
-        del lo
+    nint = int(mp.ceil(mp.mpf(T_FAR) / WG)) + 2   # centres 0 .. nint-1 (rint can round up at T_FAR)
+    nintz = int(mp.ceil(mp.mpf(T_FAR) / WZ)) + 2
+    half = WG / 2
+    # the first interval only needs [0, W/2]; fit it on [-W/2, W/2] anyway (G is entire)
+    tabG = [[float(v) for v in fit(G, i * WG, half, DEG)] for i in range(nint)]
+    tabE = [float(mp.exp(-(i * WZ) / 2)) for i in range(nintz)]
+    zc = [float((-mp.mpf(1) / 2) ** k / mp.factorial(k)) for k in range(DEG + 1)]   # exp(-u/2) Taylor coefficients
 
     if args.check:
         rng = np.random.default_rng(1)
         worst = {"G": 0.0, "H": 0.0, "Z": 0.0}
         for i in range(nint - 1):
-            c = float(i * W)
-            for t in np.concatenate([c + (rng.random(40) - 0.5) * float(W), [c - 0.4999 * float(W), c + 0.4999 * float(W)]]):
+            c = float(i * WG)
+            for t in np.concatenate([c + (rng.random(24) - 0.5) * float(WG), [c - 0.4999 * float(WG), c + 0.4999 * float(WG)]]):
                 if t < 0:
                     continue
                 u = np.float64(t) - np.float64(c)
-                for name, fn in (("G", G), ("H", H), ("Z", Z)):
-                    ref = fn(t)
-                    got = horner64(tabs[name][i], u)
+                co = tabG[i]
+                p, d = np.float64(co[-1]), np.float64(0.0)
+                for ck in co[-2::-1]:
+                    d = d * u + p
+                    p = p * u + np.float64(ck)
+                for name, got, ref in (("G", p, G(t)), ("H", 2 * d, H(t))):
                     worst[name] = max(worst[name], float(abs((mp.mpf(float(got)) - ref) / ref)))
+        for t in rng.random(4000) * T_FAR:
+            i = int(np.rint(t / float(WZ)))
+            u = np.float64(t) - np.float64(i * float(WZ))
+            got = horner64(zc, u) * np.float64(tabE[i])
+            worst["Z"] = max(worst["Z"], float(abs((mp.mpf(float(got)) - Z(t)) / Z(t))))
         print("max relative error (float64 Horner):", worst)
         print("1 - g at T_FAR:", float(1 - G(T_FAR) * mp.mpf(T_FAR) ** mp.mpf("1.5")))
 
@@ -116,22 +131,30 @@ def main():
                         "gauss_table.inc")
     with open(path, "w") as f:
         f.write("// GENERATED by tools/gen_tables.py — do not edit.\n#pragma once\n")
-        f.write("// Piecewise degree-%d polynomials in u = t - i*W, t = (r/sigma)^2, i = rint(t/W).\n" % DEG)
-        f.write("// Entry [k][i] = {G_k, H_k} (coefficient of u^k on interval i);  Z table separate.\n")
+        f.write("// t = (r/sigma)^2.  G table: degree-%d polynomials in u = t - i*W, i = rint(t/W); entry [j][i] (a double2) =\n" % DEG)
+        f.write("// {c_2j, c_2j+1}, the coefficients of u^2j and u^(2j+1) on interval i.  G(t) = p(u), H(t) = 2 p'(u).\n")
+        f.write("// Z table: Z(t) = vpm_gt_Z[i] * sum_k VPM_GZ_Ck u^k with i = rint(t/WZ), u = t - i*WZ.\n")
         f.write("#define VPM_GT_W %s\n" % repr(float(W)))
         f.write("#define VPM_GT_INVW %s\n" % repr(float(1 / W)))
         f.write("#define VPM_GT_DEG %d\n" % DEG)
-        f.write("#define VPM_GT_NINT %d\n" % nint)
         f.write("#define VPM_GT_TFAR %s\n" % repr(T_FAR))
-        f.write("static const double vpm_gt_GH[(VPM_GT_DEG + 1) * VPM_GT_NINT * 2] = {\n")
+        f.write("#define VPM_GG_W %s\n" % repr(float(WG)))
+        f.write("#define VPM_GG_INVW %s\n" % repr(float(1 / WG)))
+        f.write("#define VPM_GG_NINT %d\n" % nint)
+        f.write("#define VPM_GG_DOUBLES ((VPM_GT_DEG + 1) * VPM_GG_NINT)\n")
+        f.write("#define VPM_GZ_W %s\n" % repr(float(WZ)))
+        f.write("#define VPM_GZ_INVW %s\n" % repr(float(1 / WZ)))
+        f.write("#define VPM_GZ_NINT %d\n" % nintz)
         for k in range(DEG + 1):
+            f.write("#define VPM_GZ_C%d %s\n" % (k, repr(zc[k])))
+        f.write("static const double vpm_gt_GH[VPM_GG_DOUBLES] = {\n")
+        for j in range((DEG + 1) // 2):
             for i in range(nint):
-                f.write("  %s, %s,\n" % (repr(tabs["G"][i][k]), repr(tabs["H"][i][k])))
+                f.write("  %s, %s,\n" % (repr(tabG[i][2 * j]), repr(tabG[i][2 * j + 1])))
         f.write("};\n")
-        f.write("static const double vpm_gt_Z[(VPM_GT_DEG + 1) * VPM_GT_NINT] = {\n")
-        for k in range(DEG + 1):
-            for i in range(nint):
-                f.write("  %s,\n" % repr(tabs["Z"][i][k]))
+        f.write("static const double vpm_gt_Z[VPM_GZ_NINT] = {\n")
+        for i in range(nintz):
+            f.write("  %s,\n" % repr(tabE[i]))
         f.write("};\n")
         # FP32 table (same interval width)
         nint32 = int(mp.ceil(mp.mpf(T_FAR32) / W)) + 2
