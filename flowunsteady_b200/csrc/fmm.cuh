@@ -567,10 +567,12 @@ __device__ __forceinline__ void uj_pair2_leaf(UJAcc& a, double tx, double ty, do
     }
 }
 
-// L2P + near-field P2P: one warp per leaf.  Outputs in Morton order: sU[k * lds + i], sJ[k * lds + i].
+// L2P + near-field P2P: one warp per leaf; warps are persistent and draw leaves from a global counter (leaf costs vary by
+// two orders of magnitude, so a static 8-leaves-per-CTA split leaves a quarter of the warp slots idle).  Outputs in
+// Morton order: sU[k * lds + i], sJ[k * lds + i].
 template <int KERNEL, int P>
 __global__ void __launch_bounds__(32 * LEAF_WARPS)
-fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves,
+fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves, unsigned int* next_leaf,
                    const int2* __restrict__ runs, const unsigned int* __restrict__ p2p_off, const double* __restrict__ rec,
                    const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                    const double* __restrict__ L, const double* __restrict__ gh_table, double* __restrict__ sU,
@@ -592,10 +594,14 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
     double* sL = smem + TABD + (size_t)warp * WARPD;
     double* buf0 = sL + LPAD;
     double* buf1 = buf0 + LEAF_BATCH * REC_REALS;
-    const int leaf = blockIdx.x * LEAF_WARPS + warp;
-    if (leaf >= nleaves) return;   // whole warp exits together (after the only block-wide barrier)
+  for (;;) {   // (body keeps its indentation: one leaf per trip)
+    int leaf = 0;
+    if (lane == 0) leaf = (int)atomicAdd(next_leaf, 1u);
+    leaf = __shfl_sync(0xffffffffu, leaf, 0);
+    if (leaf >= nleaves) break;    // whole warp leaves together (the only block-wide barrier is behind it)
     const int c = leaves[leaf];
     const FmmCell cell = cells[c];
+    __syncwarp();                  // every lane is done with the previous leaf's expansion
     for (int k = lane; k < 3 * Ops::NL; k += 32) sL[k] = L[(size_t)c * 3 * Ops::NL + k];
     __syncwarp();
     const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
@@ -662,6 +668,7 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
         }
         t0 += take;
     }
+  }
 }
 
 // Two E_str sources at a time (every lane must call: warp vote).  gaussianerf: both beyond T_FAR for all lanes -> skip.
@@ -695,7 +702,7 @@ __device__ __forceinline__ void estr_pair2_leaf(EAcc& a, double tx, double ty, d
 // Near-field E_str over the same leaf pairs (second pass; needs the converged J of targets and sources).
 template <int KERNEL>
 __global__ void __launch_bounds__(32 * LEAF_WARPS)
-fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves,
+fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves, unsigned int* next_leaf,
                      const int2* __restrict__ runs, const unsigned int* __restrict__ p2p_off, const double* __restrict__ rec,
                      const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                      const double* __restrict__ sJ, int64_t lds, int transposed, const double* __restrict__ z_table,
@@ -709,8 +716,11 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
     const double* ztab = smem;
     double* buf0 = smem + TABD + (size_t)warp * (2 * LEAF_BATCH * REC_REALS);
     double* buf1 = buf0 + LEAF_BATCH * REC_REALS;
-    const int leaf = blockIdx.x * LEAF_WARPS + warp;
-    if (leaf >= nleaves) return;
+  for (;;) {   // persistent warps, one leaf per trip (see fmm_leaf_uj_kernel)
+    int leaf = 0;
+    if (lane == 0) leaf = (int)atomicAdd(next_leaf, 1u);
+    leaf = __shfl_sync(0xffffffffu, leaf, 0);
+    if (leaf >= nleaves) break;
     const int c = leaves[leaf];
     const FmmCell cell = cells[c];
     const unsigned int b0 = p2p_off[c], b1 = p2p_off[c + 1];
@@ -767,6 +777,7 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
         }
         t0 += take;
     }
+  }
 }
 
 // Leaves in Morton order: key = first particle of the leaf.

@@ -35,7 +35,25 @@ struct FmmWorkspace {
     int ncells = 0, nleaves = 0, nlevels = 0;
     int leaf_lo = 0, leaf_hi = 0;   // leaves [leaf_lo, leaf_hi) are evaluated by the near-field / L2P kernels (multi-GPU split)
     unsigned int n_m2l = 0, n_p2p = 0;
+    int sms = 0;                    // multiprocessors of the current device (grid of the persistent leaf kernels)
 };
+
+// Grid of the persistent near-field kernels: as many CTAs as are resident at once (occupancy of `kfn` x SMs), fewer when
+// there are not enough leaves; zeroes the leaf counter (counters->next is idle once the traversal is done).
+template <typename K>
+inline cudaError_t fmm_leaf_grid(FmmWorkspace& w, K kfn, size_t smem, int nl, cudaStream_t st, int& grid) {
+    int per_sm = 0;
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 32 * LEAF_WARPS, smem);
+    if (eo != cudaSuccess) return eo;
+    if (w.sms == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&w.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    }
+    grid = std::min((nl + LEAF_WARPS - 1) / LEAF_WARPS, std::max(per_sm, 1) * w.sms);
+    return cudaMemsetAsync(&w.counters->next, 0, sizeof(unsigned int), st);
+}
 
 inline void fmm_free(FmmWorkspace& w) {
     void* ptrs[] = {w.keys, w.keys_alt, w.perm, w.perm_alt, w.sx, w.sy, w.sz, w.rec, w.sU, w.sJ, w.sE, w.cells, w.nchild,
@@ -205,8 +223,10 @@ struct FmmPasses {
         if (e != cudaSuccess) return e;
         const int nl = w.leaf_hi - w.leaf_lo;
         if (nl <= 0) return cudaSuccess;
-        kfn<<<(nl + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(
-            w.cells, w.leaves + w.leaf_lo, nl, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
+        int grid = 0;
+        if ((e = fmm_leaf_grid(w, kfn, smem, nl, st, grid)) != cudaSuccess) return e;
+        kfn<<<grid, 32 * LEAF_WARPS, smem, st>>>(
+            w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
         ++launches;
         return cudaGetLastError();
     }
@@ -466,10 +486,13 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
     if (nl <= 0) return cudaSuccess;
     const size_t smem = sizeof(double) * ((kernel == K_GAUSSIANERF ? ((VPM_GZ_NINT + 1) & ~1) : 0) +
                                           LEAF_WARPS * (size_t)2 * LEAF_BATCH * REC_REALS);
+    int grid = 0;
+    cudaError_t eg = cudaSuccess;
 #define FMM_ESTR_CASE(K)                                                                                                   \
     cudaFuncSetAttribute(fmm_leaf_estr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
-    fmm_leaf_estr_kernel<K><<<(nl + LEAF_WARPS - 1) / LEAF_WARPS, 32 * LEAF_WARPS, smem, st>>>(                            \
-        w.cells, w.leaves + w.leaf_lo, nl, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
+    if ((eg = fmm_leaf_grid(w, fmm_leaf_estr_kernel<K>, smem, nl, st, grid)) != cudaSuccess) return eg;                    \
+    fmm_leaf_estr_kernel<K><<<grid, 32 * LEAF_WARPS, smem, st>>>(                                                          \
+        w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
     switch (kernel) {
     case K_GAUSSIANERF: FMM_ESTR_CASE(K_GAUSSIANERF); break;
     case K_WINCKELMANS: FMM_ESTR_CASE(K_WINCKELMANS); break;

@@ -76,24 +76,26 @@ __device__ __forceinline__ void ab_singular(double r2, double& A, double& B) {
     B = (-3.0 * ri2) * A;
 }
 
-// Gaussian-erf near field from the table: t < T_FAR.  H = 2 dG/dt, so one degree-7 polynomial per interval gives both:
-// value and derivative share the Horner recurrence (13 FMAs) and a lookup reads 64 B (four LDS.128) — the pair loops
-// are as much shared-memory-bandwidth bound as FP64 bound, so bytes per lookup matter (tools/gen_tables.py).
+// Gaussian-erf near field from the table: t < T_FAR.  H = 2 dG/dt, so one degree-9 polynomial per interval gives both:
+// value and derivative share the Horner recurrence (17 FMAs) and a lookup reads 80 B (five LDS.128) instead of two
+// polynomials' 128 B — the pair loops are co-limited by shared-memory wavefronts and the FP64 pipe (tools/gen_tables.py).
 __device__ __forceinline__ void ab_gauss_table(const double2* __restrict__ tab, double t, double sinv3, double sinv5,
                                                double& A, double& B) {
+    static_assert(VPM_GG_DEG % 2 == 1, "coefficients are stored in pairs");
     double m = fma(t, VPM_GG_INVW, MAGIC_RINT);
     int i = __double2loint(m);
     double u = fma(m - MAGIC_RINT, -VPM_GG_W, t);
     const double2* tp = tab + i;
-    const double2 c67 = tp[3 * VPM_GG_NINT], c45 = tp[2 * VPM_GG_NINT], c23 = tp[VPM_GG_NINT], c01 = tp[0];
-    double d = c67.y;                 // derivative runs one step behind the value
-    double p = fma(d, u, c67.x);
-    d = fma(d, u, p); p = fma(p, u, c45.y);
-    d = fma(d, u, p); p = fma(p, u, c45.x);
-    d = fma(d, u, p); p = fma(p, u, c23.y);
-    d = fma(d, u, p); p = fma(p, u, c23.x);
-    d = fma(d, u, p); p = fma(p, u, c01.y);
-    d = fma(d, u, p); p = fma(p, u, c01.x);
+    double2 c[(VPM_GG_DEG + 1) / 2];
+#pragma unroll
+    for (int j = 0; j < (VPM_GG_DEG + 1) / 2; ++j) c[j] = tp[j * VPM_GG_NINT];   // {c_2j, c_2j+1}
+    double d = c[(VPM_GG_DEG - 1) / 2].y;   // derivative runs one step behind the value
+    double p = fma(d, u, c[(VPM_GG_DEG - 1) / 2].x);
+#pragma unroll
+    for (int j = (VPM_GG_DEG - 1) / 2 - 1; j >= 0; --j) {
+        d = fma(d, u, p); p = fma(p, u, c[j].y);
+        d = fma(d, u, p); p = fma(p, u, c[j].x);
+    }
     A = p * sinv3;
     B = (d + d) * sinv5;
 }

@@ -15,8 +15,11 @@ centred at i*W (i = rint(t/W)); coefficients are monomials in u = t - i*W, fitte
 The pair kernels are bound by shared-memory bandwidth on the table lookups as much as by the FP64 pipe, so the FP64
 tables are laid out for the fewest bytes per lookup:
   * H = 2 dG/dt identically (differentiate g/s^3 with respect to t = s^2), so ONE polynomial serves both: the kernel
-    evaluates G and its derivative in the same Horner recurrence (value + derivative = 13 FMAs) from 8 coefficients
-    = 64 B per lookup (four LDS.128) instead of 16 coefficients.  Width 3/16 keeps the derivative exact to ~2e-15.
+    evaluates G and its derivative in the same Horner recurrence (value + derivative = 17 FMAs) from 10 coefficients
+    = 80 B per lookup (five LDS.128) instead of 16 coefficients = 128 B (eight).  Width 1/2 with degree 9 keeps both to
+    3e-16.  (A width-3/16 degree-7 variant reads 64 B per lookup but the lanes of a warp then fall into ~3x more distinct
+    intervals, which costs more shared-memory wavefronts than it saves: measured 842 M "bank conflicts" per 1M-particle
+    near-field pass, profiles/r01b_fmm_leaf_n1m.txt.)
   * Z(t) = exp(-c_i/2) * exp(-u/2): one tabulated double per interval (width 1/8), the second factor is a degree-7
     Taylor polynomial with constant coefficients (|u/2| <= 1/32: truncation 2e-17) — 8 B per lookup instead of 64 B.
 
@@ -31,7 +34,8 @@ import numpy as np
 mp.mp.dps = 60
 W = mp.mpf("0.5")        # interval width of the FP32 tables
 DEG = 7                  # polynomial degree (FP64 tables)
-WG = mp.mpf("0.1875")    # FP64 G table: interval width (exact in binary), value + derivative from one polynomial
+WG = mp.mpf("0.5")       # FP64 G table: interval width (exact in binary), value + derivative from one polynomial
+GDEG = 9                 # ... of this degree (odd: coefficients are stored in pairs)
 WZ = mp.mpf("0.125")     # FP64 Z table: interval width; Z = E[i] * taylor(exp(-u/2))
 T_FAR = 88.0             # |1 - g(sqrt(t))| < 1.2e-17 beyond this
 # FP32 variant of the pair kernel: lower degree, shorter range (|1 - g| < 3e-8 beyond T_FAR32)
@@ -99,7 +103,7 @@ def main():
     nintz = int(mp.ceil(mp.mpf(T_FAR) / WZ)) + 2
     half = WG / 2
     # the first interval only needs [0, W/2]; fit it on [-W/2, W/2] anyway (G is entire)
-    tabG = [[float(v) for v in fit(G, i * WG, half, DEG)] for i in range(nint)]
+    tabG = [[float(v) for v in fit(G, i * WG, half, GDEG)] for i in range(nint)]
     tabE = [float(mp.exp(-(i * WZ) / 2)) for i in range(nintz)]
     zc = [float((-mp.mpf(1) / 2) ** k / mp.factorial(k)) for k in range(DEG + 1)]   # exp(-u/2) Taylor coefficients
 
@@ -131,7 +135,7 @@ def main():
                         "gauss_table.inc")
     with open(path, "w") as f:
         f.write("// GENERATED by tools/gen_tables.py — do not edit.\n#pragma once\n")
-        f.write("// t = (r/sigma)^2.  G table: degree-%d polynomials in u = t - i*W, i = rint(t/W); entry [j][i] (a double2) =\n" % DEG)
+        f.write("// t = (r/sigma)^2.  G table: degree-%d polynomials in u = t - i*W, i = rint(t/W); entry [j][i] (a double2) =\n" % GDEG)
         f.write("// {c_2j, c_2j+1}, the coefficients of u^2j and u^(2j+1) on interval i.  G(t) = p(u), H(t) = 2 p'(u).\n")
         f.write("// Z table: Z(t) = vpm_gt_Z[i] * sum_k VPM_GZ_Ck u^k with i = rint(t/WZ), u = t - i*WZ.\n")
         f.write("#define VPM_GT_W %s\n" % repr(float(W)))
@@ -141,14 +145,15 @@ def main():
         f.write("#define VPM_GG_W %s\n" % repr(float(WG)))
         f.write("#define VPM_GG_INVW %s\n" % repr(float(1 / WG)))
         f.write("#define VPM_GG_NINT %d\n" % nint)
-        f.write("#define VPM_GG_DOUBLES ((VPM_GT_DEG + 1) * VPM_GG_NINT)\n")
+        f.write("#define VPM_GG_DEG %d\n" % GDEG)
+        f.write("#define VPM_GG_DOUBLES ((VPM_GG_DEG + 1) * VPM_GG_NINT)\n")
         f.write("#define VPM_GZ_W %s\n" % repr(float(WZ)))
         f.write("#define VPM_GZ_INVW %s\n" % repr(float(1 / WZ)))
         f.write("#define VPM_GZ_NINT %d\n" % nintz)
         for k in range(DEG + 1):
             f.write("#define VPM_GZ_C%d %s\n" % (k, repr(zc[k])))
         f.write("static const double vpm_gt_GH[VPM_GG_DOUBLES] = {\n")
-        for j in range((DEG + 1) // 2):
+        for j in range((GDEG + 1) // 2):
             for i in range(nint):
                 f.write("  %s, %s,\n" % (repr(tabG[i][2 * j]), repr(tabG[i][2 * j + 1])))
         f.write("};\n")
