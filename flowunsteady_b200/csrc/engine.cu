@@ -44,6 +44,12 @@ struct vpmb200_engine {
     int64_t nt = 0;
     FmmWorkspace fmm;           // GPU FMM scratch (allocated on first UJ_fmm call)
     std::vector<int> fmm_lvl;   // cell index range of every tree level
+    // DynamicSFS evaluates twice at the SAME positions and strengths (test filter sigma*alpha, then domain filter): the
+    // second evaluation reuses the tree, the interaction lists and the local expansions of the first (the far field is
+    // the singular kernel when nonzero_sigma = false, so it does not depend on sigma).  do_sfs sets the hint.
+    int fmm_hint = 0;           // 1: the next UJ_fmm call should keep its far field; 2: the next call may reuse it
+    bool fmm_far_valid = false;
+    int64_t fmm_far_np = -1;
     uint64_t launches = 0;      // kernels enqueued by this handle (bench.py's gpu_launches)
     vpmb200_schemes sch;
     std::string err;
@@ -392,6 +398,10 @@ int32_t estr_local_from_sorted(vpmb200_engine* e, const double* rec, int64_t nti
 // pfield.UJ(pfield; ...) through the GPU FMM (fmm.cuh): U, J [and the near-field E_str] of every particle
 int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     e->shard_sorted_np = -1;
+    const int hint = e->fmm_hint;
+    const bool far_was_valid = e->fmm_far_valid;
+    e->fmm_hint = 0;
+    e->fmm_far_valid = false;
     const vpmb200_schemes& s = e->sch;
     if (s.fmm_p < 2 || s.fmm_p > 6) return fail(e, VPMB200_ENOTSUP, "FMM expansion order p must be in 2..6");
     if (s.fmm_ncrit < 1 || s.fmm_ncrit > FMM_MAX_NCRIT) return fail(e, VPMB200_EINVAL, "FMM ncrit must be in 1..256");
@@ -403,12 +413,21 @@ int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     if (reset_sfs && (rc = zero_rows(e, F_SFS, 3))) return rc;
     if (e->np <= 0) return VPMB200_OK;
     std::string err;
-    if (fmm_reserve(e->fmm, e->np, s.fmm_ncrit, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+    const bool reuse = hint == 2 && far_was_valid && !s.fmm_nonzero_sigma && e->fmm_far_np == e->np;
     FmmWorkspace& w = e->fmm;
-    cudaError_t st = fmm_build(w, e->state, e->ld, e->np, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream, e->launches, err);
-    if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
+    if (reuse) {
+        CU_TRY(e, fmm_regather(w, e->state, e->ld, e->np, e->stream, e->launches));
+    } else {
+        if (fmm_reserve(e->fmm, e->np, s.fmm_ncrit, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+        cudaError_t st = fmm_build(w, e->state, e->ld, e->np, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream, e->launches, err);
+        if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
+    }
     const int block = std::min(256, std::max(32, (s.fmm_ncrit + 31) / 32 * 32));
-    CU_TRY(e, fmm_evaluate(w, s.fmm_p, s.kernel, block, e->gh_table, e->fmm_lvl, e->stream, e->launches));
+    CU_TRY(e, fmm_evaluate(w, s.fmm_p, s.kernel, block, e->gh_table, e->fmm_lvl, e->stream, e->launches, reuse));
+    if (hint == 1 && !s.fmm_nonzero_sigma) {
+        e->fmm_far_valid = true;
+        e->fmm_far_np = e->np;
+    }
     const unsigned nb = blocks_for(e->np, PK_BT);
     fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sU, w.lds, 3, e->np, w.perm, e->state + (size_t)F_U * e->ld, e->ld, reset ? 0 : 1);
     fmm_scatter_kernel<<<nb, PK_BT, 0, e->stream>>>(w.sJ, w.lds, 9, e->np, w.perm, e->state + (size_t)F_J * e->ld, e->ld, reset ? 0 : 1);
@@ -608,10 +627,15 @@ int32_t do_sfs(vpmb200_engine* e, double a, double b) {
     case VPMB200_SFS_DYNAMIC:
         if (!first) return do_uj(e, 1, 1, 1);
         if ((rc = do_stage(e, VPMB200_STAGE_SCALE_SIGMA_TEST, 0, 0, 0, nullptr, 0))) return rc;
+        e->fmm_hint = 1;   // UJ_fmm: keep the tree and the far field ...
         if ((rc = do_uj(e, 1, 1, 1))) return rc;
         if ((rc = do_stage(e, VPMB200_STAGE_STORE_TEST, 0, 0, 0, nullptr, 0))) return rc;
         if ((rc = do_stage(e, VPMB200_STAGE_SCALE_SIGMA_DOMAIN, 0, 0, 0, nullptr, 0))) return rc;
-        if ((rc = do_uj(e, 1, 1, 1))) return rc;
+        e->fmm_hint = 2;   // ... only sigma changed in between: same positions, strengths, lists and local expansions
+        rc = do_uj(e, 1, 1, 1);
+        e->fmm_hint = 0;
+        e->fmm_far_valid = false;
+        if (rc) return rc;
         if ((rc = do_stage(e, VPMB200_STAGE_DYNAMIC_COEFF, 0, 0, 0, nullptr, 0))) return rc;
         return do_stage(e, VPMB200_STAGE_CLIP_CONTROL, 0, 0, 0, nullptr, 0);
     default:

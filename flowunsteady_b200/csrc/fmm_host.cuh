@@ -458,23 +458,35 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     return cudaSuccess;
 }
 
+// Re-gather the Morton-ordered source records from the state (same positions and strengths, new core sizes): what an
+// evaluation needs when the tree, the lists and the far field of the previous one are still valid (fmm_evaluate far_valid).
+inline cudaError_t fmm_regather(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, cudaStream_t st, uint64_t& launches) {
+    fmm_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(soa, ld, n, w.perm, w.sx, w.sy, w.sz, w.rec);
+    ++launches;
+    return cudaGetLastError();
+}
+
+// far_valid: the local expansions L of the previous evaluation are still right (same positions, strengths, tree and lists;
+// the far field is the singular kernel, so it does not depend on sigma): skip P2M/M2M/M2L/L2L and only redo L2P + near field.
 template <int P>
 inline cudaError_t fmm_evaluate_p(FmmWorkspace& w, int kernel, int block, const double* gh_table, const std::vector<int>& lvl,
-                                  cudaStream_t st, uint64_t& launches) {
+                                  cudaStream_t st, uint64_t& launches, bool far_valid) {
     cudaError_t e;
-    if ((e = FmmPasses<P>::upward(w, lvl, st, launches)) != cudaSuccess) return e;
-    if ((e = FmmPasses<P>::downward(w, lvl, st, launches)) != cudaSuccess) return e;
+    if (!far_valid) {
+        if ((e = FmmPasses<P>::upward(w, lvl, st, launches)) != cudaSuccess) return e;
+        if ((e = FmmPasses<P>::downward(w, lvl, st, launches)) != cudaSuccess) return e;
+    }
     return FmmPasses<P>::leaves_uj(w, kernel, block, gh_table, st, launches);
 }
 
 inline cudaError_t fmm_evaluate(FmmWorkspace& w, int p, int kernel, int block, const double* gh_table,
-                                const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches) {
+                                const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, bool far_valid = false) {
     switch (p) {
-    case 2: return fmm_evaluate_p<2>(w, kernel, block, gh_table, lvl, st, launches);
-    case 3: return fmm_evaluate_p<3>(w, kernel, block, gh_table, lvl, st, launches);
-    case 4: return fmm_evaluate_p<4>(w, kernel, block, gh_table, lvl, st, launches);
-    case 5: return fmm_evaluate_p<5>(w, kernel, block, gh_table, lvl, st, launches);
-    case 6: return fmm_evaluate_p<6>(w, kernel, block, gh_table, lvl, st, launches);
+    case 2: return fmm_evaluate_p<2>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
+    case 3: return fmm_evaluate_p<3>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
+    case 4: return fmm_evaluate_p<4>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
+    case 5: return fmm_evaluate_p<5>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
+    case 6: return fmm_evaluate_p<6>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -138,6 +138,43 @@ def test_nextstep_with_fmm_tracks_direct():
     assert rel_l2(res["fmm"][:, 3:6], res["direct"][:, 3:6]) < 1e-3
 
 
+def test_dynamic_sfs_far_field_reuse_is_bit_exact():
+    """DynamicSFS evaluates twice at the same positions (test filter, domain filter).  vpmb200_nextstep lets the second
+    UJ_fmm evaluation reuse the tree, the lists and the local expansions of the first (engine.cu do_sfs / fmm_hint); the
+    same step driven stage by stage through the ABI rebuilds everything.  Both must give identical bits."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import engine as E, fields
+    from flowunsteady_b200.dist import RK3
+    x, g, s = fields.vortex_rings(40_000)
+    P = fb.new_particles(x, g, s)
+    sch = dict(uj="fmm", sfs="dynamic", alpha=0.999, force_positive=1, clippings=1, controls=3, fmm_nonzero_sigma=0)
+    dt, Uinf = 2e-3, (0.1, 0.0, 0.0)
+    with fb.Engine(P.shape[0], schemes=fb.default_schemes(**sch)) as eng:
+        eng.upload(P)
+        eng.nextstep(dt, Uinf, relax=True)
+        A = eng.download(np.zeros_like(P)).copy()
+    with fb.Engine(P.shape[0], schemes=fb.default_schemes(**sch)) as eng:
+        eng.upload(P)
+        eng.stage(E.STAGE_ZERO_M)
+        for a, b in RK3:
+            if a == 0.0:
+                eng.stage(E.STAGE_SCALE_SIGMA_TEST)
+                eng.uj(True, True, True)
+                eng.stage(E.STAGE_STORE_TEST)
+                eng.stage(E.STAGE_SCALE_SIGMA_DOMAIN)
+                eng.uj(True, True, True)
+                eng.stage(E.STAGE_DYNAMIC_COEFF)
+                eng.stage(E.STAGE_CLIP_CONTROL)
+            else:
+                eng.uj(True, True, True)
+            eng.stage(E.STAGE_UPDATE, a, b, dt, Uinf)
+        eng.uj(True, False, False)
+        eng.stage(E.STAGE_RELAX)
+        B = eng.download(np.zeros_like(P)).copy()
+    assert np.all(np.isfinite(A))
+    assert np.array_equal(A, B)
+
+
 def test_fmm_parameter_validation():
     import flowunsteady_b200 as fb
     P = _field(100)
