@@ -349,6 +349,13 @@ def run_ours(args):
             e2e = {"value": evals * float(n) * float(n) / dt_e2e, "unit": "interactions/s",
                    "h2d_bytes_per_step": pf.h2d_bytes // ksteps, "d2h_bytes_per_step": pf.d2h_bytes // ksteps,
                    "ms_per_step": dt_e2e * 1e3, "steps": ksteps, "api": "flowunsteady_b200.vpm.nextstep(ParticleField)"}
+            # the copies alone, engine idle (outside the timed region): the same masks nextstep uses, pinned host matrix
+            t0 = time.perf_counter()
+            pf.engine.upload(pf.particles, n, E.FM_STATE | E.FM_M)
+            e2e["h2d_ms_alone"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            pf.engine.download(pf.particles, n, E.FM_ALL & ~(E.FM_VOL | E.FM_CIRCULATION | E.FM_STATIC))
+            e2e["d2h_ms_alone"] = (time.perf_counter() - t0) * 1e3
         else:
             # sharded: every rank uploads its shard from pinned host memory, steps, and downloads its shard
             host = torch.empty((hi - lo, 43), dtype=torch.float64, pin_memory=True)

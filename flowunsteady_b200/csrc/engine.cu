@@ -828,14 +828,29 @@ int32_t vpmb200_get_np(vpmb200_handle e, int64_t* np) {
     return VPMB200_OK;
 }
 
+// Contiguous runs [c0, c1) of particle columns selected by a field-group mask (group table of include/vpmb200.h).
+static int mask_runs(uint32_t mask, int runs[13][2]) {
+    static const int first[14] = {F_X, F_GAMMA, F_SIGMA, F_VOL, F_CIRC, F_U, F_W, F_J, F_PSE, F_M, F_C, F_SFS, F_STATIC, NFIELDS};
+    int n = 0;
+    for (int g = 0; g < 13; ++g) {
+        if (!((mask >> g) & 1u)) continue;
+        if (n > 0 && runs[n - 1][1] == first[g]) runs[n - 1][1] = first[g + 1];
+        else { runs[n][0] = first[g]; runs[n][1] = first[g + 1]; ++n; }
+    }
+    return n;
+}
+
 static int32_t upload_block(vpmb200_engine* e, const double* particles, int64_t ld, int64_t n, int64_t dst0, uint32_t mask) {
     e->shard_sorted_np = -1;
     if (n <= 0) return VPMB200_OK;
     if (ld < NFIELDS) return fail(e, VPMB200_EINVAL, "ld < 43");
     CU_TRY(e, cudaSetDevice(e->device));
-    // host (ld per particle) -> device AoS staging (NFIELDS per particle)
-    CU_TRY(e, cudaMemcpy2DAsync(e->aos, sizeof(double) * NFIELDS, particles, sizeof(double) * ld, sizeof(double) * NFIELDS,
-                                (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    // host (ld per particle) -> device AoS staging (NFIELDS per particle): only the selected column runs cross the bus
+    int runs[13][2];
+    const int nr = mask_runs(mask & VPMB200_FM_ALL, runs);
+    for (int r = 0; r < nr; ++r)
+        CU_TRY(e, cudaMemcpy2DAsync(e->aos + runs[r][0], sizeof(double) * NFIELDS, particles + runs[r][0], sizeof(double) * ld,
+                                    sizeof(double) * (runs[r][1] - runs[r][0]), (size_t)n, cudaMemcpyHostToDevice, e->stream));
     dim3 grid(blocks_for(n, 32), (NFIELDS + 31) / 32), block(32, 8);
     aos_to_soa_kernel<<<grid, block, 0, e->stream>>>(e->aos, NFIELDS, n, e->state, e->ld, dst0, mask);
     CU_TRY(e, cudaGetLastError());
@@ -863,17 +878,16 @@ int32_t vpmb200_download(vpmb200_handle e, double* particles, int64_t ld, int64_
     if (!particles) return fail(e, VPMB200_EINVAL, "particles is NULL");
     if (ld < NFIELDS) return fail(e, VPMB200_EINVAL, "ld < 43");
     CU_TRY(e, cudaSetDevice(e->device));
-    if (field_mask != VPMB200_FM_ALL) {
-        // rows not selected must keep the host's values: stage the host block first
-        CU_TRY(e, cudaMemcpy2DAsync(e->aos, sizeof(double) * NFIELDS, particles, sizeof(double) * ld,
-                                    sizeof(double) * NFIELDS, (size_t)np, cudaMemcpyHostToDevice, e->stream));
-    }
     dim3 grid(blocks_for(np, 32), (NFIELDS + 31) / 32), block(32, 8);
     soa_to_aos_kernel<<<grid, block, 0, e->stream>>>(e->state, e->ld, np, e->aos, NFIELDS, field_mask);
     CU_TRY(e, cudaGetLastError());
     e->launches++;
-    CU_TRY(e, cudaMemcpy2DAsync(particles, sizeof(double) * ld, e->aos, sizeof(double) * NFIELDS, sizeof(double) * NFIELDS,
-                                (size_t)np, cudaMemcpyDeviceToHost, e->stream));
+    // columns not selected keep the host's values: only the selected column runs are written (strided 2-D copies)
+    int runs[13][2];
+    const int nr = mask_runs(field_mask & VPMB200_FM_ALL, runs);
+    for (int r = 0; r < nr; ++r)
+        CU_TRY(e, cudaMemcpy2DAsync(particles + runs[r][0], sizeof(double) * ld, e->aos + runs[r][0], sizeof(double) * NFIELDS,
+                                    sizeof(double) * (runs[r][1] - runs[r][0]), (size_t)np, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(e, cudaStreamSynchronize(e->stream));
     return VPMB200_OK;
 }

@@ -14,6 +14,7 @@ Every numerical call goes to libvpmb200.so (CUDA); there is no CPU implementatio
 from __future__ import annotations
 
 import math
+import time
 from dataclasses import dataclass, field as _dc_field
 from typing import Callable, Iterator, Optional, Sequence
 
@@ -338,6 +339,8 @@ class ParticleField:
         self._dev_dirty = 0         # field-group mask the device holds newer than the host
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.h2d_seconds = 0.0      # wall time inside upload calls
+        self.d2h_seconds = 0.0      # wall time inside download calls (includes waiting for the enqueued step)
 
     # ---- scheme translation ------------------------------------------------------------------------------------
     def _schemes(self, uj_id: int, integration_id: Optional[int] = None):
@@ -390,8 +393,10 @@ class ParticleField:
 
     def _push(self, mask: int = _E.FM_ALL):
         if self.sync == "always" or self._host_dirty:
-            self._engine.upload(self.particles, self.np, mask)
-            self.h2d_bytes += self.np * 8 * _rows(mask)
+            t0 = time.perf_counter()
+            self._engine.upload(self.particles, self.np, mask)     # returns after the copy (borrowed pointer)
+            self.h2d_seconds += time.perf_counter() - t0
+            self.h2d_bytes += self.np * 8 * _rows(mask)            # exactly what crosses the bus (selected column runs)
             self._host_dirty = False
         self._engine.set_time(self.t, self.nt)
 
@@ -405,7 +410,9 @@ class ParticleField:
         """Bring device results back into `particles`."""
         mask = self._dev_dirty if mask is None else mask
         if mask and self.np > 0:
-            self._engine.download(self.particles, self.np, mask)
+            t0 = time.perf_counter()
+            self._engine.download(self.particles, self.np, mask)   # waits for the step, then copies
+            self.d2h_seconds += time.perf_counter() - t0
             self.d2h_bytes += self.np * 8 * _rows(mask)
         self._dev_dirty &= ~mask
 

@@ -173,6 +173,36 @@ def test_partial_download_keeps_host_rows():
     assert not np.any(host[:, 9:12] == 7.0)
 
 
+def test_masked_transfers_move_only_the_selected_column_runs():
+    """Masked upload / download cross the bus as strided 2-D copies of the selected column runs (engine.cu: mask_runs):
+    every group mask, a padded host matrix (ld > 43), and columns outside the mask untouched on both sides."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import engine as E
+    n = 777
+    rng = np.random.default_rng(9)
+    A = rng.random((n, 43))
+    B = rng.random((n, 43)) + 10.0
+    big = np.zeros((n, 48))                       # ld = 48: rows are not contiguous
+    big[:, :43] = B
+    cols = {E.FM_X: (0, 3), E.FM_GAMMA: (3, 6), E.FM_SIGMA: (6, 7), E.FM_VOL: (7, 8), E.FM_CIRCULATION: (8, 9), E.FM_U: (9, 12),
+            E.FM_VORTICITY: (12, 15), E.FM_J: (15, 24), E.FM_PSE: (24, 27), E.FM_M: (27, 36), E.FM_C: (36, 39),
+            E.FM_SFS: (39, 42), E.FM_STATIC: (42, 43)}
+    for mask in (E.FM_X | E.FM_GAMMA | E.FM_J, E.FM_STATE, E.FM_SIGMA | E.FM_STATIC, E.FM_ALL & ~E.FM_M, E.FM_ALL):
+        sel = np.zeros(43, dtype=bool)
+        for bit, (c0, c1) in cols.items():
+            if mask & bit:
+                sel[c0:c1] = True
+        with fb.Engine(n) as eng:
+            eng.upload(A)                          # device = A everywhere
+            eng.upload(big[:, :43], field_mask=mask)   # selected columns <- B (strided host rows)
+            got = eng.download(np.zeros((n, 43)))
+            assert np.array_equal(got[:, sel], B[:, sel]) and np.array_equal(got[:, ~sel], A[:, ~sel])
+            host = np.full((n, 48), -1.0)
+            eng.download(host[:, :43], field_mask=mask)
+            assert np.array_equal(host[:, :43][:, sel], got[:, sel])
+            assert np.all(host[:, :43][:, ~sel] == -1.0) and np.all(host[:, 43:] == -1.0)
+
+
 def test_impulse_conserved_large():
     """Size-independent property at N = 100k: the linear impulse 0.5 sum x × Gamma is conserved by an inviscid
     rVPM step to integration accuracy, and no NaN appears."""
