@@ -311,6 +311,23 @@ def run_ours(args):
                     t_step = (time.perf_counter() - t0) / 3
                     fmm[tag] = {"ms_per_evaluation": t_eval * 1e3, "ms_per_step_rk3_dynamic_sfs_pedrizzetti": t_step * 1e3,
                                 "rel_l2_err_U_vs_direct": eU, "rel_l2_err_J_vs_direct": eJ, "tree": ef.fmm_stats()}
+            # the same FMM step end to end through the reference-facing API with a pinned HOST matrix (upload + download per call)
+            pf_f = vpm.ParticleField(n, formulation=vpm.rVPM, kernel=vpm.gaussianerf, UJ=vpm.UJ_fmm,
+                                     SFS=vpm.SFS_Cd_twolevel_nobackscatter, integration=vpm.rungekutta3,
+                                     relaxation=vpm.pedrizzetti, device=local_rank, sync="always", pinned=True)
+            pf_f.particles[:n] = P0
+            pf_f.np = n
+            vpm.nextstep(pf_f, dt_sim, relax=True)
+            pf_f.h2d_bytes = pf_f.d2h_bytes = 0
+            t0 = time.perf_counter()
+            for _ in range(3):
+                vpm.nextstep(pf_f, dt_sim, relax=True)
+            pf_f.engine.synchronize()
+            fmm["nonzero_sigma_false"]["e2e_ms_per_step_host_buffers"] = (time.perf_counter() - t0) / 3 * 1e3
+            fmm["nonzero_sigma_false"]["e2e_h2d_bytes_per_step"] = pf_f.h2d_bytes // 3
+            fmm["nonzero_sigma_false"]["e2e_d2h_bytes_per_step"] = pf_f.d2h_bytes // 3
+            pf_f.engine.close()
+            del pf_f
             fmm["settings"] = "vpm.FMM(p=4, ncrit=50, theta=0.4); error on 2048 sampled particles vs the direct kernel"
             # and the FP32 variant of the direct kernel (vpm_floattype = Float32): one evaluation, same error measure
             with fb.Engine(n, float_bits=32, schemes=fb.default_schemes(uj="direct")) as e32:

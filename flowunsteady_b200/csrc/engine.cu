@@ -35,6 +35,7 @@ struct vpmb200_engine {
     size_t partial_doubles = 0;
     int sm_count = 148;
     int direct_sort = 1;        // Morton-order the direct path internally (vpmb200_set_option)
+    int fmm_table_copies = 8;   // UJ_fmm near field: 8 = bank-conflict-free replicated G table, 1 = single copy (vpmb200_set_option)
     int64_t shard_sorted_np = -1;  // >= 0: fmm.perm / sx,sy,sz hold the Morton order of the current local particles
                                    // (set by vpmb200_pack_uj_records, dropped by anything that moves or re-counts them)
     double* probe = nullptr;    // probe scratch: 3 (X) + 3 (U) + 9 (J) rows of probe_ld, + AoS staging
@@ -422,7 +423,7 @@ int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
         cudaError_t st = fmm_build(w, e->state, e->ld, e->np, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream, e->launches, err);
         if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
     }
-    const int block = std::min(256, std::max(32, (s.fmm_ncrit + 31) / 32 * 32));
+    const int block = e->fmm_table_copies;   // geometry selector of the near-field kernels (fmm_host.cuh: leaves_uj)
     CU_TRY(e, fmm_evaluate(w, s.fmm_p, s.kernel, block, e->gh_table, e->fmm_lvl, e->stream, e->launches, reuse));
     if (hint == 1 && !s.fmm_nonzero_sigma) {
         e->fmm_far_valid = true;
@@ -507,7 +508,7 @@ int32_t do_fmm_global(vpmb200_engine* e, double* G, int64_t ldg, int64_t ntot, i
     std::string err;
     if (fmm_reserve(e->fmm, ntot, s.fmm_ncrit, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
     FmmWorkspace& w = e->fmm;
-    const int block = 32;
+    const int block = e->fmm_table_copies;
     const unsigned nb = blocks_for(ntot, PK_BT);
     if (pass == 0) {
         cudaError_t st = fmm_build(w, G, ldg, ntot, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream,
@@ -1151,6 +1152,11 @@ int32_t vpmb200_set_option(vpmb200_handle e, const char* name, int64_t value) {
     if (!name) return fail(e, VPMB200_EINVAL, "option name is NULL");
     if (std::strcmp(name, "direct_sort") == 0) {
         e->direct_sort = value != 0;
+        return VPMB200_OK;
+    }
+    if (std::strcmp(name, "fmm_table_copies") == 0) {
+        if (value != 1 && value != 8) return fail(e, VPMB200_EINVAL, "fmm_table_copies must be 1 or 8");
+        e->fmm_table_copies = (int)value;
         return VPMB200_OK;
     }
     return fail(e, VPMB200_EINVAL, std::string("unknown option: ") + name);

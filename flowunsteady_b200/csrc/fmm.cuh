@@ -425,6 +425,11 @@ constexpr int LEAF_WARPS = 8;     // leaves per CTA (one warp each)
 constexpr int LEAF_BATCH = 48;    // source records per staged batch (3.84 KB); two batches per warp (double buffer)
 constexpr int LEAF_MIN_T = 4;     // fewest targets per pass -> at most 8 ways; LEAF_BATCH is a multiple of 2 * 8
 static_assert(LEAF_BATCH % (2 * (32 / LEAF_MIN_T)) == 0, "a full batch must hold whole groups of 2 * ways records");
+// Geometry of the UJ near-field kernel with the G table stored REP times (bank-conflict-free lookups, REP = 8): the 114 KB
+// table leaves room for ONE CTA per SM, so it carries all 16 warps the 128 registers allow and stages 32-record batches.
+template <int REP> struct LeafGeom { static constexpr int WARPS = LEAF_WARPS, BATCH = LEAF_BATCH; };
+template <> struct LeafGeom<8> { static constexpr int WARPS = 16, BATCH = 32; };
+static_assert(LeafGeom<8>::BATCH % (2 * (32 / LEAF_MIN_T)) == 0, "a full batch must hold whole groups of 2 * ways records");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -458,12 +463,13 @@ struct RunReader {
 
 // Issue the asynchronous copy (LDGSTS) of up to LEAF_BATCH source records of the run list [k, b1) into `slice`.
 // (k, off) is the cursor: `off` records of run k are already consumed.  Returns the number of records in flight.
+template <int BATCH = LEAF_BATCH>
 __device__ __forceinline__ int stage_batch_async(RunReader& rr, unsigned int& k, unsigned int b1, int& off,
                                                  const double* __restrict__ rec, double* __restrict__ slice, int lane) {
     int n = 0;
-    while (k < b1 && n < LEAF_BATCH) {
+    while (k < b1 && n < BATCH) {
         const int2 r = rr.get(k, lane);
-        const int take = min(r.y - off, LEAF_BATCH - n);
+        const int take = min(r.y - off, BATCH - n);
         const double2* g2 = reinterpret_cast<const double2*>(rec + (size_t)(r.x + off) * REC_REALS);
         double2* s2 = reinterpret_cast<double2*>(slice + (size_t)n * REC_REALS);
         for (int q = lane; q < take * (REC_REALS / 2); q += 32) cp_async16(s2 + q, g2 + q);
@@ -524,9 +530,9 @@ __device__ __forceinline__ double xor_sum(double v, int T) {
 
 // Two sources at a time for a whole warp (every lane must call: warp votes).  Inside an FMM near field nearly every pair
 // is in the regularised range, so the first vote selects a straight-line block with two independent table evaluations.
-template <int KERNEL>
+template <int KERNEL, int REP>
 __device__ __forceinline__ void uj_pair2_leaf(UJAcc& a, double tx, double ty, double tz, const double2* __restrict__ recA,
-                                              const double2* __restrict__ recB, const double2* __restrict__ tab) {
+                                              const double2* __restrict__ recB, const double2* __restrict__ tab, int q) {
     const SrcCore sa = load_core(recA), sb = load_core(recB);
     double dxa = tx - sa.x, dya = ty - sa.y, dza = tz - sa.z;
     double dxb = tx - sb.x, dyb = ty - sb.y, dzb = tz - sb.z;
@@ -545,8 +551,8 @@ __device__ __forceinline__ void uj_pair2_leaf(UJAcc& a, double tx, double ty, do
         if (__all_sync(0xffffffffu, !fa && !fb)) {
             const double2 qa4 = recA[4], qb4 = recB[4];
             double Aa, Ba, Ab, Bb;
-            ab_gauss_table(tab, r2a * qa4.y, qa3.y, qa4.x, Aa, Ba);
-            ab_gauss_table(tab, r2b * qb4.y, qb3.y, qb4.x, Ab, Bb);
+            ab_gauss_table_rep<REP>(tab, q, r2a * qa4.y, qa3.y, qa4.x, Aa, Ba);
+            ab_gauss_table_rep<REP>(tab, q, r2b * qb4.y, qb3.y, qb4.x, Ab, Bb);
             Aa = nonzero_f64(r2a) ? Aa : 0.0;  // r == 0 skip (src/FLOWUnsteady_processing_force.jl:895)
             Ab = nonzero_f64(r2b) ? Ab : 0.0;
             uj_accumulate(a, dxa, dya, dza, sa.gx, sa.gy, sa.gz, Aa, Ba);
@@ -558,8 +564,8 @@ __device__ __forceinline__ void uj_pair2_leaf(UJAcc& a, double tx, double ty, do
             uj_accumulate(a, dxa, dya, dza, sa.gx, sa.gy, sa.gz, Aa, Ba);
             uj_accumulate(a, dxb, dyb, dzb, sb.gx, sb.gy, sb.gz, Ab, Bb);
         } else {
-            uj_pair_general<KERNEL>(a, dxa, dya, dza, r2a, sa, recA, tab);
-            uj_pair_general<KERNEL>(a, dxb, dyb, dzb, r2b, sb, recB, tab);
+            uj_pair_general<KERNEL, REP>(a, dxa, dya, dza, r2a, sa, recA, tab, q);
+            uj_pair_general<KERNEL, REP>(a, dxb, dyb, dzb, r2b, sb, recB, tab, q);
         }
     } else {
         uj_pair_general<KERNEL>(a, dxa, dya, dza, r2a, sa, recA, tab);
@@ -570,30 +576,32 @@ __device__ __forceinline__ void uj_pair2_leaf(UJAcc& a, double tx, double ty, do
 // L2P + near-field P2P: one warp per leaf; warps are persistent and draw leaves from a global counter (leaf costs vary by
 // two orders of magnitude, so a static 8-leaves-per-CTA split leaves a quarter of the warp slots idle).  Outputs in
 // Morton order: sU[k * lds + i], sJ[k * lds + i].
-template <int KERNEL, int P>
-__global__ void __launch_bounds__(32 * LEAF_WARPS)
+template <int KERNEL, int P, int REP>
+__global__ void __launch_bounds__(32 * LeafGeom<REP>::WARPS)
 fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ leaves, int nleaves, unsigned int* next_leaf,
                    const int2* __restrict__ runs, const unsigned int* __restrict__ p2p_off, const double* __restrict__ rec,
                    const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                    const double* __restrict__ L, const double* __restrict__ gh_table, double* __restrict__ sU,
                    double* __restrict__ sJ, int64_t lds) {
     using Ops = FmmOps<P>;
-    // shared: [G/H table (gaussianerf)] then per warp { [3 * NL padded even] local expansion, 2 x [LEAF_BATCH * 10] records }
+    constexpr int BATCH = LeafGeom<REP>::BATCH;
+    // shared: [G table x REP (gaussianerf)] then per warp { [3 * NL padded even] local expansion, 2 x [BATCH * 10] records }
     extern __shared__ __align__(16) double smem[];
     constexpr int LPAD = (3 * Ops::NL + 1) & ~1;
-    constexpr int TABD = KERNEL == K_GAUSSIANERF ? VPM_GG_DOUBLES : 0;
-    constexpr int WARPD = LPAD + 2 * LEAF_BATCH * REC_REALS;
+    constexpr int TABD = KERNEL == K_GAUSSIANERF ? VPM_GG_DOUBLES * REP : 0;
+    constexpr int WARPD = LPAD + 2 * BATCH * REC_REALS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (KERNEL == K_GAUSSIANERF) {
         const double2* g2 = reinterpret_cast<const double2*>(gh_table);
         double2* t2 = reinterpret_cast<double2*>(smem);
-        for (int k = threadIdx.x; k < TABD / 2; k += blockDim.x) t2[k] = g2[k];
+        for (int k = threadIdx.x; k < TABD / 2; k += blockDim.x) t2[k] = g2[k / REP];
     }
     __syncthreads();
     const double2* tab = reinterpret_cast<const double2*>(smem);
+    const int tq = lane & (REP - 1);   // this lane's copy of the table
     double* sL = smem + TABD + (size_t)warp * WARPD;
     double* buf0 = sL + LPAD;
-    double* buf1 = buf0 + LEAF_BATCH * REC_REALS;
+    double* buf1 = buf0 + BATCH * REC_REALS;
   for (;;) {   // (body keeps its indentation: one leaf per trip)
     int leaf = 0;
     if (lane == 0) leaf = (int)atomicAdd(next_leaf, 1u);
@@ -634,18 +642,18 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
         unsigned int k = b0;
         int off = 0, pb = 0;
         __syncwarp();
-        int n_next = stage_batch_async(rr, k, b1, off, rec, buf0, lane);
+        int n_next = stage_batch_async<BATCH>(rr, k, b1, off, rec, buf0, lane);
         while (true) {
             cp_async_wait_all();
             __syncwarp();
             int ns = n_next;
             if (ns == 0) break;
-            n_next = stage_batch_async(rr, k, b1, off, rec, pb ? buf0 : buf1, lane);
+            n_next = stage_batch_async<BATCH>(rr, k, b1, off, rec, pb ? buf0 : buf1, lane);
             ns = pad_batch<false>(pb ? buf1 : buf0, ns, 2 * S, lane);
             const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0) + way * (REC_REALS / 2);
             for (int s = 0; s < ns; s += 2 * S) {
                 const double2* ra = r2p + s * (REC_REALS / 2);
-                uj_pair2_leaf<KERNEL>(a, px, py, pz, ra, ra + S * (REC_REALS / 2), tab);
+                uj_pair2_leaf<KERNEL, REP>(a, px, py, pz, ra, ra + S * (REC_REALS / 2), tab, tq);
             }
             pb ^= 1;
         }

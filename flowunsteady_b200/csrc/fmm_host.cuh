@@ -41,9 +41,9 @@ struct FmmWorkspace {
 // Grid of the persistent near-field kernels: as many CTAs as are resident at once (occupancy of `kfn` x SMs), fewer when
 // there are not enough leaves; zeroes the leaf counter (counters->next is idle once the traversal is done).
 template <typename K>
-inline cudaError_t fmm_leaf_grid(FmmWorkspace& w, K kfn, size_t smem, int nl, cudaStream_t st, int& grid) {
+inline cudaError_t fmm_leaf_grid(FmmWorkspace& w, K kfn, int threads, size_t smem, int ctas_needed, cudaStream_t st, int& grid) {
     int per_sm = 0;
-    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 32 * LEAF_WARPS, smem);
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem);
     if (eo != cudaSuccess) return eo;
     if (w.sms == 0) {
         int dev = 0;
@@ -51,7 +51,7 @@ inline cudaError_t fmm_leaf_grid(FmmWorkspace& w, K kfn, size_t smem, int nl, cu
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&w.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
-    grid = std::min((nl + LEAF_WARPS - 1) / LEAF_WARPS, std::max(per_sm, 1) * w.sms);
+    grid = std::min(ctas_needed, std::max(per_sm, 1) * w.sms);
     return cudaMemsetAsync(&w.counters->next, 0, sizeof(unsigned int), st);
 }
 
@@ -213,22 +213,36 @@ struct FmmPasses {
         return cudaGetLastError();
     }
 
-    template <int KERNEL>
-    static cudaError_t leaves_uj(FmmWorkspace& w, int block, const double* gh_table, cudaStream_t st, uint64_t& launches) {
-        (void)block;
-        const size_t smem = sizeof(double) * ((KERNEL == K_GAUSSIANERF ? VPM_GG_DOUBLES : 0) +
-                                              LEAF_WARPS * (((3 * Ops::NL + 1) & ~1) + (size_t)2 * LEAF_BATCH * REC_REALS));
-        auto kfn = fmm_leaf_uj_kernel<KERNEL, P>;
+    template <int KERNEL, int REP>
+    static constexpr size_t leaves_uj_smem() {
+        return sizeof(double) * ((KERNEL == K_GAUSSIANERF ? (size_t)VPM_GG_DOUBLES * REP : 0) +
+                                 LeafGeom<REP>::WARPS * (((3 * Ops::NL + 1) & ~1) + (size_t)2 * LeafGeom<REP>::BATCH * REC_REALS));
+    }
+
+    template <int KERNEL, int REP>
+    static cudaError_t leaves_uj_launch(FmmWorkspace& w, const double* gh_table, cudaStream_t st, uint64_t& launches) {
+        constexpr int WARPS = LeafGeom<REP>::WARPS;
+        const size_t smem = leaves_uj_smem<KERNEL, REP>();
+        auto kfn = fmm_leaf_uj_kernel<KERNEL, P, REP>;
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         const int nl = w.leaf_hi - w.leaf_lo;
         if (nl <= 0) return cudaSuccess;
         int grid = 0;
-        if ((e = fmm_leaf_grid(w, kfn, smem, nl, st, grid)) != cudaSuccess) return e;
-        kfn<<<grid, 32 * LEAF_WARPS, smem, st>>>(
+        if ((e = fmm_leaf_grid(w, kfn, 32 * WARPS, smem, (nl + WARPS - 1) / WARPS, st, grid)) != cudaSuccess) return e;
+        kfn<<<grid, 32 * WARPS, smem, st>>>(
             w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
         ++launches;
         return cudaGetLastError();
+    }
+
+    // `copies` = 8 asks for the bank-conflict-free replicated G table (gaussianerf only, and only for p <= 4: one 512-thread
+    // CTA caps the kernel at 128 registers, which the L2P of p >= 5 overflows); anything else runs the single-copy kernel.
+    template <int KERNEL>
+    static cudaError_t leaves_uj(FmmWorkspace& w, int copies, const double* gh_table, cudaStream_t st, uint64_t& launches) {
+        if (KERNEL == K_GAUSSIANERF && copies == 8 && P <= 4 && leaves_uj_smem<K_GAUSSIANERF, 8>() <= 227 * 1024)
+            return leaves_uj_launch<K_GAUSSIANERF, 8>(w, gh_table, st, launches);
+        return leaves_uj_launch<KERNEL, 1>(w, gh_table, st, launches);
     }
 
     static cudaError_t leaves_uj(FmmWorkspace& w, int kernel, int block, const double* gh_table, cudaStream_t st,
@@ -502,7 +516,7 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
     cudaError_t eg = cudaSuccess;
 #define FMM_ESTR_CASE(K)                                                                                                   \
     cudaFuncSetAttribute(fmm_leaf_estr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
-    if ((eg = fmm_leaf_grid(w, fmm_leaf_estr_kernel<K>, smem, nl, st, grid)) != cudaSuccess) return eg;                    \
+    if ((eg = fmm_leaf_grid(w, fmm_leaf_estr_kernel<K>, 32 * LEAF_WARPS, smem, (nl + LEAF_WARPS - 1) / LEAF_WARPS, st, grid)) != cudaSuccess) return eg; \
     fmm_leaf_estr_kernel<K><<<grid, 32 * LEAF_WARPS, smem, st>>>(                                                          \
         w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
     switch (kernel) {

@@ -79,16 +79,20 @@ __device__ __forceinline__ void ab_singular(double r2, double& A, double& B) {
 // Gaussian-erf near field from the table: t < T_FAR.  H = 2 dG/dt, so one degree-9 polynomial per interval gives both:
 // value and derivative share the Horner recurrence (17 FMAs) and a lookup reads 80 B (five LDS.128) instead of two
 // polynomials' 128 B — the pair loops are co-limited by shared-memory wavefronts and the FP64 pipe (tools/gen_tables.py).
-__device__ __forceinline__ void ab_gauss_table(const double2* __restrict__ tab, double t, double sinv3, double sinv5,
-                                               double& A, double& B) {
+// REP > 1: the table is stored REP times, entry (j, i) of copy q at tab[(j * NINT + i) * REP + q]; with REP = 8 and
+// q = lane & 7 every lane of a quarter-warp reads its own 16-byte bank group, so a lookup is bank-conflict free whatever
+// the lanes' interval indices are (4 wavefronts per LDS.128 instead of the measured 6.2).
+template <int REP>
+__device__ __forceinline__ void ab_gauss_table_rep(const double2* __restrict__ tab, int q, double t, double sinv3, double sinv5,
+                                                   double& A, double& B) {
     static_assert(VPM_GG_DEG % 2 == 1, "coefficients are stored in pairs");
     double m = fma(t, VPM_GG_INVW, MAGIC_RINT);
     int i = __double2loint(m);
     double u = fma(m - MAGIC_RINT, -VPM_GG_W, t);
-    const double2* tp = tab + i;
+    const double2* tp = tab + (REP == 1 ? i : i * REP + q);
     double2 c[(VPM_GG_DEG + 1) / 2];
 #pragma unroll
-    for (int j = 0; j < (VPM_GG_DEG + 1) / 2; ++j) c[j] = tp[j * VPM_GG_NINT];   // {c_2j, c_2j+1}
+    for (int j = 0; j < (VPM_GG_DEG + 1) / 2; ++j) c[j] = tp[j * VPM_GG_NINT * REP];   // {c_2j, c_2j+1}
     double d = c[(VPM_GG_DEG - 1) / 2].y;   // derivative runs one step behind the value
     double p = fma(d, u, c[(VPM_GG_DEG - 1) / 2].x);
 #pragma unroll
@@ -98,6 +102,10 @@ __device__ __forceinline__ void ab_gauss_table(const double2* __restrict__ tab, 
     }
     A = p * sinv3;
     B = (d + d) * sinv5;
+}
+__device__ __forceinline__ void ab_gauss_table(const double2* __restrict__ tab, double t, double sinv3, double sinv5,
+                                               double& A, double& B) {
+    ab_gauss_table_rep<1>(tab, 0, t, sinv3, sinv5, A, B);
 }
 
 // Winckelmans: G = (t + 2.5)/(t+1)^2.5, H = -(3 t + 10.5)/(t+1)^3.5   (SURVEY.md A.3 in the variable t)
@@ -178,9 +186,9 @@ __device__ __forceinline__ void uj_pair_far(UJAcc& a, double tx, double ty, doub
 }
 
 // General interaction of the regularised kernels: per-lane choice between table/closed form and far field.
-template <int KERNEL>
+template <int KERNEL, int REP = 1>
 __device__ __forceinline__ void uj_pair_general(UJAcc& a, double dx, double dy, double dz, double r2, const SrcCore& s,
-                                                const double2* __restrict__ rec, const double2* __restrict__ tab) {
+                                                const double2* __restrict__ rec, const double2* __restrict__ tab, int q = 0) {
     const double2 q3 = rec[3];  // T_FAR sigma^2, 1/sigma^3
     const double2 q4 = rec[4];  // 1/sigma^5, 1/sigma^2
     double A, B;
@@ -188,7 +196,7 @@ __device__ __forceinline__ void uj_pair_general(UJAcc& a, double dx, double dy, 
         if (__double2hiint(r2) > __double2hiint(q3.x)) {
             ab_singular(r2, A, B);
         } else {
-            ab_gauss_table(tab, r2 * q4.y, q3.y, q4.x, A, B);
+            ab_gauss_table_rep<REP>(tab, q, r2 * q4.y, q3.y, q4.x, A, B);
             A = nonzero_f64(r2) ? A : 0.0;  // r == 0 skip (src/FLOWUnsteady_processing_force.jl:895)
         }
     } else if (KERNEL == K_WINCKELMANS) {

@@ -206,7 +206,10 @@ int32_t vpmb200_device_field(vpmb200_handle h, int32_t field, double** ptr, int6
 /* The CUDA stream (cudaStream_t) every call on this handle is enqueued on. */
 int32_t vpmb200_stream(vpmb200_handle h, void** stream);
 /* Engine options.  "direct_sort" (default 1): visit targets and source tiles of the DIRECT path in Morton order
- * internally (results are returned in particle order); 0 keeps the caller's particle order. */
+ * internally (results are returned in particle order); 0 keeps the caller's particle order.
+ * "fmm_table_copies" (1 or 8, default 8): shared-memory layout of the Gaussian-erf table in the UJ_fmm near-field kernel;
+ * 8 = one copy per 16-byte bank group (conflict-free lookups, one 16-warp CTA per SM), 1 = single copy (two 8-warp CTAs).
+ * Results do not depend on it. */
 int32_t vpmb200_set_option(vpmb200_handle h, const char* name, int64_t value);
 /* Tree statistics of the last UJ_fmm evaluation: stats[0..4] = cells, leaves, levels, M2L pairs, P2P (leaf) pairs. */
 int32_t vpmb200_fmm_stats(vpmb200_handle h, int64_t* stats);

@@ -17,9 +17,11 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
-def _eval(P, sfs=False, **kw):
+def _eval(P, sfs=False, options=None, **kw):
     import flowunsteady_b200 as fb
     with fb.Engine(P.shape[0], schemes=fb.default_schemes(**kw)) as eng:
+        for name, value in (options or {}).items():
+            eng.set_option(name, value)
         eng.upload(P)
         eng.uj(True, True, sfs)
         out = eng.download(np.zeros_like(P))
@@ -48,9 +50,10 @@ def test_theta_to_zero_is_the_direct_sum(kernel, n):
         assert relmax(F[:, 39:42], D[:, 39:42]) < 1e-11
 
 
+@pytest.mark.parametrize("copies", [1, 8])
 @pytest.mark.parametrize("kernel", ["gaussianerf", "winckelmans"])
 @pytest.mark.parametrize("ncrit", [5, 18, 33, 128])
-def test_near_field_lane_mapping_every_leaf_size(kernel, ncrit):
+def test_near_field_lane_mapping_every_leaf_size(kernel, ncrit, copies):
     """The near-field kernel splits a leaf's targets into passes of T = 4..32 targets x 32/T ways and pads the last source
     batch to whole groups of 2 x ways records (fmm.cuh: leaf_pass, pad_batch).  ncrit = 5 / 18 / 33 / 128 on a field with a
     dense cluster produces leaves of every count from 1 to ncrit, i.e. every (T, ways) pair, multi-pass leaves and leaves
@@ -58,7 +61,7 @@ def test_near_field_lane_mapping_every_leaf_size(kernel, ncrit):
     P = _field(1500, seed=5)
     P[:400, 0:3] = P[0, 0:3] + 0.02 * (P[:400, 0:3] - P[0, 0:3])     # cluster: deep, unevenly filled leaves
     D, _ = _eval(P, kernel=kernel, uj="direct", sfs=True)
-    F, st = _eval(P, kernel=kernel, uj="fmm", fmm_theta=1e-6, fmm_ncrit=ncrit, sfs=True)
+    F, st = _eval(P, kernel=kernel, uj="fmm", fmm_theta=1e-6, fmm_ncrit=ncrit, sfs=True, options={"fmm_table_copies": copies})
     assert st["m2l_pairs"] == 0
     assert relmax(F[:, 9:12], D[:, 9:12]) < 1e-12
     assert relmax(F[:, 15:24], D[:, 15:24]) < 1e-12
@@ -184,6 +187,21 @@ def test_fmm_parameter_validation():
             eng.set_schemes(fb.default_schemes(uj="fmm", **bad))
             with pytest.raises(fb.EngineError):
                 eng.uj()
+
+
+def test_table_layouts_agree_bit_for_bit():
+    """The replicated (bank-conflict-free) and the single-copy G table hold the same coefficients and the kernels run the
+    same arithmetic in the same order: identical bits at the reference defaults, every expansion order."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    x, g, s = fields.vortex_rings(30_000)
+    P = fb.new_particles(x, g, s)
+    for p in (3, 4, 5):
+        a, _ = _eval(P, uj="fmm", fmm_p=p, sfs=True, options={"fmm_table_copies": 1})
+        b, _ = _eval(P, uj="fmm", fmm_p=p, sfs=True, options={"fmm_table_copies": 8})
+        assert np.array_equal(a, b)
+    with fb.Engine(10) as eng, pytest.raises(fb.EngineError):
+        eng.set_option("fmm_table_copies", 4)
 
 
 def test_fmm_is_deterministic():
