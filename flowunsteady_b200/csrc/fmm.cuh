@@ -624,6 +624,7 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
         const double px = sx[i], py = sy[i], pz = sz[i];
         UJAcc a;
         acc_zero(a);
+        double trace0 = 0.0;   // trace of the L2P part of J (the pair loop leaves j8 alone, UJAcc)
         if (way == 0) {   // far field: psi_n = local expansion n; U = curl psi, J = grad U
             double g[3][3], h[3][6];
 #pragma unroll
@@ -635,6 +636,7 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
             a.j0 = h[2][1] - h[1][2]; a.j1 = h[0][2] - h[2][0]; a.j2 = h[1][0] - h[0][1];   // l = x: (xx, xy, xz) = 0, 1, 2
             a.j3 = h[2][3] - h[1][4]; a.j4 = h[0][4] - h[2][1]; a.j5 = h[1][1] - h[0][3];   // l = y: (yx, yy, yz) = 1, 3, 4
             a.j6 = h[2][4] - h[1][5]; a.j7 = h[0][5] - h[2][2]; a.j8 = h[1][2] - h[0][4];   // l = z: (zx, zy, zz) = 2, 4, 5
+            trace0 = a.j0 + a.j4 + a.j8;
         }
         // near field: double-buffered batches of source records; way w takes records w, w + S, ... two at a time
         RunReader rr;
@@ -661,10 +663,11 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
             a.u0 = xor_sum(a.u0, T); a.u1 = xor_sum(a.u1, T); a.u2 = xor_sum(a.u2, T);
             a.j0 = xor_sum(a.j0, T); a.j1 = xor_sum(a.j1, T); a.j2 = xor_sum(a.j2, T);
             a.j3 = xor_sum(a.j3, T); a.j4 = xor_sum(a.j4, T); a.j5 = xor_sum(a.j5, T);
-            a.j6 = xor_sum(a.j6, T); a.j7 = xor_sum(a.j7, T); a.j8 = xor_sum(a.j8, T);
+            a.j6 = xor_sum(a.j6, T); a.j7 = xor_sum(a.j7, T);
             a.w0 = xor_sum(a.w0, T); a.w1 = xor_sum(a.w1, T); a.w2 = xor_sum(a.w2, T);
         }
         if (live && way == 0) {
+            acc_close_trace(a, trace0);
             a.j1 -= a.w2; a.j2 += a.w1;
             a.j3 += a.w2; a.j5 -= a.w0;
             a.j6 -= a.w1; a.j7 += a.w0;

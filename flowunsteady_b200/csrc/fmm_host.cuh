@@ -80,8 +80,11 @@ inline cudaError_t fmm_grow(T*& ptr, size_t& have, size_t need, std::string& err
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
     have = 0;
-    FMM_TRY(cudaMalloc(&ptr, sizeof(T) * need));
-    have = need;
+    // 25 % headroom: the cell count drifts by a fraction of a percent from one evaluation to the next, and an exact fit
+    // would pay a cudaFree + cudaMalloc (a device synchronisation each) on every upward drift
+    const size_t cap = need + need / 4;
+    FMM_TRY(cudaMalloc(&ptr, sizeof(T) * cap));
+    have = cap;
     return cudaSuccess;
 }
 
@@ -91,8 +94,8 @@ inline cudaError_t fmm_cub(FmmWorkspace& w, size_t bytes, std::string& err) {
     if (w.cub_tmp) cudaFree(w.cub_tmp);
     w.cub_tmp = nullptr;
     w.cub_bytes = 0;
-    FMM_TRY(cudaMalloc(&w.cub_tmp, bytes + 256));
-    w.cub_bytes = bytes + 256;
+    FMM_TRY(cudaMalloc(&w.cub_tmp, bytes + bytes / 4 + 256));   // headroom: list sizes drift between evaluations
+    w.cub_bytes = bytes + bytes / 4 + 256;
     return cudaSuccess;
 }
 

@@ -28,9 +28,12 @@ namespace vpm {
 
 constexpr double MAGIC_RINT = 6755399441055744.0;  // 1.5 * 2^52: fma(t, 1/W, MAGIC) puts rint(t/W) in the low word
 
+// J of a pair is B (c x dx^T) + (antisymmetric delta term) with c = dx x G' perpendicular to dx, so its trace vanishes
+// identically (div u = 0): the pair loops do not accumulate j8; it is recovered once at the end as -(j0 + j4)
+// (acc_close_trace).  That is one FP64 instruction less per interaction.
 struct UJAcc {
     double u0, u1, u2;
-    double j0, j1, j2, j3, j4, j5, j6, j7, j8;  // J[i + 3 j]
+    double j0, j1, j2, j3, j4, j5, j6, j7, j8;  // J[i + 3 j]; j8 is NOT touched by uj_accumulate
     double w0, w1, w2;                           // sum A * G'  (delta term, expanded at the end)
 };
 
@@ -42,7 +45,7 @@ __device__ __forceinline__ void acc_zero(UJAcc& a) {
 __device__ __forceinline__ void acc_add(UJAcc& t, const UJAcc& a) {
     t.u0 += a.u0; t.u1 += a.u1; t.u2 += a.u2;
     t.j0 += a.j0; t.j1 += a.j1; t.j2 += a.j2; t.j3 += a.j3; t.j4 += a.j4;
-    t.j5 += a.j5; t.j6 += a.j6; t.j7 += a.j7; t.j8 += a.j8;
+    t.j5 += a.j5; t.j6 += a.j6; t.j7 += a.j7;
     t.w0 += a.w0; t.w1 += a.w1; t.w2 += a.w2;
 }
 
@@ -59,11 +62,28 @@ __device__ __forceinline__ void uj_accumulate(UJAcc& a, double dx, double dy, do
     double b0 = B * c0, b1 = B * c1, b2 = B * c2;
     a.j0 = fma(b0, dx, a.j0); a.j1 = fma(b1, dx, a.j1); a.j2 = fma(b2, dx, a.j2);
     a.j3 = fma(b0, dy, a.j3); a.j4 = fma(b1, dy, a.j4); a.j5 = fma(b2, dy, a.j5);
-    a.j6 = fma(b0, dz, a.j6); a.j7 = fma(b1, dz, a.j7); a.j8 = fma(b2, dz, a.j8);
+    a.j6 = fma(b0, dz, a.j6); a.j7 = fma(b1, dz, a.j7);   // j8: see UJAcc
     a.w0 = fma(A, gx, a.w0);
     a.w1 = fma(A, gy, a.w1);
     a.w2 = fma(A, gz, a.w2);
 }
+
+// Far-field flavour used by K1's all-far tiles: B3 = B / (-3) = 1/r^5 (one multiply less than B); the tile's J partial
+// sums are scaled by -3 when they are added to the running totals (acc_add_far), which costs nothing extra.
+__device__ __forceinline__ void uj_accumulate_far(UJAcc& a, double dx, double dy, double dz, double gx, double gy,
+                                                  double gz, double A, double B3) {
+    uj_accumulate(a, dx, dy, dz, gx, gy, gz, A, B3);
+}
+__device__ __forceinline__ void acc_add_far(UJAcc& t, const UJAcc& a) {
+    t.u0 += a.u0; t.u1 += a.u1; t.u2 += a.u2;
+    t.j0 = fma(-3.0, a.j0, t.j0); t.j1 = fma(-3.0, a.j1, t.j1); t.j2 = fma(-3.0, a.j2, t.j2);
+    t.j3 = fma(-3.0, a.j3, t.j3); t.j4 = fma(-3.0, a.j4, t.j4); t.j5 = fma(-3.0, a.j5, t.j5);
+    t.j6 = fma(-3.0, a.j6, t.j6); t.j7 = fma(-3.0, a.j7, t.j7);
+    t.w0 += a.w0; t.w1 += a.w1; t.w2 += a.w2;
+}
+// j8 <- trace0 - (j0 + j4): closes the trace after the pair loops (trace0 = trace of whatever J was put into the
+// accumulators before the loops: 0 for the direct kernels, the L2P part for the FMM leaf kernel).
+__device__ __forceinline__ void acc_close_trace(UJAcc& a, double trace0 = 0.0) { a.j8 = trace0 - (a.j0 + a.j4); }
 
 // x != 0 for a non-negative double, on the integer pipe (keeps DSETP off the FP64 pipe)
 __device__ __forceinline__ bool nonzero_f64(double x) { return (__double2hiint(x) | __double2loint(x)) != 0; }
@@ -180,9 +200,10 @@ __device__ __forceinline__ SrcCore load_core(const double2* __restrict__ rec) {
 __device__ __forceinline__ void uj_pair_far(UJAcc& a, double tx, double ty, double tz, const SrcCore& s) {
     double dx = tx - s.x, dy = ty - s.y, dz = tz - s.z;
     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    double A, B;
-    ab_singular(r2, A, B);
-    uj_accumulate(a, dx, dy, dz, s.gx, s.gy, s.gz, A, B);
+    double ri = rsqrt_f64(r2);
+    double ri2 = ri * ri;
+    double A = ri2 * ri;
+    uj_accumulate_far(a, dx, dy, dz, s.gx, s.gy, s.gz, A, ri2 * A);   // B / (-3); the caller adds with acc_add_far
 }
 
 // General interaction of the regularised kernels: per-lane choice between table/closed form and far field.
@@ -373,15 +394,17 @@ uj_direct_f64_kernel(const double* __restrict__ srec, int ntiles, const double* 
             // every (target, source) pair of this tile is in the singular regime: no vote, no table, full ILP
 #pragma unroll 4
             for (int j = 0; j < TILE_SRC; ++j) uj_pair_far(a, px, py, pz, load_core(rec + j * (REC_REALS / 2)));
+            acc_add_far(tot, a);
         } else {
 #pragma unroll 1
             for (int j = 0; j < TILE_SRC; j += 2) uj_pair2<KERNEL>(a, px, py, pz, rec + j * (REC_REALS / 2), tab);
+            acc_add(tot, a);
         }
-        acc_add(tot, a);
         __syncthreads();
     }
 
     if (live) {
+        acc_close_trace(tot);
         // expand the delta term: J[2,1] -= w3, J[3,1] += w2, J[1,2] += w3, J[3,2] -= w1, J[1,3] -= w2, J[2,3] += w1
         tot.j1 -= tot.w2; tot.j2 += tot.w1;
         tot.j3 += tot.w2; tot.j5 -= tot.w0;
