@@ -48,6 +48,8 @@ SYMBOLS = {
     "vpmb200_upload": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32]),
     "vpmb200_download": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32]),
     "vpmb200_get_np": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "vpmb200_host_register": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "vpmb200_host_unregister": (C.c_int32, [C.c_void_p]),
     "vpmb200_add_particles": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64]),
     "vpmb200_remove_particle": (C.c_int32, [_H, C.c_int64]),
     "vpmb200_remove_where": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),

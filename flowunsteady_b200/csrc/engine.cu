@@ -893,6 +893,35 @@ int32_t vpmb200_download(vpmb200_handle e, double* particles, int64_t ld, int64_
     return VPMB200_OK;
 }
 
+int32_t vpmb200_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return fail(nullptr, VPMB200_EINVAL, "host_register: NULL pointer or zero size");
+    cudaError_t st = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (st == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return VPMB200_OK;
+    }
+    if (st == cudaErrorNoDevice || st == cudaErrorInsufficientDriver) {
+        cudaGetLastError();
+        return fail(nullptr, VPMB200_ENODEVICE, "host_register: no CUDA device");
+    }
+    if (st != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, VPMB200_ECUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(st));
+    }
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_host_unregister(void* ptr) {
+    if (!ptr) return fail(nullptr, VPMB200_EINVAL, "host_unregister: NULL pointer");
+    cudaError_t st = cudaHostUnregister(ptr);
+    if (st != cudaSuccess && st != cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return fail(nullptr, VPMB200_ECUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(st));
+    }
+    cudaGetLastError();
+    return VPMB200_OK;
+}
+
 int32_t vpmb200_add_particles(vpmb200_handle e, const double* cols, int64_t ld, int64_t n) {
     CHECK_HANDLE(e);
     if (n < 0) return fail(e, VPMB200_EINVAL, "n < 0");

@@ -318,13 +318,14 @@ class ParticleField:
             raise ValueError("sync must be 'always' or 'lazy'")
         self.maxparticles = int(maxparticles)
         self.R = R
-        if pinned:
-            import torch
-            self._pin = torch.empty((self.maxparticles, NFIELDS), dtype=torch.float64, pin_memory=True)
-            self._pin.zero_()
-            self.particles = self._pin.numpy()
-        else:
-            self.particles = np.zeros((self.maxparticles, NFIELDS))
+        self.particles = np.zeros((self.maxparticles, NFIELDS))
+        self._registered = False
+        if pinned:   # page-lock the matrix in place (what the Julia stub does with pfield.particles): full-rate DMA, no staging
+            from . import _lib as _L
+            rc = _L.lib().vpmb200_host_register(self.particles.ctypes.data, self.particles.nbytes)
+            if rc != 0:
+                raise EngineError(rc, _L.lib().vpmb200_last_error(None).decode())
+            self._registered = True
         self.np = 0
         self.nt = 0
         self.t = 0.0
@@ -497,6 +498,16 @@ class ParticleField:
     @property
     def engine(self) -> Engine:
         return self._engine
+
+    def __del__(self):
+        # release the page lock before numpy frees the matrix (the Julia stub's finalizer does the same)
+        try:
+            if getattr(self, "_registered", False):
+                from . import _lib as _L
+                _L.lib().vpmb200_host_unregister(self.particles.ctypes.data)
+                self._registered = False
+        except Exception:
+            pass
 
 
 def _rows(mask: int) -> int:

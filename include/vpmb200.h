@@ -146,6 +146,13 @@ int32_t vpmb200_upload(vpmb200_handle h, const double* particles, int64_t ld, in
 /* Copy the groups in field_mask of particles 0..np-1 back into `particles`. */
 int32_t vpmb200_download(vpmb200_handle h, double* particles, int64_t ld, int64_t np, uint32_t field_mask);
 int32_t vpmb200_get_np(vpmb200_handle h, int64_t* np);
+/* Page-lock (cudaHostRegister) / release the caller's particle matrix so that vpmb200_upload / vpmb200_download move it by
+ * DMA at full PCIe rate straight from / into it; a pageable matrix (what `Matrix{Float64}(undef, 43, max)` is) still works
+ * but is staged by the driver at a few GB/s.  Call once after allocating `pfield.particles`
+ * (/root/reference/src/FLOWUnsteady_simulation.jl:239-253) and unregister before it is freed (the Julia stub does both in
+ * `_handle` and its finalizer).  No handle: errors are read with vpmb200_last_error(NULL). */
+int32_t vpmb200_host_register(void* ptr, uint64_t bytes);
+int32_t vpmb200_host_unregister(void* ptr);
 
 /* vpm.add_particle: append n columns.  vpm.remove_particle(pfield, i): 0-based i; the last particle is swapped
  * into slot i (the reference's behaviour). */

@@ -55,7 +55,13 @@ function _handle(pfield)
                    pfield.maxparticles, NFIELDS, bits, 0, h)
         rc == 0 || error("vpmb200_create failed ($rc): " *
                          unsafe_string(ccall((:vpmb200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
-        finalizer(_ -> ccall((:vpmb200_destroy, LIB), Int32, (Ptr{Cvoid},), h[]), pfield)
+        # page-lock the particle matrix once so uploads / downloads are full-rate DMA straight from / into it
+        P = pfield.particles
+        ccall((:vpmb200_host_register, LIB), Int32, (Ptr{Cvoid}, UInt64), pointer(P), sizeof(P))
+        finalizer(pfield) do pf
+            ccall((:vpmb200_host_unregister, LIB), Int32, (Ptr{Cvoid},), pointer(pf.particles))
+            ccall((:vpmb200_destroy, LIB), Int32, (Ptr{Cvoid},), h[])
+        end
         h[]
     end
 end

@@ -138,3 +138,33 @@ def test_lazy_sync_keeps_field_on_device():
             pf.pull()
         outs.append(pf.particles[:800].copy())
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_page_locked_host_matrix_gives_the_same_field():
+    """pinned=True page-locks `pfield.particles` in place through the ABI (vpmb200_host_register — what the Julia stub
+    does with the reference's matrix): same bits as the pageable matrix, registering twice is harmless, and the lock is
+    released with the field."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import _lib, vpm
+    from tests.util import mixed_field
+    x, g, s, static = mixed_field(1500, seed=6)
+    P = fb.new_particles(x, 50 * g + 1e-12, s)
+    outs = []
+    for pinned in (False, True):
+        pf = vpm.ParticleField(2000, UJ=vpm.UJ_fmm, SFS=vpm.SFS_Cd_twolevel_nobackscatter, pinned=pinned)
+        pf.particles[:1500] = P
+        pf.np = 1500
+        for _ in range(2):
+            vpm.nextstep(pf, 1e-3, relax=True)
+        if pinned:
+            L = _lib.lib()
+            assert L.vpmb200_host_register(pf.particles.ctypes.data, pf.particles.nbytes) == 0     # already registered: OK
+        outs.append(pf.particles[:1500].copy())
+        del pf
+    assert np.all(np.isfinite(outs[0])) and np.array_equal(outs[0], outs[1])
+    L = _lib.lib()
+    buf = np.zeros(4096)
+    assert L.vpmb200_host_register(buf.ctypes.data, buf.nbytes) == 0
+    assert L.vpmb200_host_unregister(buf.ctypes.data) == 0
+    assert L.vpmb200_host_unregister(buf.ctypes.data) == 0                                           # not registered: no-op
+    assert L.vpmb200_host_register(None, 16) != 0
