@@ -115,6 +115,14 @@ class CoreSpreading(ViscousScheme):
     tol: float = 1e-3
 
 
+@dataclass
+class ParticleStrengthExchange(ViscousScheme):
+    """vpm.ParticleStrengthExchange(nu) — named in FLOWVPM's API (SURVEY.md Appendix B) but used by none of FLOWUnsteady's
+    examples (they run Inviscid(), or CoreSpreading in commented lines).  The engine has no PSE kernel: a field constructed
+    with it raises NotImplementedError instead of silently running inviscid."""
+    nu: float = 0.0
+
+
 def isinviscid(v) -> bool:
     return isinstance(v, Inviscid)
 
@@ -312,6 +320,8 @@ class ParticleField:
         if R not in (np.float64, np.float32, float):
             raise TypeError("R must be Float64 or Float32 (vpm_floattype, simulation.jl:137)")
         viscous = Inviscid() if viscous is None else viscous
+        if isinstance(viscous, ParticleStrengthExchange):
+            raise NotImplementedError("ParticleStrengthExchange is not available in the GPU engine (use Inviscid or CoreSpreading)")
         if kernel not in _kernel_compatibility(viscous):
             raise ValueError(f"Kernel {kernel.name} is not compatible with viscous scheme {type(viscous).__name__}")
         if sync not in ("always", "lazy"):
@@ -681,3 +691,191 @@ def monitor_enstrophy_value(pfield: ParticleField) -> float:
     Jm = P[:, J_INDEX]
     w = np.stack([Jm[:, 5] - Jm[:, 7], Jm[:, 6] - Jm[:, 2], Jm[:, 1] - Jm[:, 3]], -1)
     return 0.5 * float(np.einsum("ij,ij->", P[:, GAMMA_INDEX], w))
+
+
+# ---- host-side conveniences of the FLOWVPM API that FLOWUnsteady calls around the hot path ------------------------------
+# (SURVEY.md Appendix B "I/O & misc").  Pure host code: they touch a field only through `particles`, `np`, `nt`, `t`,
+# `monitors()` and `pull()`, so the CPU tests drive them with a stand-in object.
+utilities_path = __import__("os").path.dirname(__import__("os").path.abspath(__file__))   # vpm.utilities_path (FLOWUnsteady.jl:73)
+
+
+def cd_statistics(C: np.ndarray):
+    """(ratio of zeros, mean, std, skewness, kurtosis, min, max) of the dynamic coefficient over the particles where it is
+    non-zero — the tuple vpm.monitor_Cd appends after `t` (unpacked at src/FLOWUnsteady_monitors.jl:702 as
+    `t, rationzero, mean, stddev, skew, kurt, minC, maxC`).  Sample standard deviation; skewness and kurtosis are the
+    standardised third and fourth central moments (kurtosis of a normal distribution = 3)."""
+    C = np.asarray(C, dtype=np.float64).ravel()
+    n = C.size
+    nz = C[C != 0.0]
+    if n == 0 or nz.size == 0:
+        return (1.0 if n else 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+    mean = float(nz.mean())
+    d = nz - mean
+    m2 = float(np.mean(d * d))
+    std = float(np.sqrt(np.sum(d * d) / (nz.size - 1))) if nz.size > 1 else 0.0
+    skew = float(np.mean(d ** 3) / m2 ** 1.5) if m2 > 0 else 0.0
+    kurt = float(np.mean(d ** 4) / (m2 * m2)) if m2 > 0 else 0.0
+    return (1.0 - nz.size / n, mean, std, skew, kurt, float(nz.min()), float(nz.max()))
+
+
+def _log_row(save_path, fname, header, row, first):
+    import os
+    with open(os.path.join(save_path, fname), "w" if first else "a") as f:
+        if first:
+            f.write(header + "\n")
+        f.write(",".join(repr(v) if isinstance(v, float) else str(v) for v in row) + "\n")
+
+
+def monitor_enstrophy(pfield, t, dt, save_path=None, run_name="", suff="enstrophy.log", vprintln=None, out=None) -> bool:
+    """vpm.monitor_enstrophy(pfield, t, dt; save_path, run_name, vprintln, out) (src/FLOWUnsteady_monitors.jl:614):
+    global enstrophy 0.5 sum Gamma_p . omega(x_p), reduced on the device (vpmb200_monitors), appended to `out` and to
+    `<save_path>/<run_name><suff>`.  Returns False (a runtime function's "do not stop" flag)."""
+    if pfield.np == 0:
+        return False
+    enstrophy = float(pfield.monitors()["enstrophy"])
+    if out is not None:
+        out.append(enstrophy)
+    if save_path is not None:
+        _log_row(save_path, run_name + suff, "nt,t (s),enstrophy (m^3/s^2)", (int(pfield.nt), float(t), enstrophy), pfield.nt == 0)
+    return False
+
+
+def monitor_Cd(pfield, t, dt, save_path=None, run_name="", suff="Chistory.log", vprintln=None, out=None) -> bool:
+    """vpm.monitor_Cd(pfield, t, dt; save_path, run_name, vprintln, out) (src/FLOWUnsteady_monitors.jl:697): statistics of
+    the SFS model coefficient C_d over the particles where it is non-zero; appends
+    [t, ratio of zeros, mean, std, skewness, kurtosis, min, max] to `out` and a CSV row to `<save_path>/<run_name><suff>`."""
+    if pfield.np == 0:
+        return False
+    if getattr(pfield, "_dev_dirty", 0):
+        pfield.pull(_E.FM_C)
+    stats = cd_statistics(pfield.particles[:pfield.np, C_INDEX][:, 0])
+    if out is not None:
+        out.append([float(t), *stats])
+    if save_path is not None:
+        _log_row(save_path, run_name + suff, "nt,t (s),ratio of zeros,mean,std,skewness,kurtosis,min,max",
+                 (int(pfield.nt), float(t), *stats), pfield.nt == 0)
+    return False
+
+
+def create_path(save_path: str, prompt: bool = True):
+    """vpm.create_path(save_path, prompt) (simulation.jl:318): make `save_path` an empty directory.  With prompt=True an
+    existing directory is only replaced after the user confirms on stdin (the reference asks the same question)."""
+    import os
+    import shutil
+    if os.path.isdir(save_path):
+        if prompt:
+            ans = input(f"\n\nFolder {save_path} already exists. Remove? (y/n) ")
+            if ans.strip().lower() != "y":
+                return
+        shutil.rmtree(save_path)
+    os.makedirs(save_path)
+
+
+def settings_of(pfield) -> dict:
+    """The solver settings of a field as plain data (what vpm.save_settings stores)."""
+    sfs = pfield.SFS
+    d = {"maxparticles": int(pfield.maxparticles), "floattype": "Float32" if pfield.R is np.float32 else "Float64",
+         "formulation": {"f": pfield.formulation.f, "g": pfield.formulation.g}, "kernel": pfield.kernel.name,
+         "viscous": type(pfield.viscous).__name__, "UJ": getattr(pfield.UJ, "__name__", str(pfield.UJ)),
+         "integration": getattr(pfield.integration, "__name__", str(pfield.integration)), "transposed": bool(pfield.transposed),
+         "relaxation": {"name": getattr(pfield.relaxation, "name", type(pfield.relaxation).__name__),
+                        "rlxf": getattr(pfield.relaxation, "rlxf", None), "nsteps_relax": getattr(pfield.relaxation, "nsteps_relax", None)},
+         "fmm": {"p": pfield.fmm.p, "ncrit": pfield.fmm.ncrit, "theta": pfield.fmm.theta, "nonzero_sigma": bool(pfield.fmm.nonzero_sigma)},
+         "SFS": {"type": type(sfs).__name__}}
+    for k in ("alpha", "rlxf", "minC", "maxC", "Cs"):
+        if hasattr(sfs, k):
+            d["SFS"][k] = getattr(sfs, k)
+    for k in ("clippings", "controls"):
+        if hasattr(sfs, k):
+            d["SFS"][k] = [getattr(c, "__name__", str(c)) for c in getattr(sfs, k)]
+    if hasattr(sfs, "procedure"):
+        d["SFS"]["procedure"] = getattr(sfs.procedure, "__name__", str(sfs.procedure))
+    if iscorespreading(pfield.viscous):
+        v = pfield.viscous
+        d["viscous_parameters"] = {"nu": v.nu, "sgm0": v.sgm0, "beta": v.beta, "itmax": v.itmax, "tol": v.tol}
+    return d
+
+
+def save_settings(pfield, file_name: str, path: str = "", suff: str = "_settings") -> str:
+    """vpm.save_settings(pfield, file_name; path) (simulation.jl:326).  The reference writes a JLD file; JLD is a Julia
+    serialisation no other tool reads, so the mirror writes the same content as `<file_name><suff>.json`."""
+    import json
+    import os
+    fname = os.path.join(path, file_name + suff + ".json")
+    with open(fname, "w") as f:
+        json.dump(settings_of(pfield), f, indent=1)
+    return fname
+
+
+def initialize_verbose(verbose, save_path, run_name, pfield, dt, nsteps_save, runtime_function=None,
+                       static_particles_function=None, v_lvl: int = 0):
+    """vpm.initialize_verbose(...) (simulation.jl:333): returns (line1, line2, run_id, file_verbose, vprintln, time_beg);
+    `vprintln(str, v_lvl)` prints and mirrors every line into `<save_path>/<run_name>.log`."""
+    import datetime
+    import os
+    line1 = "*" * 73
+    line2 = "-" * 73
+    run_id = save_path if save_path is not None else run_name
+    file_verbose = os.path.join(save_path, run_name + ".log") if save_path is not None else None
+    if file_verbose is not None:
+        open(file_verbose, "w").close()
+
+    def vprintln(s="", lvl=0):
+        text = "\t" * lvl + str(s)
+        if verbose:
+            print(text)
+        if file_verbose is not None:
+            with open(file_verbose, "a") as f:
+                f.write(text + "\n")
+
+    time_beg = datetime.datetime.now()
+    vprintln(line1, v_lvl)
+    vprintln(f"START {run_id}\t{time_beg}", v_lvl)
+    vprintln(line1, v_lvl)
+    vprintln(f"max particles: {pfield.maxparticles}, dt: {dt}, save every {nsteps_save} steps", v_lvl + 1)
+    return line1, line2, run_id, file_verbose, vprintln, time_beg
+
+
+def finalize_verbose(time_beg, line1, vprintln, run_id, v_lvl: int = 0):
+    """vpm.finalize_verbose(time_beg, line1, vprintln, run_id, v_lvl) (simulation.jl:450)."""
+    import datetime
+    time_end = datetime.datetime.now()
+    el = time_end - time_beg
+    hrs, rem = divmod(int(el.total_seconds()), 3600)
+    mins, secs = divmod(rem, 60)
+    vprintln(line1, v_lvl)
+    vprintln(f"END {run_id}\t{time_end}", v_lvl)
+    vprintln(line1, v_lvl)
+    vprintln(f"ELAPSED TIME: {hrs} hours {mins} minutes {secs} seconds", v_lvl)
+
+
+def run_vpm_(pfield, dt: float, nsteps: int, runtime_function=None, static_particles_function=None, nsteps_relax: int = 1,
+             save_path=None, run_name: str = "pfield", nsteps_save: int = 1, verbose: bool = True, v_lvl: int = 0,
+             create_savepath: bool = True, prompt: bool = True, save_time: bool = True):
+    """vpm.run_vpm!(pfield, dt, nsteps; ...): FLOWVPM's own driver loop (FLOWUnsteady inlines it, simulation.jl:300-447).
+    Per step: static particles in -> nextstep -> static particles out -> runtime_function(pfield, t, dt) (True stops the
+    run) -> save every `nsteps_save` steps."""
+    if save_path is not None:
+        if create_savepath:
+            create_path(save_path, prompt)
+        save_settings(pfield, run_name, path=save_path)
+    line1, line2, run_id, file_verbose, vprintln, time_beg = initialize_verbose(
+        verbose, save_path, run_name, pfield, dt, nsteps_save, runtime_function, static_particles_function, v_lvl)
+    for i in range(nsteps + 1):
+        if i % max(1, nsteps // 10) == 0:
+            vprintln(f"Time step {i} out of {nsteps}\tParticles: {get_np(pfield)}", v_lvl + 1)
+        relax = (getattr(pfield.relaxation, "id", 0) != 0 and nsteps_relax >= 1 and i > 0 and i % nsteps_relax == 0)
+        org_np = get_np(pfield)
+        if i != 0:
+            if static_particles_function is not None:
+                static_particles_function(pfield, pfield.t, dt)
+            nextstep(pfield, dt, relax=relax)
+            for pi in range(get_np(pfield), org_np, -1):     # statics were appended last (simulation.jl:361-365)
+                remove_particle(pfield, pi - 1)
+        breakflag = bool(runtime_function(pfield, pfield.t, dt)) if runtime_function is not None else False
+        if save_path is not None and (i % nsteps_save == 0 or i == nsteps or breakflag):
+            save(pfield, run_name, path=save_path, add_num=True, overwrite_time=pfield.t if save_time else float(pfield.nt))
+        if breakflag:
+            break
+    finalize_verbose(time_beg, line1, vprintln, run_id, v_lvl)
+    return pfield

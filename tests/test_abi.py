@@ -72,7 +72,9 @@ def test_vpm_mirror_surface():
         correctedpedrizzetti norelaxation relaxation_none Inviscid CoreSpreading zeta_fmm isinviscid iscorespreading
         _kernel_compatibility SFS_none SFS_Cs_nobackscatter SFS_Cd_twolevel_nobackscatter SFS_Cd_threelevel_nobackscatter
         DynamicSFS ConstantSFS Estr_fmm Estr_direct pseudo3level pseudo3level_positive clipping_backscatter
-        control_directional control_magnitude control_sigmasensor isSFSenabled save read zeta_direct""".split()
+        control_directional control_magnitude control_sigmasensor isSFSenabled save read zeta_direct
+        ParticleStrengthExchange monitor_enstrophy monitor_Cd save_settings create_path initialize_verbose
+        finalize_verbose utilities_path run_vpm_""".split()
     for n in names:
         assert hasattr(vpm, n), n
     g, dg = vpm.gaussianerf.g_dgdr(1.3)
