@@ -200,3 +200,26 @@ def test_oracle_matches_its_frozen_step_fixture():
         for _ in range(2):
             t, nt = o.nextstep(P, o.default_schemes(**kw), 5e-3, (1.0, -0.5, 0.25), relax=True, t=t, nt=nt)
         assert np.allclose(P, G[name], rtol=1e-12, atol=1e-14), name
+
+
+def test_thin_vortex_ring_self_induced_velocity():
+    """a thin ring of circulation Gamma and radius R discretised along its centreline moves along its axis
+    with U = Gamma/(4 pi R) [ln(8R/sigma) - C]: direction by the right-hand rule, 1/(4 pi R) in front of the logarithm, a
+    constant C that does not depend on sigma, R or Gamma — and within a few percent of Saffman's speed of a Gaussian-core ring
+    (core a = sqrt(2) sigma, constant 0.558), which is the velocity of the vorticity centroid rather than of the centreline."""
+    def ring(N, R, G, sig):
+        phi = 2 * np.pi * (np.arange(N) + 0.5) / N
+        x = np.stack([R * np.cos(phi), R * np.sin(phi), np.zeros(N)], -1)
+        t = np.stack([-np.sin(phi), np.cos(phi), np.zeros(N)], -1)
+        return x, G * (2 * np.pi * R / N) * t, np.full(N, sig)
+
+    consts = []
+    for R, G, sig in ((1.0, 1.0, 0.05), (1.0, 1.0, 0.02), (2.0, 3.0, 0.04)):
+        x, g, s = ring(4000, R, G, sig)
+        U, J = o.uj_direct("gaussianerf", x, g, s, x[:4], accum=0)
+        assert np.abs(U[:, :2]).max() < 1e-12 and np.all(U[:, 2] > 0)          # along +z for a counter-clockwise ring
+        consts.append(np.log(8 * R / sig) - 4 * np.pi * R * U[0, 2] / G)
+        saffman = G / (4 * np.pi * R) * (np.log(8 * R / (np.sqrt(2) * sig)) - 0.558)
+        assert abs(U[0, 2] / saffman - 1) < 0.05
+        assert abs(J[0, 0] + J[0, 4] + J[0, 8]) < 1e-12 * np.abs(J[0]).max()
+    assert max(consts) - min(consts) < 3e-3, consts
