@@ -110,6 +110,14 @@ class ShardedField:
                     if r != self.rank and self._ntiles[r] > 0:
                         apply_rest(self._slot_ptr(r), self._ntiles[r])
 
+    def _state_view(self):
+        """(43, ld) torch view of the backend's SoA state (no copy).  The CUDA engine hands out its device pointer; the
+        numpy stand-in of the gloo tests provides `state_tensor()` itself."""
+        if hasattr(self.b, "state_tensor"):
+            return self.b.state_tensor()
+        ptr, ld = self.b.device_field(0)
+        return torch.as_tensor(_DevArray(ptr, (43, ld)), device=self.device)
+
     # ---- UJ_fmm over the sharded field: replicated tree, leaves split over the ranks ---------------------------------
     def _uj_fmm(self, reset: bool, reset_sfs: bool, sfs: bool):
         """All ranks gather (X, Gamma, sigma) of every particle (56 B each), build the SAME tree, evaluate 1/world of the
@@ -126,9 +134,8 @@ class ShardedField:
         counts = [int(v) for v in cnt.tolist()]
         ntot, slot = sum(counts), max(max(counts), 1)
         off = sum(counts[:self.rank])
-        ptr, ld = b.device_field(0)
         with self._stream_ctx():
-            state = torch.as_tensor(_DevArray(ptr, (43, ld)), device=dev)
+            state = self._state_view()
             ldg = (ntot + 31) // 32 * 32
             if getattr(self, "_G", None) is None or self._G.shape[1] < ldg:
                 self._G = torch.zeros((24, ldg), dtype=torch.float64, device=dev)

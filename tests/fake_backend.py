@@ -111,6 +111,32 @@ class FakeBackend:
         S = np.einsum("plk,pl->pk", Jm, a) if self.so.transposed else np.einsum("pkl,pl->pk", Jm, a)
         self.P[:, E.SFS:E.SFS + 3] += S - bq
 
+    # ---- UJ_fmm over the sharded field (dist.ShardedField._uj_fmm): the stand-in "FMM" is the exact sum -------------------
+    def state_tensor(self):
+        import torch
+        return torch.from_numpy(self.P.T)            # (43, n) view: writes go straight into self.P
+
+    def fmm_global(self, G_ptr, ldg, ntot, part, nparts, pass_):
+        """Same contract as vpmb200_fmm_global: G holds (X, Gamma, sigma) of ALL particles in rows 0..6; this rank fills the
+        U (9..11), J (15..23) rows [pass 0] or the E_str rows (12..14) [pass 1, reading the all-reduced J] of ITS share of
+        the particles and zeros everywhere else, so that one all-reduce over the ranks assembles the field."""
+        from flowunsteady_b200.dist import partition
+        G = _view(G_ptr, 24 * ldg).reshape(24, ldg)
+        lo, hi = partition(ntot, nparts)[part]
+        X, Gm, sg = G[0:3, :ntot].T.copy(), G[3:6, :ntot].T.copy(), G[6, :ntot].copy()
+        if pass_ == 0:
+            G[9:24, :] = 0.0
+            if hi > lo:
+                U, J = o.uj_direct(self.kernel, X, Gm, sg, X[lo:hi], accum=0)
+                G[9:12, lo:hi] = U.T
+                G[15:24, lo:hi] = J.T
+        else:
+            G[12:15, :] = 0.0
+            if hi > lo:
+                Jall = G[15:24, :ntot].T.copy()
+                Es = o.estr_direct(self.kernel, int(self.so.transposed), X, Gm, sg, Jall, X[lo:hi], Jall[lo:hi], accum=0)
+                G[12:15, lo:hi] = np.asarray(Es).T
+
     # ---- per-particle stages through the oracle's exported pieces -------------------------------------------------
     def stage(self, stage, a=0.0, b=0.0, dt=0.0, Uinf=None):
         P, so = self.P, self.so
