@@ -3,9 +3,13 @@
 
 Metric (BASELINE.json): particle interactions/s and s/timestep (UJ + SFS + RK3) at N = 1M, direct P2P FP64.
 Workload (BASELINE.json configs[2]): synthetic isolated vortex-ring leapfrog, N = 1,000,000 particles, gaussianerf.
-A *step* is one `vpm.nextstep` with rungekutta3 + pedrizzetti relaxation and SFS_none (FLOWUnsteady's defaults,
-/root/reference/src/FLOWUnsteady_simulation.jl:36-44): 3 substeps + the relaxation evaluation = 4 full U/J
-evaluations = 4 N^2 ordered (target, source) interactions, plus the O(N) pack / update / relaxation kernels.
+A *step* is one `vpm.nextstep` with rungekutta3 + pedrizzetti relaxation and the dynamic SFS model of the
+rotor-hover high-fidelity preset (DynamicSFS, pseudo3level_positive, alpha = 0.999, backscatter clipping;
+/root/reference/examples/rotorhover/rotorhover.jl:53-55) — the metric's "UJ+SFS+RK3".  That is 3 substeps (the first
+evaluates twice: test filter + domain filter) + the relaxation evaluation = 5 full U/J evaluations, 4 of them followed
+by the E_str pass (K2), plus the O(N) pack / coefficient / update / relaxation kernels.  An *interaction* is one ordered
+(target, source) pair evaluated by the U+J kernel: 5 N^2 per step; the E_str pairs are NOT counted in
+`value` although their time is.  `--sfs none` times FLOWUnsteady's default step (SFS_none, simulation.jl:36-44; 4 N^2).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles 1000000] [--sfs none|dynamic]
 
@@ -14,8 +18,8 @@ N > 1 is launched by the driver as torchrun (one rank per GPU, NCCL); particles 
 
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores): the
 reference's own implementation is Julia code in an un-vendored dependency and no julia binary exists in this image
-(DESIGN.md §3), so there is no oracle/_ref; each of its steps is a bounded sample (1024 targets x N sources per
-evaluation) of the same workload.
+(DESIGN.md §3), so there is no oracle/_ref; each of its steps is a bounded sample (REF_TARGETS targets x N sources per
+evaluation, the same sequence of U/J and E_str evaluations as our step) of the same workload.
 """
 from __future__ import annotations
 
@@ -36,7 +40,32 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_INTERACTION = 86          # U + J, gaussianerf, reference expression form
 FP64_INSTR_FAR = 37                 # FP64-pipe instructions K1 issues per far-field interaction (uj_direct.cuh, SASS-counted)
+FLOPS_PER_ESTR = 47                 # E_str pass, reference expression form
 EVALS_PER_STEP = {"none": 4, "dynamic": 5}   # full U/J evaluations per RK3 + pedrizzetti step
+ESTR_PER_STEP = {"none": 0, "dynamic": 4}    # ... of which this many are followed by the E_str pass
+REF_TARGETS = 512                   # bounded sample of the reference arm: targets per evaluation
+PARITY_TARGETS = 2048               # sampled targets of the parity key
+PARITY_TOL = {"U": 1e-12, "J": 1e-12, "SFS": 1e-11}   # max-norm relative (north_star: 1e-12 for U/J; E_str DESIGN.md §3)
+METRIC = "particle interactions/s (UJ+SFS+RK3 step, direct P2P FP64)"
+FIELD_NAMES = {"rings": "vortex-ring leapfrog (2 coaxial rings)", "rotor": "rotor-hover helical wake stand-in",
+               "random": "random particle field"}
+
+
+def host_threads() -> int:
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def make_config(args, n: int, world: int) -> dict:
+    """The `config` object of BOTH arms (ours and --impl reference) — identical by construction."""
+    sfs = ("DynamicSFS(pseudo3level_positive, alpha=0.999, clipping_backscatter)" if args.sfs == "dynamic" else "SFS_none")
+    return {"workload": f"{FIELD_NAMES[args.field]}, direct P2P FP64, gaussianerf, rVPM, rungekutta3 + pedrizzetti, {sfs}",
+            "particles": int(n), "sfs": args.sfs, "uj": args.uj, "field": args.field,
+            "evaluations_per_step": EVALS_PER_STEP[args.sfs], "estr_passes_per_step": ESTR_PER_STEP[args.sfs],
+            "gpus": int(world)}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -47,13 +76,15 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", dest="n", type=int, default=1_000_000, help="particles (BASELINE config: 1M)")
-    ap.add_argument("--sfs", default="none", choices=["none", "dynamic"], help="SFS scheme of the timed step")
+    ap.add_argument("--sfs", default="dynamic", choices=["none", "dynamic"],
+                    help="SFS scheme of the timed step (dynamic = the metric's UJ+SFS+RK3 step)")
     ap.add_argument("--uj", default="direct", choices=["direct", "fmm"],
                     help="direct = headline (BASELINE configs[2]); fmm = secondary mode (configs[1]/[3]): UJ_fmm p=4 ncrit=50 theta=0.4")
     ap.add_argument("--field", default="rings", choices=["rings", "rotor", "random"], help="synthetic field generator")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffers) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fmm", action="store_true", help="skip the secondary UJ_fmm figures")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle parity check of the timed state")
     ap.add_argument("--cpu-targets", type=int, default=4096, help="targets of the CPU baseline slab")
     return ap.parse_args()
 
@@ -108,23 +139,32 @@ def make_field(n: int, kind: str = "rings"):
 
 # --------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """CPU arm: OpenMP restatement of the reference algorithm on the host cores (rank 0 only)."""
+    """CPU arm: OpenMP restatement of the reference algorithm on ALL host cores (rank 0 only; the other ranks exit 0).
+
+    Each step replays our step's sequence of pair evaluations on a bounded sample: REF_TARGETS sampled targets x all N
+    sources, EVALS_PER_STEP U/J evaluations and ESTR_PER_STEP E_str evaluations (the O(N) update kernels are noise)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     from oracle import oracle as o
     o.build()
+    o.set_num_threads(host_threads())                          # torchrun exports OMP_NUM_THREADS=1
     x, g, s = make_field(args.n, args.field)
     n = x.shape[0]
-    m = 1024                                                   # bounded sample: targets per evaluation
+    m = REF_TARGETS
     idx = np.random.default_rng(1234).choice(n, m, replace=False)
     xt = np.ascontiguousarray(x[idx])
-    evals = EVALS_PER_STEP[args.sfs]
+    evals, nestr = EVALS_PER_STEP[args.sfs], ESTR_PER_STEP[args.sfs]
     cores = o.num_threads()
+    Js = np.random.default_rng(7).standard_normal((n, 9)) if nestr else None     # E_str reads J of every source
+    Jt = np.ascontiguousarray(Js[idx]) if nestr else None
 
     def step():
-        for _ in range(evals):
+        for k in range(evals):
             o.uj_direct("gaussianerf", x, g, s, xt, accum=0)
+            if k < nestr:
+                o.estr_direct("gaussianerf", 1, x, g, s, Js, xt, Jt, accum=0)
 
     for _ in range(args.warmup):
         step()
@@ -134,19 +174,75 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     value = evals * m * n / dt
     line = {
-        "impl": "reference", "metric": "particle interactions/s (UJ+SFS+RK3 step, direct P2P FP64)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "vortex-ring leapfrog, direct P2P FP64, gaussianerf", "particles": n, "sfs": args.sfs,
-                   "evaluations_per_step": evals},
+        "data": "synthetic", "config": make_config(args, n, world),
         "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": "port",
-                         "sample": f"{m} targets x {n} sources per U/J evaluation, {evals} evaluations per step; "
-                                   "OpenMP restatement of the reference algorithm (oracle/vpm_oracle.c), not FLOWVPM itself"},
+                         "sample": f"{m} sampled targets x {n} sources per evaluation; {evals} U/J + {nestr} E_str "
+                                   "evaluations per step (the sequence of our step); -O3 -ffp-contract=off scalar glibc "
+                                   "erf/exp in the reference's expression form; OpenMP restatement of the reference "
+                                   "algorithm (oracle/vpm_oracle.c), not FLOWVPM itself"},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "full_step_ms_extrapolated": dt * 1e3 * n / m,
     }
     print(json.dumps(line), flush=True)
+
+
+def gather_state_rows(field, eng, rows, world, rank, local_rank):
+    """Rows `rows` of the sharded SoA state of ALL particles, in global particle order, as a (len(rows), n) numpy array on
+    rank 0 (None elsewhere).  One all-gather of equal-size slots over NCCL; a plain device read at world = 1."""
+    import torch
+    import torch.distributed as dist
+    eng.synchronize()
+    dev = torch.device("cuda", local_rank)
+    state = field._state_view()
+    n_loc = int(eng.np)
+    cnt = torch.zeros(world, dtype=torch.int64, device=dev)
+    cnt[rank] = n_loc
+    if world > 1:
+        dist.all_reduce(cnt)
+    counts = [int(v) for v in cnt.tolist()]
+    slot = max(max(counts), 1)
+    send = torch.zeros((len(rows), slot), dtype=torch.float64, device=dev)
+    send[:, :n_loc] = state[list(rows), :n_loc]
+    if world > 1:
+        recv = torch.empty((world, len(rows), slot), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1))
+    else:
+        recv = send.view(1, len(rows), slot)
+    torch.cuda.synchronize()
+    if rank != 0:
+        return None
+    return np.concatenate([recv[r, :, :c].cpu().numpy() for r, c in enumerate(counts)], axis=1)
+
+
+def parity_check(field, eng, sch, n, world, rank, local_rank):
+    """Driver-visible parity record: PARITY_TARGETS targets sampled with default_rng(1234) over ALL particles of the (sharded)
+    field; U, J from the oracle's UJ_direct over all n sources, E_str from the oracle's Estr_direct fed with the device's J
+    (whose parity the same record checks).  Returns the dict printed as "parity" in the JSON line."""
+    rows = list(range(0, 7)) + list(range(9, 12)) + list(range(15, 24)) + list(range(39, 42))
+    A = gather_state_rows(field, eng, rows, world, rank, local_rank)
+    if rank != 0:
+        return None
+    from oracle import oracle as o
+    o.build()
+    o.set_num_threads(host_threads())
+    t0 = time.perf_counter()
+    X, G, S = np.ascontiguousarray(A[0:3].T), np.ascontiguousarray(A[3:6].T), np.ascontiguousarray(A[6])
+    Ud, Jd, Ed = A[7:10].T, np.ascontiguousarray(A[10:19].T), A[19:22].T
+    idx = np.sort(np.random.default_rng(1234).choice(n, min(PARITY_TARGETS, n), replace=False))
+    Uo, Jo = o.uj_direct("gaussianerf", X, G, S, X[idx], accum=1)
+    Eo = o.estr_direct("gaussianerf", int(sch.transposed), X, G, S, Jd, X[idx], Jd[idx], accum=1)
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / np.abs(b).max())
+
+    err = {"U": rel(Ud[idx], Uo), "J": rel(Jd[idx], Jo), "SFS": rel(Ed[idx], Eo)}
+    ok = all(np.isfinite(err[k]) and err[k] < PARITY_TOL[k] for k in err)
+    return {**err, "tol": PARITY_TOL, "ok": bool(ok), "targets": int(idx.size), "sources": int(n), "ranks": int(world),
+            "measure": "max-norm relative error vs oracle (UJ_direct / Estr_direct restatement, long-double accumulation)",
+            "oracle_s": time.perf_counter() - t0}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -220,11 +316,13 @@ def run_ours(args):
     def step():
         field.nextstep(dt_sim, Uinf, relax=True)
 
-    # ---- FP64 peak of this GPU, live (roofline denominator; MEASURED_PEAKS.json has no FP64 entry) -----------------
+    # ---- FP64 peak of this GPU, live (roofline denominator; MEASURED_PEAKS.json has no FP64 entry and the profiling guide
+    #      states no FP64 fallback).  Denominator = the FP64 PIPE rate SMs x 64 lanes x 2 flop x SM clock, the clock taken from
+    #      the microbenchmark's own clock64 span; the best register-only DFMA throughput is reported beside it.
     L = _lib.lib()
-    tf, ms_ = C.c_double(), C.c_double()
-    L.vpmb200_measure_fp64_peak(local_rank, 2000, 5, C.byref(tf), C.byref(ms_))
-    fp64_peak_tflops = tf.value
+    pk = (C.c_double * 8)()
+    L.vpmb200_measure_fp64_peak2(local_rank, 20000, 3, pk)
+    fp64_dfma_tflops, fp64_clock_mhz, fp64_peak_tflops = pk[0], pk[2], pk[3]
 
     # ---- device-resident throughput: W warm-up + K timed steps ------------------------------------------------------
     for _ in range(args.warmup):
@@ -256,17 +354,34 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- dominant kernel alone: one U/J evaluation (K1 + its pack kernel) ---------------------------------------------
+    # ---- dominant kernel alone: one U/J evaluation (K1 + its pack kernel), and the same with the E_str pass (K2) -----
     k1_reps = 3
     k1_ms = timed(lambda: field.uj(True, False, False), k1_reps) / k1_reps
     k1_rate = float(n) * float(n) / (k1_ms * 1e-3)
+    k12_ms = timed(lambda: field.uj(True, True, True), k1_reps) / k1_reps
+    k2_ms = max(k12_ms - k1_ms, 1e-6)
+    # K2 skips tiles beyond T_FAR (zeta/zeta(0) < 8e-20), so its ALGORITHMIC rate counts all N^2 pairs of the reference's
+    # Estr_direct while it touches only the neighbourhood
+    k2 = {"kernel": "estr_direct_f64_kernel<gaussianerf>", "ms_per_pass": k2_ms,
+          "algorithmic_interactions_per_s": float(n) * float(n) / (k2_ms * 1e-3),
+          "algorithmic_tflops_per_gpu": float(n) * float(n) * FLOPS_PER_ESTR / (k2_ms * 1e-3) / 1e12 / world,
+          "flops_per_interaction": FLOPS_PER_ESTR, "share_of_uj_plus_estr": k2_ms / k12_ms}
+
+    # ---- parity of what was just timed: 2048 sampled targets of the (sharded) U, J and SFS rows against the oracle -----
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(field, eng, sch, n, world, rank, local_rank)   # state rows are fresh from uj(True, True, True)
     achieved_tflops = k1_rate * FLOPS_PER_INTERACTION / 1e12 / world       # per GPU
     roofline = {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None, "traffic": None,
                 "kernel": "uj_direct_f64_kernel<gaussianerf>", "kernel_ms": k1_ms,
                 "interactions_per_s": k1_rate, "flops_per_interaction": FLOPS_PER_INTERACTION,
-                "peak_source": "live DFMA microbenchmark on this GPU (vpmb200_measure_fp64_peak); "
-                               "MEASURED_PEAKS.json has HBM/bf16 only",
+                "peak_source": "FP64 pipe rate = SMs x 64 lanes x 2 flop x SM clock, the clock measured by clock64 inside a "
+                               "live DFMA microbenchmark on this GPU (vpmb200_measure_fp64_peak2); MEASURED_PEAKS.json has "
+                               "HBM/bf16 only",
+                "peak_detail": {"sm_clock_mhz_measured": fp64_clock_mhz, "sms": int(pk[6]),
+                                "dfma_microbenchmark_tflops": fp64_dfma_tflops, "dfma_microbenchmark_frac_of_pipe": pk[4],
+                                "dfma_shape": int(pk[5])},
                 # `achieved` counts the 86 ALGORITHMIC flops of the reference's expression form; the kernel
                 # itself issues FP64_INSTR_FAR FP64-pipe instructions per far-field interaction (the bulk at N = 1M; SASS
                 # count of the unrolled far loop), so frac can exceed 1 while the pipe is not saturated:
@@ -284,6 +399,44 @@ def run_ours(args):
                 roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass
+
+    # ---- secondary figures of the DIRECT path (single GPU): where K1's time goes on this field and on the rotor-hover
+    #      stand-in — far-tile fraction, the regularised-branch rate alone, the SFS_none step
+    direct2 = None
+    if world == 1 and not args.no_fmm:
+        try:
+            direct2 = {"tile_stats_this_field": eng.direct_tile_stats()}
+            if args.sfs == "dynamic":          # FLOWUnsteady's default step (SFS_none): 4 evaluations, no E_str pass
+                eng.set_schemes(fb.default_schemes(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti",
+                                                   uj=args.uj))
+                ms_none = timed(step, 1)
+                eng.set_schemes(sch)
+                direct2["step_sfs_none"] = {"ms_per_step": ms_none, "interactions_per_s": 4 * float(n) * float(n) / (ms_none * 1e-3)}
+            # regularised branch alone: the same generator at 200k particles with sigma blown up so that EVERY pair is inside
+            # T_FAR (no tile takes the far loop), and the rotor-hover stand-in (BASELINE configs[1]) at 200k as it is
+            from flowunsteady_b200 import fields as F
+            for tag, (xx, gg, ss) in (("all_regularised_200k", (lambda r: (r[0], r[1], r[2] * 1000.0))(F.vortex_rings(200_000))),
+                                      ("rotor_hover_200k", F.rotor_wake(200_000, nfil=101, nsteps_per_rev=72))):
+                m2 = xx.shape[0]
+                with fb.Engine(m2, schemes=fb.default_schemes(uj="direct")) as e2:
+                    e2.upload(fb.new_particles(xx, gg, ss))
+                    e2.uj(); e2.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        e2.uj()
+                    e2.synchronize()
+                    t_uj = (time.perf_counter() - t0) / 3
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        e2.uj(True, True, True)
+                    e2.synchronize()
+                    t_uje = (time.perf_counter() - t0) / 3
+                    direct2[tag] = {"particles": m2, "ms_per_uj_evaluation": t_uj * 1e3,
+                                    "uj_interactions_per_s": float(m2) * m2 / t_uj,
+                                    "ms_per_uj_plus_estr": t_uje * 1e3, "all_in_interactions_per_s": float(m2) * m2 / t_uje,
+                                    **e2.direct_tile_stats()}
+        except Exception as exc:   # secondary figure: never fail the headline line
+            direct2 = {"error": str(exc)}
 
     # ---- secondary: the same field through UJ_fmm (reference defaults p=4, ncrit=50, theta=0.4) — BASELINE configs[1]
     #      (rotor hover high fidelity runs RK3 + dynamic SFS on the FMM path); single GPU only
@@ -408,6 +561,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as o
         o.build()
+        o.set_num_threads(host_threads())
         m = args.cpu_targets
         idx = np.random.default_rng(1234).choice(n, m, replace=False)
         xt = np.ascontiguousarray(x[idx])
@@ -422,23 +576,29 @@ def run_ours(args):
                        "implementation (FLOWVPM) cannot run in this image"}
 
     if rank == 0:
+        cfg = make_config(args, n, world)
         line = {
-            "metric": "particle interactions/s (UJ+SFS+RK3 step, direct P2P FP64)", "value": value,
+            "metric": METRIC, "value": value,
             "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "s_per_timestep": ms_per_step * 1e-3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "vortex-ring leapfrog (2 coaxial rings), direct P2P FP64, gaussianerf, rVPM, "
-                                   "rungekutta3 + pedrizzetti", "particles": n, "sfs": args.sfs,
-                       "evaluations_per_step": evals, "parallelism": f"targets block-partitioned over {world} GPU(s), "
-                       "source tiles all-gathered (NCCL)", "l2": "inputs larger than L2 (state 344 MB > 126 MB); state is "
-                       "rewritten every substep"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "secondary": fmm,
+            "config": cfg,
+            "config_notes": {"parallelism": f"targets block-partitioned over {world} GPU(s), source tiles all-gathered (NCCL)",
+                             "l2": "inputs larger than L2 (state 344 MB > 126 MB); state is rewritten every substep",
+                             "interaction": "ordered (target, source) pair of the U+J kernel; E_str pairs are timed but "
+                                            "not counted"},
+            "roofline": roofline, "estr_pass": k2, "parity": parity, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
+            "secondary": fmm, "secondary_direct": direct2,
         }
         print(json.dumps(line), flush=True)
+    failed = bool(parity is not None and not parity["ok"]) if rank == 0 else False
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        print(f"[bench] PARITY FAILED: {parity}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():

@@ -69,6 +69,7 @@ SYMBOLS = {
     "vpmb200_fmm_global": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "vpmb200_set_option": (C.c_int32, [_H, C.c_char_p, C.c_int64]),
     "vpmb200_fmm_stats": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "vpmb200_direct_tile_stats": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "vpmb200_launch_count": (C.c_int32, [_H, C.POINTER(C.c_uint64)]),
     "vpmb200_tiles_for": (C.c_int64, [C.c_int64]),
     "vpmb200_tile_doubles": (C.c_int64, []),
@@ -77,6 +78,7 @@ SYMBOLS = {
     "vpmb200_uj_from_records": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int32]),
     "vpmb200_estr_from_records": (C.c_int32, [_H, C.c_void_p, C.c_int64]),
     "vpmb200_measure_fp64_peak": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _dp, _dp]),
+    "vpmb200_measure_fp64_peak2": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _dp]),
     "vpmb200_stage": (C.c_int32, [_H, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p]),
 }
 

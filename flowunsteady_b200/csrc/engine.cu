@@ -687,6 +687,31 @@ __global__ void join_rows_kernel(const double* __restrict__ soa, int64_t ld, int
     for (int c = 0; c < nc; ++c) aos[i * nc + c] = soa[(size_t)c * ld + i];
 }
 
+// Instrumentation (not on the hot path): how many (target block, source tile) pairs K1 sends to its branch-free far loop —
+// and K2 skips — for the CURRENT field.  One CTA per target block recomputes the box exactly as the pair kernels do.
+__global__ void __launch_bounds__(UJ_BT) tile_class_count_kernel(const double* __restrict__ srec, int ntiles,
+                                                                 const double* __restrict__ tx, const double* __restrict__ ty,
+                                                                 const double* __restrict__ tz, int64_t nt,
+                                                                 unsigned long long* __restrict__ far_count) {
+    __shared__ PairSmem sm;
+    __shared__ int block_far;
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * UJ_BT + tid;
+    const bool live = i < nt;
+    if (tid == 0) block_far = 0;
+    cta_target_box(sm, live, live ? tx[i] : 0.0, live ? ty[i] : 0.0, live ? tz[i] : 0.0);
+    int mine = 0;
+    for (int k = tid; k < ntiles; k += UJ_BT) {
+        const double* hdr = srec + (size_t)k * TILE_DOUBLES + TILE_HDR;
+        double h[7];
+        for (int c = 0; c < 7; ++c) h[c] = hdr[c];
+        mine += box_dist2(sm.tbox, h) > h[6] ? 1 : 0;
+    }
+    atomicAdd(&block_far, mine);
+    __syncthreads();
+    if (tid == 0) atomicAdd(far_count, (unsigned long long)block_far);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1199,6 +1224,49 @@ int32_t vpmb200_fmm_stats(vpmb200_handle e, int64_t* stats) {
     stats[2] = e->fmm.nlevels;
     stats[3] = e->fmm.n_m2l;
     stats[4] = e->fmm.n_p2p;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_direct_tile_stats(vpmb200_handle e, int64_t* stats) {
+    CHECK_HANDLE(e);
+    if (!stats) return fail(e, VPMB200_EINVAL, "stats is NULL");
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (e->np <= 0) return VPMB200_OK;
+    if (e->np >= 2000000000LL) return fail(e, VPMB200_ECAPACITY, "tile statistics index particles with 32-bit integers");
+    CU_TRY(e, cudaSetDevice(e->device));
+    e->shard_sorted_np = -1;
+    const int64_t n = e->np;
+    const int ntiles = (int)vpmb200_tiles_for(n);
+    const unsigned nb = blocks_for(n, PK_BT);
+    const double *tx = e->state + (size_t)F_X * e->ld, *ty = tx + e->ld, *tz = ty + e->ld;
+    if (e->direct_sort && n >= 4 * TILE_SRC) {   // the geometry do_uj_direct_sorted uses
+        std::string err;
+        if (fmm_reserve(e->fmm, n, 50, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+        FmmWorkspace& w = e->fmm;
+        if (fmm_sort(w, e->state, e->ld, n, e->stream, e->launches, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
+        gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X, 1, n, w.perm, w.sx, w.lds);
+        gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X + 1, 1, n, w.perm, w.sy, w.lds);
+        gather_rows_kernel<<<nb, PK_BT, 0, e->stream>>>(e->state, e->ld, F_X + 2, 1, n, w.perm, w.sz, w.lds);
+        pack_uj_records_kernel<<<blocks_for(n, TILE_SRC), TILE_SRC, 0, e->stream>>>(e->state, e->ld, n, w.perm, e->rec);
+        CU_TRY(e, cudaGetLastError());
+        e->launches += 4;
+        tx = w.sx; ty = w.sy; tz = w.sz;
+    } else {
+        int32_t rc = pack_uj(e, e->rec);
+        if (rc) return rc;
+    }
+    CU_TRY(e, cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+    const unsigned nblocks = blocks_for(n, UJ_BT);
+    tile_class_count_kernel<<<nblocks, UJ_BT, 0, e->stream>>>(e->rec, ntiles, tx, ty, tz, n, e->counter);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    unsigned long long c = 0;
+    CU_TRY(e, cudaMemcpyAsync(&c, e->counter, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    stats[0] = nblocks;
+    stats[1] = ntiles;
+    stats[2] = (int64_t)c;
+    stats[3] = (int64_t)nblocks * ntiles;
     return VPMB200_OK;
 }
 

@@ -1,7 +1,13 @@
-// peak_fp64.cu — measures the FP64 vector-pipe FMA peak of the device, live, for the roofline denominator.
-// MEASURED_PEAKS.json carries HBM and bf16 only; K1 is bound by the FP64 pipe, so bench.py needs
-// this number from the same box, the same clocks and the same run.  Pure register DFMA chains: 8 independent
-// accumulators per thread, 1024 threads per SM x 2 CTAs, no memory traffic.
+// peak_fp64.cu — the FP64 vector-pipe FMA peak of the device, live, for the roofline denominator.
+// MEASURED_PEAKS.json carries HBM and bf16 only; K1 is bound by the FP64 pipe, so bench.py needs this number
+// from the same box, the same clocks and the same run.
+//
+// Two figures are produced:
+//   * `pipe`  = SMs x 64 FP64 lanes x 2 flop x f_SM, with f_SM MEASURED from the kernel's own clock64() span against the CUDA
+//     event span (no nvidia-smi sampling).  This is the issue-rate ceiling ncu's sm__inst_executed_pipe_fp64 counts against
+//     (one warp-wide DFMA per 2 cycles per SM sub-partition); the roofline denominator bench.py uses.
+//   * `measured` = the best of several register-only DFMA chain kernels (different chain counts / CTA shapes), so the gap
+//     between a real instruction stream and the pipe rate is visible (round 1's single shape read 92 % of `pipe`).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -9,48 +15,114 @@
 
 namespace {
 
-__global__ void __launch_bounds__(512) dfma_peak_kernel(double* out, int iters, double a, double b) {
-    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+// NCH independent chains per thread, two alternating multipliers; every shape below keeps ALL its CTAs resident at once
+// (registers: 2 NCH + ~10), so block 0's clock64 span is the span of the launch.
+template <int NCH>
+__global__ void dfma_peak_kernel(double* out, long long* clk, int iters, double a, double b) {
+    double x[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) x[c] = threadIdx.x * 1e-3 + c;
+    const double a2 = a - 1e-9;
+    const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        for (int u = 0; u < 128 / NCH; ++u) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) x[c] = fma(x[c], (c & 1) ? a2 : a, b);
         }
     }
-    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    const long long t1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) s += x[c];
     if (s == 123.456) out[0] = s;  // keep the chains alive without a store in the common case
+    if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = t1 - t0;
+}
+
+struct Shape {
+    int nch, block, ctas_per_sm;
+};
+
+template <int NCH>
+cudaError_t run_shape(int grid, int block, double* d, long long* clk, int iters) {
+    dfma_peak_kernel<NCH><<<grid, block>>>(d, clk, iters, 0.999999, 1e-7);
+    return cudaGetLastError();
+}
+
+cudaError_t launch(const Shape& s, int sms, double* d, long long* clk, int iters) {
+    const int grid = sms * s.ctas_per_sm;
+    switch (s.nch) {
+    case 4: return run_shape<4>(grid, s.block, d, clk, iters);
+    case 8: return run_shape<8>(grid, s.block, d, clk, iters);
+    default: return run_shape<16>(grid, s.block, d, clk, iters);
+    }
 }
 
 }  // namespace
 
-extern "C" int32_t vpmb200_measure_fp64_peak(int32_t device, int32_t iters, int32_t repeats, double* tflops, double* ms) {
-    if (!tflops || iters <= 0 || repeats <= 0) return VPMB200_EINVAL;
+extern "C" int32_t vpmb200_measure_fp64_peak2(int32_t device, int32_t iters, int32_t repeats, double* out8) {
+    if (!out8 || iters <= 0 || repeats <= 0) return VPMB200_EINVAL;
     if (cudaSetDevice(device) != cudaSuccess) return VPMB200_ENODEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VPMB200_ECUDA;
     double* d = nullptr;
+    long long* clk = nullptr;
     if (cudaMalloc(&d, 64) != cudaSuccess) return VPMB200_ECUDA;
+    if (cudaMalloc(&clk, 64) != cudaSuccess) { cudaFree(d); return VPMB200_ECUDA; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int grid = prop.multiProcessorCount * 4, block = 512;
-    dfma_peak_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-7);  // warm-up
-    double best = 1e30;
-    for (int r = 0; r < repeats; ++r) {
-        cudaEventRecord(e0);
-        dfma_peak_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-7);
-        cudaEventRecord(e1);
-        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return VPMB200_ECUDA; }
-        float t = 0;
-        cudaEventElapsedTime(&t, e0, e1);
-        if (t < best) best = t;
+    // 8 chains x 16 warps/scheduler (round 1's shape), 16 chains x 8 warps, 4 chains x 16 warps, 8 chains x 8 warps
+    const Shape shapes[4] = {{8, 512, 4}, {16, 256, 4}, {4, 512, 4}, {8, 256, 4}};
+    double best_tf = 0.0, best_ms = 0.0, best_mhz = 0.0;
+    int best_shape = -1;
+    for (int k = 0; k < 4; ++k) {
+        const Shape& s = shapes[k];
+        if (launch(s, prop.multiProcessorCount, d, clk, iters) != cudaSuccess) continue;   // warm-up
+        cudaDeviceSynchronize();
+        for (int r = 0; r < repeats; ++r) {
+            cudaEventRecord(e0);
+            launch(s, prop.multiProcessorCount, d, clk, iters);
+            cudaEventRecord(e1);
+            if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); cudaFree(clk); return VPMB200_ECUDA; }
+            float t = 0;
+            cudaEventElapsedTime(&t, e0, e1);
+            long long cyc = 0;
+            cudaMemcpy(&cyc, clk, sizeof(cyc), cudaMemcpyDeviceToHost);
+            const double flops = 2.0 * 128.0 * (double)iters * (double)prop.multiProcessorCount * s.ctas_per_sm * s.block;
+            const double tf = flops / (t * 1e-3) / 1e12;
+            if (tf > best_tf) {
+                best_tf = tf;
+                best_ms = t;
+                best_shape = k;
+                // block 0 runs for (almost) the whole launch: its cycle count over the event span is the SM clock under this load
+                best_mhz = (double)cyc / (t * 1e-3) / 1e6;
+            }
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(d);
-    double flops = 2.0 * 8 * 16 * (double)iters * (double)grid * block;
-    *tflops = flops / (best * 1e-3) / 1e12;
-    if (ms) *ms = best;
+    cudaFree(clk);
+    if (best_shape < 0) return VPMB200_ECUDA;
+    const double pipe_tf = (double)prop.multiProcessorCount * 64.0 * 2.0 * best_mhz * 1e6 / 1e12;
+    out8[0] = best_tf;                 // best measured DFMA throughput, TFLOP/s
+    out8[1] = best_ms;                 // its launch time
+    out8[2] = best_mhz;                // SM clock during that launch, from clock64 / event time (lower bound: launch ramp)
+    out8[3] = pipe_tf;                 // SMs x 64 lanes x 2 x that clock
+    out8[4] = pipe_tf > 0 ? best_tf / pipe_tf : 0.0;
+    out8[5] = (double)best_shape;      // index into {8ch x 512 x 4, 16ch x 256 x 4, 4ch x 512 x 4, 8ch x 256 x 4}
+    out8[6] = (double)prop.multiProcessorCount;
+    out8[7] = (double)prop.clockRate * 1e-3;   // the driver's nominal max SM clock, MHz
+    return VPMB200_OK;
+}
+
+extern "C" int32_t vpmb200_measure_fp64_peak(int32_t device, int32_t iters, int32_t repeats, double* tflops, double* ms) {
+    if (!tflops) return VPMB200_EINVAL;
+    double o[8];
+    int32_t rc = vpmb200_measure_fp64_peak2(device, iters, repeats, o);
+    if (rc) return rc;
+    *tflops = o[0];
+    if (ms) *ms = o[1];
     return VPMB200_OK;
 }

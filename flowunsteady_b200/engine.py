@@ -223,6 +223,14 @@ class Engine:
         self._check(self._L.vpmb200_fmm_stats(self._h, a))
         return dict(zip(("cells", "leaves", "levels", "m2l_pairs", "p2p_pairs"), [int(v) for v in a]))
 
+    def direct_tile_stats(self) -> dict:
+        """(target block, source tile) classification of the direct path for the current field (instrumentation)."""
+        a = (C.c_int64 * 4)()
+        self._check(self._L.vpmb200_direct_tile_stats(self._h, a))
+        d = dict(zip(("target_blocks", "source_tiles", "far_pairs", "all_pairs"), [int(v) for v in a]))
+        d["tile_far_fraction"] = d["far_pairs"] / d["all_pairs"] if d["all_pairs"] else 0.0
+        return d
+
     @property
     def launch_count(self) -> int:
         c = C.c_uint64()

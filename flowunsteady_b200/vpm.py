@@ -346,8 +346,9 @@ class ParticleField:
         self.fmm = FMM() if fmm is None else fmm
         self.sync = sync
         self._engine = Engine(self.maxparticles, float_bits=32 if R is np.float32 else 64, device=device)
-        self._host_dirty = True     # host matrix holds changes the device has not seen
+        self._host_dirty = True     # host matrix holds changes (to rows the device already has) the device has not seen
         self._dev_dirty = 0         # field-group mask the device holds newer than the host
+        self._dev_np = 0            # particles the device holds; rows [_dev_np, np) are host-side appends not yet sent
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.h2d_seconds = 0.0      # wall time inside upload calls
@@ -402,13 +403,37 @@ class ParticleField:
         """Tell the field that `particles` was modified on the host."""
         self._host_dirty = True
 
+    def _device_is_truth(self) -> bool:
+        """Lazy mode with nothing pending on the host side for the rows the device holds: rows [0, _dev_np) live on the GPU
+        and the host copy of the `_dev_dirty` groups is stale until `pull()`."""
+        return self.sync == "lazy" and not self._host_dirty
+
+    def _flush_appends(self):
+        """Send the particles appended on the host since the last call (vpm.add_particle) — only those rows cross the bus."""
+        if self.np > self._dev_np:
+            t0 = time.perf_counter()
+            self._engine.add_particles(self.particles[self._dev_np:self.np])
+            self.h2d_seconds += time.perf_counter() - t0
+            self.h2d_bytes += (self.np - self._dev_np) * 8 * NFIELDS
+            self._dev_np = self.np
+
     def _push(self, mask: int = _E.FM_ALL):
         if self.sync == "always" or self._host_dirty:
+            if self.sync == "lazy" and self._dev_dirty:
+                # the host copy of the device-newer groups is stale: they must not go back up (ADVICE r1: a shed between two
+                # lazy steps used to overwrite X/Gamma/sigma with the previous step's values)
+                mask &= ~self._dev_dirty
+                if self._dev_np < self.np:       # rows the device never saw need every group
+                    self.pull()
+                    mask = _E.FM_ALL
             t0 = time.perf_counter()
             self._engine.upload(self.particles, self.np, mask)     # returns after the copy (borrowed pointer)
             self.h2d_seconds += time.perf_counter() - t0
             self.h2d_bytes += self.np * 8 * _rows(mask)            # exactly what crosses the bus (selected column runs)
             self._host_dirty = False
+            self._dev_np = self.np
+        else:
+            self._flush_appends()
         self._engine.set_time(self.t, self.nt)
 
     def _pulled(self, mask: int):
@@ -420,11 +445,12 @@ class ParticleField:
     def pull(self, mask: Optional[int] = None):
         """Bring device results back into `particles`."""
         mask = self._dev_dirty if mask is None else mask
-        if mask and self.np > 0:
+        n = min(self.np, self._dev_np)      # rows [_dev_np, np) are host-side appends the device has not seen yet
+        if mask and n > 0:
             t0 = time.perf_counter()
-            self._engine.download(self.particles, self.np, mask)   # waits for the step, then copies
+            self._engine.download(self.particles, n, mask)         # waits for the step, then copies
             self.d2h_seconds += time.perf_counter() - t0
-            self.d2h_bytes += self.np * 8 * _rows(mask)
+            self.d2h_bytes += n * 8 * _rows(mask)
         self._dev_dirty &= ~mask
 
     # ---- hot-path entry points (called by the scheme objects) -----------------------------------------------------
@@ -461,7 +487,7 @@ class ParticleField:
             return 0
         self._push(_E.FM_ALL)
         removed = self._engine.remove_where(criterion, params)
-        self.np = self._engine.np
+        self.np = self._dev_np = self._engine.np
         if removed:
             self._pulled(_E.FM_ALL)
         return removed
@@ -564,19 +590,29 @@ def add_particle(pfield: ParticleField, X, Gamma=None, sigma=None, *, vol=0.0, c
         col[C_INDEX] = C
         col[STATIC_INDEX] = 1.0 if static else 0.0
     pfield.np += 1
-    pfield.mark_dirty()
+    if not pfield._device_is_truth():
+        pfield.mark_dirty()
+    # lazy + device-resident field: the new row is a pending append (rows [_dev_np, np)); the next hot-path call sends
+    # exactly those rows through vpmb200_add_particles and leaves the device-newer rows alone
 
 
 def remove_particle(pfield: ParticleField, i: int):
     """vpm.remove_particle(pfield, i): the last particle is moved into slot i (0-based here)."""
     if i < 0 or i >= pfield.np:
         raise IndexError(f"Requested removal of invalid particle index {i}")
-    if pfield._dev_dirty:
+    if pfield._device_is_truth():
+        # same swap-remove on both sides; the host copy of the device-newer groups stays stale until pull()
+        pfield._flush_appends()
+        pfield._engine.remove_particle(i)
+        pfield._dev_np -= 1
+    elif pfield._dev_dirty:
         pfield.pull()
+        pfield.mark_dirty()
+    else:
+        pfield.mark_dirty()
     if i != pfield.np - 1:
         pfield.particles[i] = pfield.particles[pfield.np - 1]
     pfield.np -= 1
-    pfield.mark_dirty()
 
 
 def _reset_particles(pfield: ParticleField):
@@ -584,12 +620,22 @@ def _reset_particles(pfield: ParticleField):
     pfield.particles[:pfield.np, U_INDEX] = 0.0
     pfield.particles[:pfield.np, J_INDEX] = 0.0
     pfield.particles[:pfield.np, PSE_INDEX] = 0.0
-    pfield.mark_dirty()
+    if pfield._device_is_truth():
+        pfield._flush_appends()
+        pfield._engine.reset_particles()
+        pfield._dev_dirty &= ~(_E.FM_U | _E.FM_J | _E.FM_PSE)     # both sides hold zeros now
+    else:
+        pfield.mark_dirty()
 
 
 def _reset_particles_sfs(pfield: ParticleField):
     pfield.particles[:pfield.np, SFS_INDEX] = 0.0
-    pfield.mark_dirty()
+    if pfield._device_is_truth():
+        pfield._flush_appends()
+        pfield._engine.reset_particles_sfs()
+        pfield._dev_dirty &= ~_E.FM_SFS
+    else:
+        pfield.mark_dirty()
 
 
 def nextstep(pfield: ParticleField, dt: float, relax: bool = False, custom_UJ=None):
@@ -661,6 +707,11 @@ def read_(pfield, h5_fname: str, path: str = "", overwrite: bool = True, load_ti
     from . import h5min
     d = h5min.read(os.path.join(path, h5_fname))
     n = int(d["np"])
+    if getattr(pfield, "_dev_dirty", 0):
+        if overwrite:
+            pfield._dev_dirty = 0          # the device's results are discarded with the particles
+        else:
+            pfield.pull()                  # keep the device-newer rows of the particles that stay
     if overwrite:
         pfield.np = 0
     if pfield.np + n > pfield.maxparticles:

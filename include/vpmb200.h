@@ -220,6 +220,11 @@ int32_t vpmb200_stream(vpmb200_handle h, void** stream);
 int32_t vpmb200_set_option(vpmb200_handle h, const char* name, int64_t value);
 /* Tree statistics of the last UJ_fmm evaluation: stats[0..4] = cells, leaves, levels, M2L pairs, P2P (leaf) pairs. */
 int32_t vpmb200_fmm_stats(vpmb200_handle h, int64_t* stats);
+/* Instrumentation of the DIRECT path for the current field (what bench.py reports as `tile_far_fraction`): stats[0] = target
+ * blocks (256 targets each), stats[1] = source tiles (256 sources each), stats[2] = (block, tile) pairs whose boxes are
+ * farther apart than the tile's T_FAR sigma_max (K1 runs its branch-free singular loop on them, K2 skips them),
+ * stats[3] = all (block, tile) pairs.  Uses the same ordering (direct_sort) and boxes as vpmb200_uj. */
+int32_t vpmb200_direct_tile_stats(vpmb200_handle h, int64_t* stats);
 /* Number of CUDA kernels this handle has enqueued since creation (bench.py reports the per-step delta). */
 int32_t vpmb200_launch_count(vpmb200_handle h, uint64_t* count);
 /* Block the host until all enqueued work on the handle has finished. */
@@ -264,6 +269,11 @@ int32_t vpmb200_stage(vpmb200_handle h, int32_t stage, double a, double b, doubl
  * kernel, `iters` x 128 FMAs per thread).  bench.py uses it as the roofline denominator of the FP64-bound pair
  * kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int32_t vpmb200_measure_fp64_peak(int32_t device, int32_t iters, int32_t repeats, double* tflops, double* ms);
+/* The same with its evidence: out8 = { best measured DFMA TFLOP/s over several chain/CTA shapes, its launch ms, the SM clock
+ * (MHz) during that launch derived from the kernel's own clock64() span over the CUDA-event span, the FP64 PIPE rate
+ * SMs x 64 lanes x 2 flop x that clock (what ncu's sm__inst_executed_pipe_fp64 counts against; bench.py's roofline
+ * denominator), measured / pipe, index of the best shape, SM count, the driver's nominal max SM clock (MHz) }. */
+int32_t vpmb200_measure_fp64_peak2(int32_t device, int32_t iters, int32_t repeats, double* out8);
 
 /* Library identification. */
 const char* vpmb200_version(void);

@@ -1,0 +1,116 @@
+"""Parity at the sizes BASELINE.json names, where the tile-level shortcuts actually fire.
+
+The small-N tests (tests/test_gpu_step.py) use clouds whose sigma spans the whole box, so K2's T_FAR tile skip, K1's all-far
+tiles and the FP32 far path never run there.  Here the fields are the wake geometries of the BASELINE configurations:
+rotor-hover stand-in at N = 70,000 (configs[1]) — every target of one RK3 + DynamicSFS step against the oracle — and the
+vortex-ring field at N = 1,000,000 (configs[2]) — 2048 sampled targets of U, J and E_str against oracle slabs.
+Tolerances: 1e-12 U/J (north_star), 1e-11 E_str, 1e-9 for what passes through the dynamic procedure.
+"""
+import numpy as np
+import pytest
+
+from tests.util import relmax
+
+pytestmark = pytest.mark.gpu
+
+DYN = dict(kernel="gaussianerf", integration="rungekutta3", relaxation="pedrizzetti", sfs="dynamic", alpha=0.999,
+           force_positive=1, clippings=1)
+
+
+def _sample(n, m=2048):
+    return np.sort(np.random.default_rng(1234).choice(n, m, replace=False))
+
+
+def _estr_sampled(o, P, idx, transposed=1):
+    """Oracle E_str at the sampled targets, fed with the J the device produced for ALL particles (J's own parity is asserted
+    on the same sample)."""
+    X, G, S = (np.ascontiguousarray(P[:, 0:3]), np.ascontiguousarray(P[:, 3:6]), np.ascontiguousarray(P[:, 6]))
+    J = np.ascontiguousarray(P[:, 15:24])
+    return o.estr_direct("gaussianerf", transposed, X, G, S, J, X[idx], J[idx], accum=1)
+
+
+def test_tile_skip_fires_on_wake_fields():
+    """The premise of this file: on the wake geometries most (block, tile) pairs ARE beyond T_FAR, on the unit-cube cloud of
+    the small tests none is."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    from tests.util import mixed_field
+    for (x, g, s), lo, hi in ((fields.rotor_wake(70_000), 0.2, 1.0), (fields.vortex_rings(200_000), 0.5, 1.0),
+                              (mixed_field(1500, seed=5)[:3], 0.0, 0.0)):
+        with fb.Engine(x.shape[0], schemes=fb.default_schemes()) as eng:
+            eng.upload(fb.new_particles(x, g, s))
+            st = eng.direct_tile_stats()
+        assert st["all_pairs"] == st["target_blocks"] * st["source_tiles"]
+        assert lo <= st["tile_far_fraction"] <= hi, st
+
+
+def test_rotor70k_uj_estr_sampled_parity():
+    """configs[1] geometry, N = 70k: U, J, E_str of `pfield.UJ(pfield; sfs=true)` at 2048 targets vs the oracle (FP64)."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    from oracle import oracle as o
+    x, g, s = fields.rotor_wake(70_000)
+    P = fb.new_particles(x, g, s)
+    with fb.Engine(P.shape[0], schemes=fb.default_schemes(**DYN)) as eng:
+        eng.upload(P)
+        eng.uj(True, True, True)
+        Pg = eng.download(np.zeros_like(P))
+    idx = _sample(P.shape[0])
+    Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x[idx], accum=1)
+    assert relmax(Pg[idx, 9:12], Uo) < 1e-12
+    assert relmax(Pg[idx, 15:24], Jo) < 1e-12
+    assert relmax(Pg[idx, 39:42], _estr_sampled(o, Pg, idx)) < 1e-11
+
+
+def test_rotor70k_nextstep_dynamic_sfs_full_parity():
+    """One whole RK3 + DynamicSFS (alpha = 0.999, pseudo3level_positive, backscatter clipping) + pedrizzetti step on the
+    rotor-hover stand-in at N = 70k (rotorhover.jl:53-55): EVERY particle's X, Gamma, sigma, C, U, J against the oracle's
+    step (5 U/J + 4 E_str full N^2 evaluations on the host: about a minute on 16 cores)."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    from oracle import oracle as o
+    x, g, s = fields.rotor_wake(70_000)
+    P = fb.new_particles(x, fields.floor_gamma(g), s)
+    dt, Uinf = 1e-4, (0.0, 0.0, -1.0)
+    Po = P.copy()
+    o.nextstep(Po, o.default_schemes(**DYN), dt, Uinf, relax=True)
+    with fb.Engine(P.shape[0], schemes=fb.default_schemes(**DYN)) as eng:
+        eng.upload(P)
+        eng.nextstep(dt, Uinf, relax=True)
+        Pg = eng.download(np.zeros_like(P))
+    assert relmax(Pg[:, 0:3], Po[:, 0:3]) < 1e-12
+    assert relmax(Pg[:, 9:12], Po[:, 9:12]) < 1e-11
+    assert relmax(Pg[:, 15:24], Po[:, 15:24]) < 1e-11
+    for sl in (slice(3, 6), slice(6, 7), slice(36, 39)):      # through the dynamic procedure: 1/(1 - alpha) amplification
+        assert relmax(Pg[:, sl], Po[:, sl]) < 1e-9
+    assert np.abs(Po[:, 36]).max() > 0                        # the coefficient is active on this field
+
+
+def test_rings1m_uj_estr_sampled_parity_fp64_and_fp32():
+    """configs[2] at full size: `pfield.UJ(pfield; sfs=true)` on 10^6 vortex-ring particles; 2048 sampled targets of U, J,
+    E_str vs oracle slabs over all 10^6 sources.  Then the FP32 variant (vpm_floattype = Float32) on the same field, whose
+    far path only runs at sizes like this one."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import engine as E, fields
+    from oracle import oracle as o
+    x, g, s = fields.vortex_rings(1_000_000)
+    P = fb.new_particles(x, g, s)
+    idx = _sample(P.shape[0])
+    Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x[idx], accum=1)
+    mask = E.FM_X | E.FM_GAMMA | E.FM_SIGMA | E.FM_U | E.FM_J | E.FM_SFS
+    with fb.Engine(P.shape[0], schemes=fb.default_schemes(**DYN)) as eng:
+        eng.upload(P)
+        eng.uj(True, True, True)
+        Pg = eng.download(np.zeros_like(P), field_mask=mask)
+        st = eng.direct_tile_stats()
+    assert st["tile_far_fraction"] > 0.8
+    assert relmax(Pg[idx, 9:12], Uo) < 1e-12
+    assert relmax(Pg[idx, 15:24], Jo) < 1e-12
+    assert relmax(Pg[idx, 39:42], _estr_sampled(o, Pg, idx)) < 1e-11
+    with fb.Engine(P.shape[0], float_bits=32, schemes=fb.default_schemes(**DYN)) as eng:
+        eng.upload(P)
+        eng.uj(True, True, True)
+        P32 = eng.download(np.zeros_like(P), field_mask=mask)
+    assert relmax(P32[idx, 9:12], Uo) < 2e-5
+    assert relmax(P32[idx, 15:24], Jo) < 4e-4
+    assert relmax(P32[idx, 39:42], Pg[idx, 39:42]) < 4e-3     # E_str from FP32 J: differences of J lose a further digit

@@ -140,6 +140,40 @@ def test_lazy_sync_keeps_field_on_device():
     assert np.array_equal(outs[0], outs[1])
 
 
+def test_lazy_sync_with_shedding_and_removal_between_steps():
+    """sync='lazy' + vpm.add_particle / remove_particle / _reset_particles between steps.  The appended
+    rows alone cross the bus (vpmb200_add_particles); the device-newer X / Gamma / sigma of the previous step must survive
+    (they used to be overwritten by the stale host copy).  Same bits as sync='always'."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import vpm
+    from tests.util import mixed_field
+    x, g, s, _ = mixed_field(900, seed=4)
+    g = 50 * g + 1e-12
+    outs, traffic = [], []
+    for mode in ("always", "lazy"):
+        pf = vpm.ParticleField(1000, UJ=vpm.UJ_direct, SFS=vpm.SFS_Cd_twolevel_nobackscatter, sync=mode)
+        for i in range(600):
+            vpm.add_particle(pf, x[i], g[i], s[i], vol=1e-3, circulation=1.0)
+        for k in range(3):
+            vpm.nextstep(pf, 2e-3, relax=True)
+            for i in range(600 + 100 * k, 700 + 100 * k):         # shed 100 particles (simulation.jl:363)
+                vpm.add_particle(pf, x[i], g[i], s[i], vol=1e-3, circulation=1.0)
+            vpm.remove_particle(pf, 17 + k)                       # a wake treatment removing one particle
+            vpm.remove_particle(pf, pf.np - 1)
+            if k == 1:
+                vpm._reset_particles(pf)
+        vpm.nextstep(pf, 2e-3, relax=True)
+        if mode == "lazy":
+            # one full upload of the first 600 rows, then only the appended rows
+            assert pf.h2d_bytes == 600 * 8 * 22 + 3 * 100 * 8 * 43
+            pf.pull()
+        outs.append(pf.particles[:pf.np].copy())
+        traffic.append(pf.h2d_bytes)
+    assert outs[0].shape == outs[1].shape == (896, 43)
+    assert np.array_equal(outs[0], outs[1])
+    assert traffic[1] < traffic[0] / 3
+
+
 def test_page_locked_host_matrix_gives_the_same_field():
     """pinned=True page-locks `pfield.particles` in place through the ABI (vpmb200_host_register — what the Julia stub
     does with the reference's matrix): same bits as the pageable matrix, registering twice is harmless, and the lock is
