@@ -15,6 +15,7 @@
 #include "estr_direct.cuh"
 #include "field_kernels.cuh"
 #include "fmm_host.cuh"
+#include "fmm_let.cuh"
 #include "uj_direct.cuh"
 #include "uj_direct_f32.cuh"
 
@@ -44,6 +45,7 @@ struct vpmb200_engine {
     double t = 0.0;
     int64_t nt = 0;
     FmmWorkspace fmm;           // GPU FMM scratch (allocated on first UJ_fmm call)
+    FmmLet let;                 // multi-GPU UJ_fmm: local-essential-tree phases (fmm_let.cuh)
     std::vector<int> fmm_lvl;   // cell index range of every tree level
     // DynamicSFS evaluates twice at the SAME positions and strengths (test filter sigma*alpha, then domain filter): the
     // second evaluation reuses the tree, the interaction lists and the local expansions of the first (the far field is
@@ -810,6 +812,7 @@ int32_t vpmb200_destroy(vpmb200_handle e) {
     cudaFree(e->partial);
     cudaFree(e->counter);
     fmm_free(e->fmm);
+    let_free(e->let);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return VPMB200_OK;
@@ -1199,6 +1202,159 @@ int32_t vpmb200_fmm_global(vpmb200_handle e, double* G, int64_t ldg, int64_t nto
         return fail(e, VPMB200_EINVAL, "bad fmm_global arguments");
     CU_TRY(e, cudaSetDevice(e->device));
     return do_fmm_global(e, G, ldg, ntot, part, nparts, pass);
+}
+
+// ---- multi-GPU UJ_fmm: local-essential-tree phases (fmm_let.cuh; the collectives between them are the caller's) ----------
+#define LET_TRY(e, call)                                                                         \
+    do {                                                                                         \
+        std::string _err;                                                                        \
+        auto _f = [&](std::string& err) -> cudaError_t { return (call); };                       \
+        cudaError_t _st = _f(_err);                                                              \
+        if (_st != cudaSuccess)                                                                  \
+            return fail((e), _st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, \
+                        _err.empty() ? std::string(cudaGetErrorString(_st)) : _err);             \
+    } while (0)
+
+int32_t vpmb200_let_cell_bytes(void) { return (int32_t)sizeof(FmmCell); }
+
+int32_t vpmb200_let_bounds(vpmb200_handle e, double* lohi6) {
+    CHECK_HANDLE(e);
+    if (!lohi6) return fail(e, VPMB200_EINVAL, "lohi is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    int32_t rc = check_fmm_settings(e);
+    if (rc) return rc;
+    if (e->np > 2000000000LL) return fail(e, VPMB200_ECAPACITY, "UJ_fmm indexes particles with 32-bit integers");
+    e->shard_sorted_np = -1;
+    LET_TRY(e, let_bounds(e->fmm, e->state, e->ld, e->np, lohi6, e->stream, e->launches, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_keys(vpmb200_handle e, const double* lohi6_global, int32_t Lc, void** hist_dev, void** binmax_dev) {
+    CHECK_HANDLE(e);
+    if (!lohi6_global || Lc < 1 || Lc > LET_MAX_LC) return fail(e, VPMB200_EINVAL, "let_keys: bad arguments (1 <= Lc <= 6)");
+    CU_TRY(e, cudaSetDevice(e->device));
+    FmmRoot cube;
+    if (!let_cube_from_bounds(lohi6_global, &cube)) return fail(e, VPMB200_EINVAL, "particle positions are not finite");
+    LET_TRY(e, let_keys(e->fmm, e->let, e->state, e->ld, e->np, cube, Lc, e->sch.fmm_nonzero_sigma != 0, e->stream, e->launches, err));
+    if (hist_dev) *hist_dev = e->let.hist;
+    if (binmax_dev) *binmax_dev = e->sch.fmm_nonzero_sigma ? (void*)e->let.binmax : nullptr;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_partition(vpmb200_handle e, int32_t nparts, int32_t part, int64_t* send_counts) {
+    CHECK_HANDLE(e);
+    if (nparts < 1 || part < 0 || part >= nparts || !send_counts) return fail(e, VPMB200_EINVAL, "let_partition: bad arguments");
+    if (!e->let.hist) return fail(e, VPMB200_EINVAL, "let_partition needs let_keys first");
+    CU_TRY(e, cudaSetDevice(e->device));
+    LET_TRY(e, let_partition(e->let, nparts, part, e->sch.fmm_ncrit, send_counts, e->stream, e->launches, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_pack(vpmb200_handle e, double* rows) {
+    CHECK_HANDLE(e);
+    if (e->np > 0 && !rows) return fail(e, VPMB200_EINVAL, "rows is NULL");
+    if (e->let.n_home != e->np) return fail(e, VPMB200_EINVAL, "let_pack needs let_keys of the current particles first");
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (e->np > 0) {
+        let_pack_rows_kernel<<<blocks_for(e->np, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, e->let.hperm, rows);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_build(vpmb200_handle e, const double* rows, int64_t n_own, int64_t n_all, int32_t reuse, int64_t* info4) {
+    CHECK_HANDLE(e);
+    if (n_own < 0 || n_all < n_own || (n_own > 0 && !rows)) return fail(e, VPMB200_EINVAL, "let_build: bad arguments");
+    if (n_all > 2000000000LL) return fail(e, VPMB200_ECAPACITY, "UJ_fmm indexes particles with 32-bit integers");
+    CU_TRY(e, cudaSetDevice(e->device));
+    int32_t rc = check_fmm_settings(e);
+    if (rc) return rc;
+    const vpmb200_schemes& s = e->sch;
+    LET_TRY(e, let_build(e->fmm, e->let, rows, n_own, n_all, s.fmm_ncrit, s.fmm_nonzero_sigma ? 5.0 : 0.0, s.fmm_p, reuse != 0,
+                         e->stream, e->launches, err));
+    if (info4) {
+        info4[0] = e->let.ncells_own;
+        info4[1] = e->fmm.nleaves;
+        info4[2] = 3 * let_nm(s.fmm_p);
+        info4[3] = e->let.n_own;
+    }
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_ptrs(vpmb200_handle e, void** ptrs3) {
+    CHECK_HANDLE(e);
+    if (!ptrs3) return fail(e, VPMB200_EINVAL, "ptrs is NULL");
+    ptrs3[0] = e->fmm.cells;
+    ptrs3[1] = e->fmm.M;
+    ptrs3[2] = e->fmm.rec;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_attach_tree(vpmb200_handle e, const void* cells_recv, const double* M_recv, int64_t slot_cells,
+                                const int64_t* ncells, const int64_t* nparticles) {
+    CHECK_HANDLE(e);
+    if (!ncells || !nparticles || slot_cells < 0) return fail(e, VPMB200_EINVAL, "let_attach_tree: bad arguments");
+    CU_TRY(e, cudaSetDevice(e->device));
+    LET_TRY(e, let_attach_tree(e->fmm, e->let, static_cast<const FmmCell*>(cells_recv), M_recv, slot_cells, ncells, nparticles,
+                               e->stream, e->launches, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_attach_records(vpmb200_handle e, const double* rec_recv, int64_t slot_n, const int64_t* nparticles) {
+    CHECK_HANDLE(e);
+    if (!nparticles || slot_n < 0) return fail(e, VPMB200_EINVAL, "let_attach_records: bad arguments");
+    if ((int)e->let.part_off.size() != e->let.nparts) return fail(e, VPMB200_EINVAL, "let_attach_records needs let_attach_tree first");
+    CU_TRY(e, cudaSetDevice(e->device));
+    LET_TRY(e, let_attach_records(e->fmm, e->let, rec_recv, slot_n, nparticles, e->stream, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_evaluate(vpmb200_handle e, double* out_rows, int32_t reuse) {
+    CHECK_HANDLE(e);
+    if (e->let.n_own > 0 && !out_rows) return fail(e, VPMB200_EINVAL, "out_rows is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    const vpmb200_schemes& s = e->sch;
+    if (reuse && (s.fmm_nonzero_sigma || !e->let.far_valid)) return fail(e, VPMB200_EINVAL, "let_evaluate: nothing to reuse");
+    LET_TRY(e, let_evaluate(e->fmm, e->let, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, s.kernel, e->fmm_table_copies, e->gh_table,
+                            out_rows, reuse != 0, e->stream, e->launches, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_estr_records(vpmb200_handle e) {
+    CHECK_HANDLE(e);
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, let_estr_records(e->fmm, e->let, e->sch.transposed, zeta0_of(e->sch.kernel), e->stream, e->launches));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_estr_evaluate(vpmb200_handle e, double* out_rows) {
+    CHECK_HANDLE(e);
+    if (e->let.n_own > 0 && !out_rows) return fail(e, VPMB200_EINVAL, "out_rows is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    LET_TRY(e, let_estr_evaluate(e->fmm, e->let, e->sch.kernel, e->fmm_table_copies, e->sch.transposed, e->z_table, out_rows,
+                                 e->stream, e->launches, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_finish(vpmb200_handle e, const double* res_rows, int32_t what, int32_t reset) {
+    CHECK_HANDLE(e);
+    if (what != 0 && what != 1) return fail(e, VPMB200_EINVAL, "let_finish: what must be 0 (U, J) or 1 (E_str)");
+    if (e->np > 0 && !res_rows) return fail(e, VPMB200_EINVAL, "res_rows is NULL");
+    if (e->let.n_home != e->np) return fail(e, VPMB200_EINVAL, "let_finish: the particle count changed since let_keys");
+    CU_TRY(e, cudaSetDevice(e->device));
+    int32_t rc;
+    if (what == 0 && reset && (rc = zero_rows(e, F_PSE, 3))) return rc;
+    if (e->np <= 0) return VPMB200_OK;
+    if (what == 0)
+        let_finish_kernel<<<blocks_for(e->np, PK_BT), PK_BT, 0, e->stream>>>(res_rows, 12, e->np, e->let.hperm, e->state, e->ld, F_U, 3,
+                                                                           F_J, 9, reset ? 0 : 1);
+    else
+        let_finish_kernel<<<blocks_for(e->np, PK_BT), PK_BT, 0, e->stream>>>(res_rows, 3, e->np, e->let.hperm, e->state, e->ld, F_SFS, 3,
+                                                                           F_SFS, 0, 1);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    return VPMB200_OK;
 }
 
 int32_t vpmb200_set_option(vpmb200_handle e, const char* name, int64_t value) {

@@ -150,14 +150,30 @@ __device__ __forceinline__ int lower_bound_key(const uint64_t* __restrict__ keys
     return lo;
 }
 
+// Is this cell split?  Single GPU: more than ncrit particles.  Local essential tree (fmm_let.cuh): the cells above level
+// `Lc` belong to the GLOBAL tree's top, which is split by the GLOBAL particle count — `hpre` is the exclusive prefix sum of
+// the all-reduced level-Lc histogram in Morton order, so a cell at level l with Morton prefix q holds
+// hpre[(q + 1) << 3 (Lc - l)] - hpre[q << 3 (Lc - l)] particles over all ranks — so that every rank's partial top tree has
+// exactly the structure of the one-GPU tree.
+__device__ __forceinline__ bool fmm_cell_splits(const FmmCell& cell, const uint64_t* __restrict__ keys, int ncrit,
+                                                const int* __restrict__ hpre, int Lc) {
+    if (cell.level >= FMM_MAXLEVEL) return false;
+    if (hpre != nullptr && cell.level < Lc) {
+        const uint64_t q = keys[cell.start] >> (3 * (FMM_MAXLEVEL - cell.level));
+        const int sh = 3 * (Lc - cell.level);
+        return hpre[(q + 1) << sh] - hpre[q << sh] > ncrit;
+    }
+    return cell.count > ncrit;
+}
+
 // For each cell of the level: number of non-empty children (0 if the cell is a leaf).
 __global__ void fmm_split_count_kernel(const FmmCell* __restrict__ cells, int c0, int c1, const uint64_t* __restrict__ keys,
-                                       int ncrit, int* __restrict__ nchild) {
+                                       int ncrit, int* __restrict__ nchild, const int* __restrict__ hpre = nullptr, int Lc = 0) {
     int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
     const FmmCell cell = cells[c];
     int nc = 0;
-    if (cell.count > ncrit && cell.level < FMM_MAXLEVEL) {
+    if (fmm_cell_splits(cell, keys, ncrit, hpre, Lc)) {
         const int shift = 3 * (FMM_MAXLEVEL - cell.level - 1);
         const uint64_t prefix = (keys[cell.start] >> (shift + 3)) << 3;
         int lo = cell.start;
@@ -172,11 +188,12 @@ __global__ void fmm_split_count_kernel(const FmmCell* __restrict__ cells, int c0
 }
 
 __global__ void fmm_split_emit_kernel(FmmCell* __restrict__ cells, int c0, int c1, const uint64_t* __restrict__ keys,
-                                      int ncrit, const int* __restrict__ child_off, int next0) {
+                                      int ncrit, const int* __restrict__ child_off, int next0,
+                                      const int* __restrict__ hpre = nullptr, int Lc = 0) {
     int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
     FmmCell cell = cells[c];
-    if (!(cell.count > ncrit && cell.level < FMM_MAXLEVEL)) {
+    if (!fmm_cell_splits(cell, keys, ncrit, hpre, Lc)) {
         cells[c].child0 = -1;
         cells[c].nchild = 0;
         return;

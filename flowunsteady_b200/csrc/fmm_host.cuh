@@ -36,6 +36,10 @@ struct FmmWorkspace {
     int leaf_lo = 0, leaf_hi = 0;   // leaves [leaf_lo, leaf_hi) are evaluated by the near-field / L2P kernels (multi-GPU split)
     unsigned int n_m2l = 0, n_p2p = 0;
     int sms = 0;                    // multiprocessors of the current device (grid of the persistent leaf kernels)
+    // local essential tree (fmm_let.cuh): when set, the downward pass and the leaf kernels read cells / multipoles from these
+    // combined arrays ([own | other ranks']) instead of w.cells / w.M; targets are always the own cells [0, ncells)
+    const FmmCell* cells_eval = nullptr;
+    const double* M_eval = nullptr;
 };
 
 // Grid of the persistent near-field kernels: as many CTAs as are resident at once (occupancy of `kfn` x SMs), fewer when
@@ -206,11 +210,13 @@ struct FmmPasses {
         const size_t smem = sizeof(double) * 3 * Ops::NL * 32;
         if ((e = cudaFuncSetAttribute(fmm_m2l_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
             return e;
-        fmm_m2l_kernel<P><<<w.ncells, 32, smem, st>>>(w.cells, w.ncells, w.m2l_sorted, w.m2l_off, w.M, w.L);
+        const FmmCell* cells = w.cells_eval ? w.cells_eval : w.cells;
+        const double* M = w.M_eval ? w.M_eval : w.M;
+        fmm_m2l_kernel<P><<<w.ncells, 32, smem, st>>>(cells, w.ncells, w.m2l_sorted, w.m2l_off, M, w.L);
         ++launches;
         for (int l = 1; l + 1 < (int)lvl.size(); ++l) {
             const int c0 = lvl[l], c1 = lvl[l + 1];
-            fmm_l2l_kernel<P><<<((c1 - c0) * 3 + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.L);
+            fmm_l2l_kernel<P><<<((c1 - c0) * 3 + 127) / 128, 128, 0, st>>>(cells, c0, c1, w.L);
             ++launches;
         }
         return cudaGetLastError();
@@ -234,7 +240,7 @@ struct FmmPasses {
         int grid = 0;
         if ((e = fmm_leaf_grid(w, kfn, 32 * WARPS, smem, (nl + WARPS - 1) / WARPS, st, grid)) != cudaSuccess) return e;
         kfn<<<grid, 32 * WARPS, smem, st>>>(
-            w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
+            w.cells_eval ? w.cells_eval : w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
         ++launches;
         return cudaGetLastError();
     }
@@ -317,27 +323,18 @@ inline cudaError_t fmm_sort(FmmWorkspace& w, const double* soa, int64_t ld, int6
         FMM_TRY(call_with_tmp);                                              \
     } while (0)
 
-// Build the adaptive octree and the interaction lists for the particles of the field.
-inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, int ncrit, double theta,
-                             double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err,
-                             int part = 0, int nparts = 1) {
-    FMM_TRY(fmm_reserve_particles(w, n, err));
-    FmmRoot rt;
-    {
-        cudaError_t e0 = fmm_sort(w, soa, ld, n, st, launches, err, &rt);
-        if (e0 != cudaSuccess) return e0;
-    }
-    const double cx = rt.cx, cy = rt.cy, cz = rt.cz, side = rt.side;
-    const unsigned nbk = (unsigned)((n + 255) / 256);
-    fmm_gather_kernel<<<nbk, 256, 0, st>>>(soa, ld, n, w.perm, w.sx, w.sy, w.sz, w.rec);
-    ++launches;
-    // ---- tree, level by level; the cell arrays start from an estimate and the build restarts if they are too small
-    if (w.cap_cells == 0) FMM_TRY(fmm_reserve_cells(w, std::max<int64_t>(8192, 6 * n / std::max(ncrit, 1)), err));
+// The adaptive octree over the Morton-sorted keys in w.keys (n particles), level by level; fills w.cells, w.ncells, w.nlevels,
+// lvl (cell index range of every level) and the leaf list (w.leaves, w.nleaves).  hpre / Lc: fmm_cell_splits.
+inline cudaError_t fmm_tree(FmmWorkspace& w, int64_t n, int ncrit, const FmmRoot& rt, std::vector<int>& lvl, cudaStream_t st,
+                            uint64_t& launches, std::string& err, const int* hpre = nullptr, int Lc = 0) {
+    // the cell arrays start from an estimate and the build restarts if they are too small; the estimate follows the CURRENT
+    // particle count (a field that grew from a small first call must not rely on doublings alone)
+    FMM_TRY(fmm_reserve_cells(w, std::max<int64_t>(8192, 6 * n / std::max(ncrit, 1)), err));
     int ncells = 1;
     for (int attempt = 0;; ++attempt) {
         FmmCell root;
         root.start = 0; root.count = (int)n; root.parent = -1; root.child0 = -1; root.nchild = 0; root.level = 0;
-        root.cx = cx; root.cy = cy; root.cz = cz; root.R = 0.5 * side; root.smax = 0.0; root.pad_ = 0.0;
+        root.cx = rt.cx; root.cy = rt.cy; root.cz = rt.cz; root.R = 0.5 * rt.side; root.smax = 0.0; root.pad_ = 0.0;
         FMM_TRY(cudaMemcpyAsync(w.cells, &root, sizeof(root), cudaMemcpyHostToDevice, st));
         lvl.clear();
         lvl.push_back(0);
@@ -347,7 +344,7 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
         while (true) {
             const int c0 = lvl[lvl.size() - 2], c1 = lvl.back();
             const int nc = c1 - c0;
-            fmm_split_count_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.nchild);
+            fmm_split_count_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.nchild, hpre, Lc);
             FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, w.nchild, w.child_off, nc, st));
             int last_off = 0, last_n = 0;
             FMM_TRY(cudaMemcpyAsync(&last_off, w.child_off + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -359,14 +356,15 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
                 overflow = true;
                 break;
             }
-            fmm_split_emit_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.child_off, ncells);
+            fmm_split_emit_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.child_off, ncells, hpre, Lc);
             ++launches;
             if (nnew == 0) break;
             ncells += nnew;
             lvl.push_back(ncells);
         }
         if (!overflow) break;
-        if (attempt >= 8 || (int64_t)w.cap_cells * 2 > 2 * n + 64 * FMM_MAXLEVEL) {
+        // single-child chains are not compressed, so the only hard bound is one cell per particle per level
+        if (attempt >= 12 || (int64_t)w.cap_cells > n * (FMM_MAXLEVEL + 1) + 64) {
             err = "FMM: octree needs more cells than particles allow (corrupt positions?)";
             return cudaErrorMemoryAllocation;
         }
@@ -386,52 +384,41 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     w.nleaves = lp + lf;
     w.leaf_lo = 0;
     w.leaf_hi = w.nleaves;
-    const int* mine = nullptr;
-    if (nparts > 1) {
-        // leaves in Morton order; this rank takes the leaves covering particles [part, part + 1) * n / nparts of that order
-        // and marks them and their ancestors: only those target cells are traversed / receive M2L, L2L, L2P, P2P
-        fmm_leaf_starts_kernel<<<(w.nleaves + 255) / 256, 256, 0, st>>>(w.cells, w.leaves, w.nleaves, w.leaf_keys);
-        FMM_CUB(cub::DeviceRadixSort::SortPairs(tmp, tb, w.leaf_keys, w.leaf_keys_alt, w.leaves, w.leaves_alt, w.nleaves, 0, 32, st));
-        std::swap(w.leaf_keys, w.leaf_keys_alt);
-        std::swap(w.leaves, w.leaves_alt);
-        const int p_lo = (int)(n * part / nparts), p_hi = (int)(n * (part + 1) / nparts);
-        fmm_leaf_range_kernel<<<1, 32, 0, st>>>(w.leaf_keys, w.nleaves, p_lo, p_hi, w.leaf_flag);
-        int range[2] = {0, 0};
-        FMM_TRY(cudaMemcpyAsync(range, w.leaf_flag, sizeof(range), cudaMemcpyDeviceToHost, st));
-        FMM_TRY(cudaStreamSynchronize(st));
-        w.leaf_lo = range[0];
-        w.leaf_hi = part == nparts - 1 ? w.nleaves : range[1];
-        FMM_TRY(cudaMemsetAsync(w.mine, 0, sizeof(int) * ncells, st));
-        if (w.leaf_hi > w.leaf_lo)
-            fmm_flag_owned_kernel<<<(w.leaf_hi - w.leaf_lo + 255) / 256, 256, 0, st>>>(w.cells, w.leaves + w.leaf_lo, w.leaf_hi - w.leaf_lo, w.mine);
-        launches += 4;
-        mine = w.mine;
-    }
-    if (nzs_factor > 0.0) {   // largest core size per cell, leaves first then level by level upward
-        fmm_smax_leaf_kernel<<<(ncells + 127) / 128, 128, 0, st>>>(w.cells, ncells, w.rec);
+    return cudaSuccess;
+}
+
+// smax (largest core size per cell) of the cells in `cells`, leaves first then level by level upward.
+inline void fmm_smax(FmmWorkspace& w, FmmCell* cells, int ncells, const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches) {
+    fmm_smax_leaf_kernel<<<(ncells + 127) / 128, 128, 0, st>>>(cells, ncells, w.rec);
+    ++launches;
+    for (int l = (int)lvl.size() - 3; l >= 0; --l) {
+        fmm_smax_up_kernel<<<(lvl[l + 1] - lvl[l] + 127) / 128, 128, 0, st>>>(cells, lvl[l], lvl[l + 1]);
         ++launches;
-        for (int l = (int)lvl.size() - 3; l >= 0; --l) {
-            fmm_smax_up_kernel<<<(lvl[l + 1] - lvl[l] + 127) / 128, 128, 0, st>>>(w.cells, lvl[l], lvl[l + 1]);
-            ++launches;
-        }
     }
-    // ---- dual tree traversal (pair buffers start from an estimate, grow and start over if a list overflows)
+}
+
+// Dual tree traversal from the seed (target, source) pairs over the cell array `cells` (targets are cells [0, ntarget); sources
+// may sit anywhere in `cells` — the local essential tree appends the other ranks' trees behind the rank's own), then the
+// lists sorted by (target, source), their per-target offsets and the particle run of every P2P entry.  Pair buffers start
+// from an estimate, grow and start over if a list overflows.  count_at must already hold the particle count of every
+// SOURCE leaf outside [0, ntarget) (remote leaves), indexed by first particle; own leaves are filled in here.
+inline cudaError_t fmm_lists(FmmWorkspace& w, const FmmCell* cells, int ntarget, double theta, double nzs_factor, const int* mine,
+                             const uint64_t* seeds, int nseeds, int nparts, cudaStream_t st, uint64_t& launches, std::string& err) {
     if (!w.front_a) {
-        w.cap_pairs = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 192LL * ncells / nparts), 1500000000LL);
-        w.cap_p2p = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 96LL * ncells / nparts), 1500000000LL);
+        w.cap_pairs = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 192LL * ntarget / nparts), 1500000000LL);
+        w.cap_p2p = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 96LL * ntarget / nparts), 1500000000LL);
         FMM_TRY(fmm_alloc_pairs(w, err));
     }
     FmmCounters zero = {0, 0, 0, 0};
     FmmCounters hc = zero;
     for (int attempt = 0;; ++attempt) {
         FMM_TRY(cudaMemcpyAsync(w.counters, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
-        const uint64_t rootpair = 0;
-        FMM_TRY(cudaMemcpyAsync(w.front_a, &rootpair, sizeof(rootpair), cudaMemcpyHostToDevice, st));
-        unsigned int nfront = 1;
+        FMM_TRY(cudaMemcpyAsync(w.front_a, seeds, sizeof(uint64_t) * nseeds, cudaMemcpyHostToDevice, st));
+        unsigned int nfront = (unsigned int)nseeds;
         uint64_t *fa = w.front_a, *fb = w.front_b;
         hc = zero;
         while (nfront > 0) {
-            fmm_traverse_kernel<<<(nfront + 255) / 256, 256, 0, st>>>(w.cells, fa, nfront, theta, nzs_factor, fb, w.cap_pairs, w.m2l,
+            fmm_traverse_kernel<<<(nfront + 255) / 256, 256, 0, st>>>(cells, fa, nfront, theta, nzs_factor, fb, w.cap_pairs, w.m2l,
                                                                      w.cap_pairs, w.p2p, w.cap_p2p, w.counters, mine);
             ++launches;
             FMM_TRY(cudaMemcpyAsync(&hc, w.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -457,7 +444,7 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
     w.n_p2p = hc.p2p;
     // ---- sort the lists by (target, source) and index them per target cell
     int bits = 1;
-    while ((1 << bits) < ncells) ++bits;
+    while ((1 << bits) < ntarget) ++bits;
     if (w.n_m2l > 0) {
         FMM_CUB(cub::DeviceRadixSort::SortKeys(tmp, tb, w.m2l, w.m2l_sorted, (int)w.n_m2l, 0, 32 + bits, st));
         ++launches;
@@ -466,13 +453,57 @@ inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int
         FMM_CUB(cub::DeviceRadixSort::SortKeys(tmp, tb, w.p2p, w.p2p_sorted, (int)w.n_p2p, 0, 32 + bits, st));
         ++launches;
     }
-    fmm_list_offsets_kernel<<<(ncells + 256) / 256, 256, 0, st>>>(w.m2l_sorted, w.n_m2l, ncells, w.m2l_off);
-    fmm_list_offsets_kernel<<<(ncells + 256) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, ncells, w.p2p_off);
-    fmm_leaf_counts_kernel<<<(w.nleaves + 255) / 256, 256, 0, st>>>(w.cells, w.leaves, w.nleaves, w.count_at);
+    fmm_list_offsets_kernel<<<(ntarget + 256) / 256, 256, 0, st>>>(w.m2l_sorted, w.n_m2l, ntarget, w.m2l_off);
+    fmm_list_offsets_kernel<<<(ntarget + 256) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, ntarget, w.p2p_off);
+    fmm_leaf_counts_kernel<<<(w.nleaves + 255) / 256, 256, 0, st>>>(cells, w.leaves, w.nleaves, w.count_at);
     if (w.n_p2p > 0) fmm_p2p_runs_kernel<<<(w.n_p2p + 255) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, w.count_at, w.runs);
     launches += 4;
     FMM_TRY(cudaGetLastError());
     return cudaSuccess;
+}
+
+// Build the adaptive octree and the interaction lists for the particles of the field.
+inline cudaError_t fmm_build(FmmWorkspace& w, const double* soa, int64_t ld, int64_t n, int ncrit, double theta,
+                             double nzs_factor, std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, std::string& err,
+                             int part = 0, int nparts = 1) {
+    FMM_TRY(fmm_reserve_particles(w, n, err));
+    FmmRoot rt;
+    {
+        cudaError_t e0 = fmm_sort(w, soa, ld, n, st, launches, err, &rt);
+        if (e0 != cudaSuccess) return e0;
+    }
+    const unsigned nbk = (unsigned)((n + 255) / 256);
+    fmm_gather_kernel<<<nbk, 256, 0, st>>>(soa, ld, n, w.perm, w.sx, w.sy, w.sz, w.rec);
+    ++launches;
+    {
+        cudaError_t e1 = fmm_tree(w, n, ncrit, rt, lvl, st, launches, err);
+        if (e1 != cudaSuccess) return e1;
+    }
+    const int ncells = w.ncells;
+    const int* mine = nullptr;
+    if (nparts > 1) {
+        // leaves in Morton order; this rank takes the leaves covering particles [part, part + 1) * n / nparts of that order
+        // and marks them and their ancestors: only those target cells are traversed / receive M2L, L2L, L2P, P2P
+        fmm_leaf_starts_kernel<<<(w.nleaves + 255) / 256, 256, 0, st>>>(w.cells, w.leaves, w.nleaves, w.leaf_keys);
+        FMM_CUB(cub::DeviceRadixSort::SortPairs(tmp, tb, w.leaf_keys, w.leaf_keys_alt, w.leaves, w.leaves_alt, w.nleaves, 0, 32, st));
+        std::swap(w.leaf_keys, w.leaf_keys_alt);
+        std::swap(w.leaves, w.leaves_alt);
+        const int p_lo = (int)(n * part / nparts), p_hi = (int)(n * (part + 1) / nparts);
+        fmm_leaf_range_kernel<<<1, 32, 0, st>>>(w.leaf_keys, w.nleaves, p_lo, p_hi, w.leaf_flag);
+        int range[2] = {0, 0};
+        FMM_TRY(cudaMemcpyAsync(range, w.leaf_flag, sizeof(range), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaStreamSynchronize(st));
+        w.leaf_lo = range[0];
+        w.leaf_hi = part == nparts - 1 ? w.nleaves : range[1];
+        FMM_TRY(cudaMemsetAsync(w.mine, 0, sizeof(int) * ncells, st));
+        if (w.leaf_hi > w.leaf_lo)
+            fmm_flag_owned_kernel<<<(w.leaf_hi - w.leaf_lo + 255) / 256, 256, 0, st>>>(w.cells, w.leaves + w.leaf_lo, w.leaf_hi - w.leaf_lo, w.mine);
+        launches += 4;
+        mine = w.mine;
+    }
+    if (nzs_factor > 0.0) fmm_smax(w, w.cells, ncells, lvl, st, launches);
+    const uint64_t rootpair = 0;
+    return fmm_lists(w, w.cells, ncells, theta, nzs_factor, mine, &rootpair, 1, nparts, st, launches, err);
 }
 
 // Re-gather the Morton-ordered source records from the state (same positions and strengths, new core sizes): what an
@@ -487,23 +518,24 @@ inline cudaError_t fmm_regather(FmmWorkspace& w, const double* soa, int64_t ld, 
 // the far field is the singular kernel, so it does not depend on sigma): skip P2M/M2M/M2L/L2L and only redo L2P + near field.
 template <int P>
 inline cudaError_t fmm_evaluate_p(FmmWorkspace& w, int kernel, int block, const double* gh_table, const std::vector<int>& lvl,
-                                  cudaStream_t st, uint64_t& launches, bool far_valid) {
+                                  cudaStream_t st, uint64_t& launches, bool far_valid, bool skip_upward) {
     cudaError_t e;
     if (!far_valid) {
-        if ((e = FmmPasses<P>::upward(w, lvl, st, launches)) != cudaSuccess) return e;
+        if (!skip_upward && (e = FmmPasses<P>::upward(w, lvl, st, launches)) != cudaSuccess) return e;
         if ((e = FmmPasses<P>::downward(w, lvl, st, launches)) != cudaSuccess) return e;
     }
     return FmmPasses<P>::leaves_uj(w, kernel, block, gh_table, st, launches);
 }
 
 inline cudaError_t fmm_evaluate(FmmWorkspace& w, int p, int kernel, int block, const double* gh_table,
-                                const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, bool far_valid = false) {
+                                const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, bool far_valid = false,
+                                bool skip_upward = false) {
     switch (p) {
-    case 2: return fmm_evaluate_p<2>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
-    case 3: return fmm_evaluate_p<3>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
-    case 4: return fmm_evaluate_p<4>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
-    case 5: return fmm_evaluate_p<5>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
-    case 6: return fmm_evaluate_p<6>(w, kernel, block, gh_table, lvl, st, launches, far_valid);
+    case 2: return fmm_evaluate_p<2>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
+    case 3: return fmm_evaluate_p<3>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
+    case 4: return fmm_evaluate_p<4>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
+    case 5: return fmm_evaluate_p<5>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
+    case 6: return fmm_evaluate_p<6>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -521,7 +553,7 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
     cudaFuncSetAttribute(fmm_leaf_estr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
     if ((eg = fmm_leaf_grid(w, fmm_leaf_estr_kernel<K>, 32 * LEAF_WARPS, smem, (nl + LEAF_WARPS - 1) / LEAF_WARPS, st, grid)) != cudaSuccess) return eg; \
     fmm_leaf_estr_kernel<K><<<grid, 32 * LEAF_WARPS, smem, st>>>(                                                          \
-        w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
+        w.cells_eval ? w.cells_eval : w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
     switch (kernel) {
     case K_GAUSSIANERF: FMM_ESTR_CASE(K_GAUSSIANERF); break;
     case K_WINCKELMANS: FMM_ESTR_CASE(K_WINCKELMANS); break;

@@ -3,11 +3,11 @@
 // from the same box, the same clocks and the same run.
 //
 // Two figures are produced:
-//   * `pipe`  = SMs x 64 FP64 lanes x 2 flop x f_SM, with f_SM MEASURED from the kernel's own clock64() span against the CUDA
-//     event span (no nvidia-smi sampling).  This is the issue-rate ceiling ncu's sm__inst_executed_pipe_fp64 counts against
-//     (one warp-wide DFMA per 2 cycles per SM sub-partition); the roofline denominator bench.py uses.
-//   * `measured` = the best of several register-only DFMA chain kernels (different chain counts / CTA shapes), so the gap
-//     between a real instruction stream and the pipe rate is visible (round 1's single shape read 92 % of `pipe`).
+//   * `measured` = the best of several register-only DFMA chain kernels (different chain counts / CTA shapes) — the roofline
+//     denominator bench.py uses.  ncu reads 99.97 % FP64 pipe active on it (profiles/r02a_dfma_peak.txt) and it reaches
+//     99.8 % of the nominal pipe rate (round 1's single 4 ms launch read 92 %: too short, one shape);
+//   * `pipe` = SMs x 64 FP64 lanes x 2 flop x the driver's nominal max SM clock: the issue-rate ceiling ncu's
+//     sm__inst_executed_pipe_fp64 counts against (one warp-wide DFMA per 2 cycles per SM sub-partition), for context.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -95,7 +95,7 @@ extern "C" int32_t vpmb200_measure_fp64_peak2(int32_t device, int32_t iters, int
                 best_tf = tf;
                 best_ms = t;
                 best_shape = k;
-                // block 0 runs for (almost) the whole launch: its cycle count over the event span is the SM clock under this load
+                // block 0's own span in SM cycles (diagnostic only: CTAs of one launch do not all start at once)
                 best_mhz = (double)cyc / (t * 1e-3) / 1e6;
             }
         }
@@ -105,11 +105,11 @@ extern "C" int32_t vpmb200_measure_fp64_peak2(int32_t device, int32_t iters, int
     cudaFree(d);
     cudaFree(clk);
     if (best_shape < 0) return VPMB200_ECUDA;
-    const double pipe_tf = (double)prop.multiProcessorCount * 64.0 * 2.0 * best_mhz * 1e6 / 1e12;
+    const double pipe_tf = (double)prop.multiProcessorCount * 64.0 * 2.0 * (double)prop.clockRate * 1e3 / 1e12;
     out8[0] = best_tf;                 // best measured DFMA throughput, TFLOP/s
     out8[1] = best_ms;                 // its launch time
-    out8[2] = best_mhz;                // SM clock during that launch, from clock64 / event time (lower bound: launch ramp)
-    out8[3] = pipe_tf;                 // SMs x 64 lanes x 2 x that clock
+    out8[2] = best_mhz;                // block 0's clock64 span / event span, MHz (diagnostic)
+    out8[3] = pipe_tf;                 // SMs x 64 lanes x 2 x nominal max SM clock
     out8[4] = pipe_tf > 0 ? best_tf / pipe_tf : 0.0;
     out8[5] = (double)best_shape;      // index into {8ch x 512 x 4, 16ch x 256 x 4, 4ch x 512 x 4, 8ch x 256 x 4}
     out8[6] = (double)prop.multiProcessorCount;

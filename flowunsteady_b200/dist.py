@@ -1,18 +1,29 @@
-"""Multi-GPU direct path: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch), particles
+"""Multi-GPU particle field: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch), particles
 block-partitioned by index.
 
-Each rank owns the targets [lo, hi) and their full state; sources are a read-only broadcast.  Per U/J evaluation a
-rank packs its particles into source tiles (the engine's wire format, 2570 doubles per 256 sources), the tiles are
-all-gathered, and the pair kernel runs once per peer's tile set.  The gather is issued asynchronously and the rank's OWN
+Direct path.  Each rank owns the targets [lo, hi) and their full state; sources are a read-only broadcast.  Per U/J
+evaluation a rank packs its particles into source tiles (the engine's wire format, 2570 doubles per 256 sources), the tiles
+are all-gathered, and the pair kernel runs once per peer's tile set.  The gather is issued asynchronously and the rank's OWN
 tiles are processed first, so the NVLink transfer (56-80 MB at N = 1M, ~0.1 ms at 770 GB/s) is hidden behind the first
 of `world` kernel launches; nothing else in the step communicates (update / SFS-coefficient / relaxation kernels are
-local to the owner shard).  The reference has no distributed mode at all (README.md:145 of the reference).
+local to the owner shard).
 
-The orchestration is written against a small backend protocol (pack / from_records / stage) so the world_size-2 gloo
-tests on CPU can drive it with a numpy stand-in; the product backend is `Engine` (CUDA).
+UJ_fmm.  A local essential tree (`fmm="let"`, default): the Morton curve is cut into `world` ranges at the unit boundaries
+of the global tree's top, particles travel to the owner of their range (all-to-all), every rank builds ITS part of the one
+global octree and runs the upward pass on it, tree skeletons / multipoles / source records are exchanged, every rank
+evaluates its own targets against all trees with the single-GPU kernels, and the results travel home with the inverse
+all-to-all (per-rank phases: flowunsteady_b200/csrc/fmm_let.cuh).  Sort, tree build, upward pass, traversal, M2L and near
+field are all distributed; results equal the one-GPU UJ_fmm to round-off.  `fmm="replicated"` keeps round 1's scheme
+(every rank builds the whole tree, leaves are split, one all-reduce) as a cross-check.
+The reference has no distributed mode at all (README.md:145 of the reference).
+
+The orchestration is written against a small backend protocol (pack / from_records / stage / let_*) and a collectives
+object, so the world_size-2 gloo tests on CPU can drive the direct path with a numpy stand-in and the LET path can be
+tested with several engines on ONE GPU (tests/loopback.py); the product backend is `Engine` (CUDA) + `TorchCollectives`.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Sequence, Tuple
 
 import torch
@@ -21,13 +32,14 @@ import torch.distributed as dist
 from . import engine as _E
 
 RK3 = ((0.0, 1.0 / 3.0), (-5.0 / 9.0, 15.0 / 16.0), (-153.0 / 128.0, 8.0 / 15.0))
+LET_LEVEL = 5          # level of the histogram that cuts the Morton curve: 8^5 = 32,768 bins
 
 
 class _DevArray:
     """Raw CUDA pointer -> torch (via __cuda_array_interface__); the engine keeps ownership."""
 
-    def __init__(self, ptr: int, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+    def __init__(self, ptr: int, shape, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
 
 
 def partition(n: int, world: int) -> List[Tuple[int, int]]:
@@ -41,30 +53,76 @@ def partition(n: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+class TorchCollectives:
+    """The collectives the sharded field needs, on torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_reduce_(self, t: torch.Tensor, op: str = "sum"):
+        if self.world > 1:
+            dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op], group=self.group)
+        return t
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """(world, *t.shape): every rank's `t` (equal shapes)."""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
+        return out
+
+    def all_gather_into_async(self, out: torch.Tensor, t: torch.Tensor):
+        if self.world == 1:
+            return None
+        return dist.all_gather_into_tensor(out, t, group=self.group, async_op=True)
+
+    def all_gather_ints(self, vals: Sequence[int], device) -> List[List[int]]:
+        t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=device)
+        return [[int(x) for x in row] for row in self.all_gather(t).tolist()]
+
+    def all_to_all_rows(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
+        """Rows [sum(send_counts[:k]), +send_counts[k]) of `send` go to rank k; returns the rows received, by source rank."""
+        n = int(sum(recv_counts))
+        if self.world == 1:
+            return send[:n]
+        recv = torch.empty((max(n, 1),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv[:n], send[:int(sum(send_counts))], [int(c) for c in recv_counts], [int(c) for c in send_counts],
+                               group=self.group)
+        return recv[:n]
+
+
 class ShardedField:
     """Drives pfield.UJ / pfield.SFS / vpm.nextstep over a particle field sharded across the ranks of `group`.
 
     backend: object with the Engine methods used below (np, tiles_for, tile_doubles, pack_uj_records,
-             pack_estr_records, uj_from_records, estr_from_records, stage, get_schemes, set_time, get_time, stream).
-    device:  torch device the tile buffers live on ("cuda:N" for Engine).
+             pack_estr_records, uj_from_records, estr_from_records, stage, get_schemes, set_time, get_time, stream, let_*).
+    device:  torch device the exchange buffers live on ("cuda:N" for Engine).
+    coll:    collectives object (default: TorchCollectives(group)).
+    fmm:     "let" (local essential tree) or "replicated" (round-1 scheme) for vpm_UJ = UJ_fmm.
     """
 
-    def __init__(self, backend, max_local: int, device, group=None):
+    def __init__(self, backend, max_local: int, device, group=None, coll=None, fmm: str = "let", let_level: int = LET_LEVEL):
         self.b = backend
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.coll = coll if coll is not None else TorchCollectives(group)
+        self.world, self.rank = self.coll.world, self.coll.rank
         self.device = torch.device(device)
+        self.fmm_mode = fmm if hasattr(backend, "let_bounds") else "replicated"
+        self.let_level = int(let_level)
         self.td = int(backend.tile_doubles())
         # every rank's slot in the gathered buffer has the same capacity (all_gather needs equal counts)
         cap = torch.tensor([int(backend.tiles_for(max_local))], dtype=torch.int64, device=self._ctl_device())
-        if self.world > 1:
-            dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        self.coll.all_reduce_(cap, "max")
         self.slot_tiles = int(cap.item())
         self.local = torch.zeros(self.slot_tiles * self.td, dtype=torch.float64, device=self.device)
         self.gathered = (torch.zeros(self.world * self.slot_tiles * self.td, dtype=torch.float64, device=self.device)
                          if self.world > 1 else self.local)
         self._ntiles = [0] * self.world
+        self._fmm_hint = 0          # 1: the next UJ_fmm evaluation's far field may be reused; 2: reuse it (DynamicSFS)
+        self._let = None            # partition / exchange state of the last LET evaluation
         self.refresh_counts()
 
     def _ctl_device(self):
@@ -75,25 +133,17 @@ class ShardedField:
         mine = int(self.b.tiles_for(self.b.np))
         if mine > self.slot_tiles:
             raise RuntimeError("local shard outgrew the tile slot; recreate the ShardedField with a larger max_local")
-        if self.world > 1:
-            t = torch.zeros(self.world, dtype=torch.int64, device=self._ctl_device())
-            t[self.rank] = mine
-            dist.all_reduce(t, group=self.group)
-            self._ntiles = [int(v) for v in t.tolist()]
-        else:
-            self._ntiles = [mine]
+        t = torch.zeros(self.world, dtype=torch.int64, device=self._ctl_device())
+        t[self.rank] = mine
+        self.coll.all_reduce_(t, "sum")
+        self._ntiles = [int(v) for v in t.tolist()]
+        self._let = None
 
     # ---- stream plumbing: collectives are ordered against the backend's CUDA stream -----------------------------
     def _stream_ctx(self):
         if self.device.type == "cuda":
             return torch.cuda.stream(torch.cuda.ExternalStream(self.b.stream, device=self.device))
-        import contextlib
         return contextlib.nullcontext()
-
-    def _gather_async(self):
-        if self.world == 1:
-            return None
-        return dist.all_gather_into_tensor(self.gathered, self.local, group=self.group, async_op=True)
 
     def _slot_ptr(self, r: int) -> int:
         return self.gathered.data_ptr() + r * self.slot_tiles * self.td * 8
@@ -102,7 +152,7 @@ class ShardedField:
         """pack -> async all-gather -> own tiles -> wait -> every peer's tiles."""
         with self._stream_ctx():
             pack(self.local.data_ptr())
-            work = self._gather_async()
+            work = self.coll.all_gather_into_async(self.gathered, self.local)
             apply_first(self.local.data_ptr(), self._ntiles[self.rank])
             if work is not None:
                 work.wait()
@@ -118,7 +168,88 @@ class ShardedField:
         ptr, ld = self.b.device_field(0)
         return torch.as_tensor(_DevArray(ptr, (43, ld)), device=self.device)
 
-    # ---- UJ_fmm over the sharded field: replicated tree, leaves split over the ranks ---------------------------------
+    # ---- UJ_fmm over the sharded field: local essential tree ---------------------------------------------------------
+    def _dev_view(self, ptr: int, n: int, typestr: str = "<f8", dtype=torch.float64):
+        if n <= 0 or not ptr:
+            return torch.empty(0, dtype=dtype, device=self.device)
+        return torch.as_tensor(_DevArray(ptr, (n,), typestr), device=self.device)
+
+    def _uj_fmm_let(self, reset: bool, reset_sfs: bool, sfs: bool):
+        """One UJ_fmm evaluation with a local essential tree; phases and what is exchanged between them: fmm_let.cuh."""
+        if sfs and not reset:
+            raise NotImplementedError("sharded UJ_fmm with sfs=True needs reset=True (what every SFS scheme calls)")
+        b, c, dev, G, r = self.b, self.coll, self.device, self.world, self.rank
+        hint, self._fmm_hint = self._fmm_hint, 0
+        sch = b.get_schemes()
+        L = self._let
+        reuse = bool(hint == 2 and L is not None and L.get("far_valid") and not sch.fmm_nonzero_sigma and L["n_home"] == int(b.np))
+        with self._stream_ctx():
+            n_home = int(b.np)
+            if not reuse:
+                lohi = torch.tensor(b.let_bounds(), dtype=torch.float64, device=dev)
+                lohi[:3] = -lohi[:3]
+                c.all_reduce_(lohi, "max")                           # one collective: max of (-min, max)
+                lohi[:3] = -lohi[:3]
+                lohi_g = lohi.cpu().numpy()
+                L = self._let = {"n_home": n_home, "far_valid": False}
+                if not (lohi_g[0] <= lohi_g[3]):                     # no particle anywhere
+                    return
+                hist_ptr, binmax_ptr = b.let_keys(lohi_g, self.let_level)
+                bins = 8 ** self.let_level
+                c.all_reduce_(self._dev_view(hist_ptr, bins, "<i4", torch.int32), "sum")
+                if binmax_ptr:
+                    c.all_reduce_(self._dev_view(binmax_ptr, bins), "max")
+                L["send"] = b.let_partition(G, r)
+                counts = c.all_gather_ints(L["send"], dev)           # counts[q][k]: particles rank q sends to rank k
+                L["recv"] = [counts[q][r] for q in range(G)]
+                L["n_all"] = sum(sum(row) for row in counts)
+            elif "send" not in L:
+                return
+            n_own = sum(L["recv"])
+            send = torch.empty((max(n_home, 1), 7), dtype=torch.float64, device=dev)
+            b.let_pack(send.data_ptr())
+            rows = c.all_to_all_rows(send[:n_home], L["send"], L["recv"])
+            L["rows"] = rows                                         # the engine reads it until the evaluation ends
+            info = b.let_build(rows.data_ptr(), n_own, L["n_all"], reuse)
+            cells_ptr, M_ptr, rec_ptr = b.let_ptrs()
+            if not reuse:
+                ncells_own, _, nm3, _ = info
+                sizes = c.all_gather_ints([n_own, ncells_own], dev)
+                L["np"], L["nc"] = [s[0] for s in sizes], [s[1] for s in sizes]
+                L["slot_c"], L["slot_n"] = max(max(L["nc"]), 1), max(max(L["np"]), 1)
+                cb = b.let_cell_bytes()
+                sc = torch.zeros(L["slot_c"] * cb, dtype=torch.uint8, device=dev)
+                sc[:ncells_own * cb] = self._dev_view(cells_ptr, ncells_own * cb, "|u1", torch.uint8)
+                sm = torch.zeros(L["slot_c"] * nm3, dtype=torch.float64, device=dev)
+                sm[:ncells_own * nm3] = self._dev_view(M_ptr, ncells_own * nm3)
+                cells_all, M_all = c.all_gather(sc), c.all_gather(sm)
+                b.let_attach_tree(cells_all.data_ptr(), M_all.data_ptr(), L["slot_c"], L["nc"], L["np"])
+            srec = torch.zeros(L["slot_n"] * 10, dtype=torch.float64, device=dev)
+
+            def exchange_records():
+                srec[:n_own * 10] = self._dev_view(rec_ptr, n_own * 10)
+                rec_all = c.all_gather(srec)
+                b.let_attach_records(rec_all.data_ptr(), L["slot_n"], L["np"])
+                return rec_all
+
+            keep = exchange_records()
+            out = torch.empty((max(n_own, 1), 12), dtype=torch.float64, device=dev)
+            b.let_evaluate(out.data_ptr(), reuse)
+            res = c.all_to_all_rows(out[:n_own], L["recv"], L["send"])
+            b.let_finish(res.data_ptr(), 0, reset)
+            if reset_sfs:
+                b.reset_particles_sfs()
+            if sfs:
+                b.let_estr_records()
+                keep = exchange_records()
+                outE = torch.empty((max(n_own, 1), 3), dtype=torch.float64, device=dev)
+                b.let_estr_evaluate(outE.data_ptr())
+                resE = c.all_to_all_rows(outE[:n_own], L["recv"], L["send"])
+                b.let_finish(resE.data_ptr(), 1, False)
+            L["far_valid"] = bool(hint == 1 and not sch.fmm_nonzero_sigma)
+            del keep
+
+    # ---- UJ_fmm over the sharded field: replicated tree, leaves split over the ranks (round-1 scheme) ----------------
     def _uj_fmm(self, reset: bool, reset_sfs: bool, sfs: bool):
         """All ranks gather (X, Gamma, sigma) of every particle (56 B each), build the SAME tree, evaluate 1/world of the
         leaves (near field + L2P are > 85 % of the evaluation), and combine with one all-reduce of the U, J rows (the
@@ -129,8 +260,7 @@ class ShardedField:
         n_loc = int(b.np)
         cnt = torch.zeros(self.world, dtype=torch.int64, device=dev)
         cnt[self.rank] = n_loc
-        if self.world > 1:
-            dist.all_reduce(cnt, group=self.group)
+        self.coll.all_reduce_(cnt, "sum")
         counts = [int(v) for v in cnt.tolist()]
         ntot, slot = sum(counts), max(max(counts), 1)
         off = sum(counts[:self.rank])
@@ -143,8 +273,7 @@ class ShardedField:
             send = torch.zeros((7, slot), dtype=torch.float64, device=dev)
             send[:, :n_loc] = state[0:7, :n_loc]
             if self.world > 1:
-                recv = torch.empty((self.world, 7, slot), dtype=torch.float64, device=dev)
-                dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+                recv = self.coll.all_gather(send)
                 o = 0
                 for r, c in enumerate(counts):
                     G[0:7, o:o + c] = recv[r, :, :c]
@@ -152,8 +281,7 @@ class ShardedField:
             else:
                 G[0:7, :n_loc] = send[:, :n_loc]
             b.fmm_global(G.data_ptr(), G.shape[1], ntot, self.rank, self.world, 0)
-            if self.world > 1:
-                dist.all_reduce(G[9:24], group=self.group)
+            self.coll.all_reduce_(G[9:24], "sum")
             mine = slice(off, off + n_loc)
             if reset:
                 state[9:12, :n_loc] = G[9:12, mine]
@@ -166,14 +294,15 @@ class ShardedField:
                 state[39:42, :n_loc] = 0.0
             if sfs:
                 b.fmm_global(G.data_ptr(), G.shape[1], ntot, self.rank, self.world, 1)
-                if self.world > 1:
-                    dist.all_reduce(G[12:15], group=self.group)
+                self.coll.all_reduce_(G[12:15], "sum")
                 state[39:42, :n_loc] += G[12:15, mine]
 
     # ---- pfield.UJ(pfield; reset, reset_sfs, sfs) -------------------------------------------------------------------
     def uj(self, reset: bool = True, reset_sfs: bool = False, sfs: bool = False):
         b = self.b
         if b.get_schemes().uj == _E.UJ_IDS["fmm"]:
+            if self.fmm_mode == "let":
+                return self._uj_fmm_let(reset, reset_sfs, sfs)
             return self._uj_fmm(reset, reset_sfs, sfs)
         if reset:
             b.reset_particles()        # U, J, PSE <- 0 (the pair kernel then accumulates chunk by chunk)
@@ -202,10 +331,15 @@ class ShardedField:
                 self.uj(True, True, True)
                 return
             st(_E.STAGE_SCALE_SIGMA_TEST)
+            self._fmm_hint = 1      # UJ_fmm: keep the tree, the lists and the far field ...
             self.uj(True, True, True)
             st(_E.STAGE_STORE_TEST)
             st(_E.STAGE_SCALE_SIGMA_DOMAIN)
+            self._fmm_hint = 2      # ... only sigma changed in between (engine.cu do_sfs does the same on one GPU)
             self.uj(True, True, True)
+            self._fmm_hint = 0
+            if self._let is not None:
+                self._let["far_valid"] = False
             st(_E.STAGE_DYNAMIC_COEFF)
             st(_E.STAGE_CLIP_CONTROL)
 

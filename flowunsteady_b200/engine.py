@@ -215,6 +215,62 @@ class Engine:
     def fmm_global(self, G_ptr: int, ldg: int, ntot: int, part: int, nparts: int, pass_: int):
         self._check(self._L.vpmb200_fmm_global(self._h, C.c_void_p(G_ptr), int(ldg), int(ntot), int(part), int(nparts), int(pass_)))
 
+    # ---- multi-GPU UJ_fmm: local-essential-tree phases (include/vpmb200.h: vpmb200_let_*) ----------------
+    def let_bounds(self) -> np.ndarray:
+        o = (C.c_double * 6)()
+        self._check(self._L.vpmb200_let_bounds(self._h, o))
+        return np.array(o[:])
+
+    def let_keys(self, lohi_global, Lc: int):
+        """-> (device pointer of the int32 histogram [8^Lc], device pointer of the per-bin sigma max or None)."""
+        g = (C.c_double * 6)(*[float(v) for v in lohi_global])
+        h, m = C.c_void_p(), C.c_void_p()
+        self._check(self._L.vpmb200_let_keys(self._h, g, int(Lc), C.byref(h), C.byref(m)))
+        return h.value, m.value
+
+    def let_partition(self, nparts: int, part: int):
+        sc = (C.c_int64 * nparts)()
+        self._check(self._L.vpmb200_let_partition(self._h, int(nparts), int(part), sc))
+        return [int(v) for v in sc]
+
+    def let_pack(self, rows_ptr: int):
+        self._check(self._L.vpmb200_let_pack(self._h, C.c_void_p(rows_ptr)))
+
+    def let_build(self, rows_ptr: int, n_own: int, n_all: int, reuse: bool = False):
+        info = (C.c_int64 * 4)()
+        self._check(self._L.vpmb200_let_build(self._h, C.c_void_p(rows_ptr), int(n_own), int(n_all), int(reuse), info))
+        return [int(v) for v in info]
+
+    def let_ptrs(self):
+        p = (C.c_void_p * 3)()
+        self._check(self._L.vpmb200_let_ptrs(self._h, p))
+        return [v or 0 for v in p]
+
+    def let_attach_tree(self, cells_ptr: int, M_ptr: int, slot_cells: int, ncells, nparticles):
+        g = len(ncells)
+        a, b = (C.c_int64 * g)(*[int(v) for v in ncells]), (C.c_int64 * g)(*[int(v) for v in nparticles])
+        self._check(self._L.vpmb200_let_attach_tree(self._h, C.c_void_p(cells_ptr), C.c_void_p(M_ptr), int(slot_cells), a, b))
+
+    def let_attach_records(self, rec_ptr: int, slot_n: int, nparticles):
+        b = (C.c_int64 * len(nparticles))(*[int(v) for v in nparticles])
+        self._check(self._L.vpmb200_let_attach_records(self._h, C.c_void_p(rec_ptr), int(slot_n), b))
+
+    def let_evaluate(self, out_ptr: int, reuse: bool = False):
+        self._check(self._L.vpmb200_let_evaluate(self._h, C.c_void_p(out_ptr), int(reuse)))
+
+    def let_estr_records(self):
+        self._check(self._L.vpmb200_let_estr_records(self._h))
+
+    def let_estr_evaluate(self, out_ptr: int):
+        self._check(self._L.vpmb200_let_estr_evaluate(self._h, C.c_void_p(out_ptr)))
+
+    def let_finish(self, res_ptr: int, what: int, reset: bool):
+        self._check(self._L.vpmb200_let_finish(self._h, C.c_void_p(res_ptr), int(what), int(reset)))
+
+    @staticmethod
+    def let_cell_bytes() -> int:
+        return _lib.lib().vpmb200_let_cell_bytes()
+
     def set_option(self, name: str, value: int):
         self._check(self._L.vpmb200_set_option(self._h, name.encode(), int(value)))
 

@@ -249,6 +249,38 @@ int32_t vpmb200_estr_from_records(vpmb200_handle h, const double* tiles, int64_t
  * so the ranks' outputs combine with one all-reduce (flowunsteady_b200/dist.py). */
 int32_t vpmb200_fmm_global(vpmb200_handle h, double* G, int64_t ldg, int64_t ntot, int32_t part, int32_t nparts, int32_t pass);
 
+/* ---- multi-GPU UJ_fmm with a LOCAL ESSENTIAL TREE: per-rank phases (flowunsteady_b200/csrc/fmm_let.cuh) -----------------
+ * One evaluation = bounds -> [all-reduce min/max] -> keys -> [all-reduce histogram (sum), bin sigma (max)] -> partition ->
+ * pack -> [all-to-all of 7-double rows] -> build -> [all-gather of cells / multipoles / records] -> attach_tree +
+ * attach_records -> evaluate -> [inverse all-to-all of 12-double rows] -> finish; with sfs: estr_records -> [all-gather of
+ * records] -> attach_records -> estr_evaluate -> [inverse all-to-all of 3-double rows] -> finish(what = 1).
+ * The bracketed collectives are the caller's (flowunsteady_b200/dist.py: NCCL); all pointers below are DEVICE pointers
+ * except lohi6, send_counts, info4, ncells, nparticles and ptrs3 (host).  Results equal the one-GPU UJ_fmm to round-off. */
+int32_t vpmb200_let_cell_bytes(void);                               /* bytes of one tree cell in the skeleton exchange     */
+int32_t vpmb200_let_bounds(vpmb200_handle h, double* lohi6);        /* min xyz, max xyz of the local particles             */
+/* Morton keys + sort of the local ("home") particles in the cube of the GLOBAL bounds, level-Lc histogram: *hist_dev = int32
+ * [8^Lc] (all-reduce SUM in place), *binmax_dev = double [8^Lc] or NULL (all-reduce MAX in place; nonzero_sigma only). */
+int32_t vpmb200_let_keys(vpmb200_handle h, const double* lohi6_global, int32_t Lc, void** hist_dev, void** binmax_dev);
+/* Cuts the Morton curve into nparts key ranges of equal count at top-tree unit boundaries; send_counts[k] = local
+ * particles owned by rank k (contiguous in the packed order). */
+int32_t vpmb200_let_partition(vpmb200_handle h, int32_t nparts, int32_t part, int64_t* send_counts);
+int32_t vpmb200_let_pack(vpmb200_handle h, double* rows);           /* np rows of (x, y, z, Gamma, sigma), Morton order    */
+/* Owner side: sort the n_own received rows, build this rank's part of the global octree, upward pass.  n_all = particles of
+ * all ranks.  reuse != 0: same positions / strengths as the previous evaluation (DynamicSFS's second filter): only the
+ * records are refreshed.  info4 = { cells, leaves, doubles per cell multipole, n_own }. */
+int32_t vpmb200_let_build(vpmb200_handle h, const double* rows, int64_t n_own, int64_t n_all, int32_t reuse, int64_t* info4);
+int32_t vpmb200_let_ptrs(vpmb200_handle h, void** ptrs3);           /* own cells, multipoles, records (send buffers)        */
+/* all-gathered blocks (rank q at q * slot): tree skeletons + multipoles, then source records (UJ or E_str flavour) */
+int32_t vpmb200_let_attach_tree(vpmb200_handle h, const void* cells_recv, const double* M_recv, int64_t slot_cells,
+                                const int64_t* ncells, const int64_t* nparticles);
+int32_t vpmb200_let_attach_records(vpmb200_handle h, const double* rec_recv, int64_t slot_n, const int64_t* nparticles);
+int32_t vpmb200_let_evaluate(vpmb200_handle h, double* out_rows, int32_t reuse);   /* n_own rows of U(3), J(9), arrival order */
+int32_t vpmb200_let_estr_records(vpmb200_handle h);                 /* own records -> E_str flavour (needs evaluate's J)    */
+int32_t vpmb200_let_estr_evaluate(vpmb200_handle h, double* out_rows);             /* n_own rows of E_str(3)                  */
+/* Home side: res_rows in the packed order.  what = 0: U, J rows (reset != 0 overwrites and zeroes PSE, else accumulates);
+ * what = 1: SFS rows += E_str. */
+int32_t vpmb200_let_finish(vpmb200_handle h, const double* res_rows, int32_t what, int32_t reset);
+
 /* The per-particle stages of pfield.SFS / nextstep, exposed so a sharded driver can interleave its exchange:
  * stage ids in vpmb200_stage. */
 enum {
@@ -269,10 +301,10 @@ int32_t vpmb200_stage(vpmb200_handle h, int32_t stage, double a, double b, doubl
  * kernel, `iters` x 128 FMAs per thread).  bench.py uses it as the roofline denominator of the FP64-bound pair
  * kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int32_t vpmb200_measure_fp64_peak(int32_t device, int32_t iters, int32_t repeats, double* tflops, double* ms);
-/* The same with its evidence: out8 = { best measured DFMA TFLOP/s over several chain/CTA shapes, its launch ms, the SM clock
- * (MHz) during that launch derived from the kernel's own clock64() span over the CUDA-event span, the FP64 PIPE rate
- * SMs x 64 lanes x 2 flop x that clock (what ncu's sm__inst_executed_pipe_fp64 counts against; bench.py's roofline
- * denominator), measured / pipe, index of the best shape, SM count, the driver's nominal max SM clock (MHz) }. */
+/* The same with its evidence: out8 = { best measured DFMA TFLOP/s over several chain/CTA shapes (bench.py's roofline
+ * denominator; ncu: 99.97 % FP64 pipe active), its launch ms, a clock64 diagnostic, the nominal FP64 PIPE rate
+ * SMs x 64 lanes x 2 flop x nominal max SM clock (what ncu's sm__inst_executed_pipe_fp64 counts against),
+ * measured / nominal, index of the best shape, SM count, the driver's nominal max SM clock (MHz) }. */
 int32_t vpmb200_measure_fp64_peak2(int32_t device, int32_t iters, int32_t repeats, double* out8);
 
 /* Library identification. */
