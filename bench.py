@@ -85,6 +85,8 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fmm", action="store_true", help="skip the secondary UJ_fmm figures")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle parity check of the timed state")
+    ap.add_argument("--fmm-mode", default="let", choices=["let", "replicated"],
+                    help="multi-GPU UJ_fmm: local essential tree (default) or round 1's replicated tree")
     ap.add_argument("--cpu-targets", type=int, default=4096, help="targets of the CPU baseline slab")
     return ap.parse_args()
 
@@ -245,6 +247,42 @@ def parity_check(field, eng, sch, n, world, rank, local_rank):
             "oracle_s": time.perf_counter() - t0}
 
 
+def fmm_parity_check(field, eng, sch, n, world, rank, local_rank):
+    """UJ_fmm record: the sharded U, J, E_str (fresh from field.uj(True, True, True)) at PARITY_TARGETS sampled particles against
+    (i) ONE GPU running the same UJ_fmm on the whole field (must agree to round-off: the union of the ranks' trees is the
+    one-GPU tree) and (ii) the direct kernel (the method's own error at the reference's default settings)."""
+    import flowunsteady_b200 as fb
+    rows = list(range(0, 7)) + list(range(9, 12)) + list(range(15, 24)) + list(range(39, 42))
+    A = gather_state_rows(field, eng, rows, world, rank, local_rank)
+    if rank != 0:
+        return None
+    t0 = time.perf_counter()
+    P = np.zeros((n, 43))
+    P[:, 0:7] = A[0:7].T
+    idx = np.sort(np.random.default_rng(1234).choice(n, min(PARITY_TARGETS, n), replace=False))
+    one = fb.default_schemes(kernel=sch.kernel, uj="fmm", fmm_p=sch.fmm_p, fmm_ncrit=sch.fmm_ncrit, fmm_theta=sch.fmm_theta,
+                             fmm_nonzero_sigma=sch.fmm_nonzero_sigma, transposed=sch.transposed)
+    with fb.Engine(n, device=local_rank, schemes=one) as e1:
+        e1.upload(P)
+        e1.uj(True, True, True)
+        R = e1.download(np.zeros_like(P))
+        e1.set_schemes(fb.default_schemes(kernel=sch.kernel, uj="direct"))
+        Ud, Jd = e1.uj_probe(P[idx, 0:3], want_J=True)
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / np.abs(b).max())
+
+    got = {"U": A[7:10].T[idx], "J": A[10:19].T[idx], "SFS": A[19:22].T[idx]}
+    ref = {"U": R[idx, 9:12], "J": R[idx, 15:24], "SFS": R[idx, 39:42]}
+    err = {k: rel(got[k], ref[k]) for k in got}
+    tol = {"U": 1e-12, "J": 1e-12, "SFS": 1e-11}
+    return {**err, "tol": tol, "ok": bool(all(np.isfinite(err[k]) and err[k] < tol[k] for k in err)), "targets": int(idx.size),
+            "ranks": int(world), "measure": "max-norm relative difference to ONE GPU running the same UJ_fmm on the whole field",
+            "fmm_rel_l2_err_vs_direct": {"U": float(np.linalg.norm(got["U"] - Ud) / np.linalg.norm(Ud)),
+                                         "J": float(np.linalg.norm(got["J"] - Jd) / np.linalg.norm(Jd))},
+            "seconds": time.perf_counter() - t0}
+
+
 # --------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -290,7 +328,7 @@ def run_ours(args):
 
     eng = fb.Engine(hi - lo, float_bits=64, device=local_rank, schemes=sch)
     eng.upload(P_local)
-    field = ShardedField(eng, max_local=hi - lo, device=f"cuda:{local_rank}")
+    field = ShardedField(eng, max_local=hi - lo, device=f"cuda:{local_rank}", fmm=args.fmm_mode)
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -338,21 +376,33 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = evals * float(n) * float(n) / (ms_per_step * 1e-3)
     if args.uj == "fmm":
-        # secondary mode: an O(N) method has no pair count; report particle-evaluations per second and stop here
+        # secondary mode (BASELINE configs[1], [3], [4]): an O(N) method has no pair count; report particle-evaluations/s
+        eval_ms = timed(lambda: field.uj(True, True, True), 3) / 3
+        parity = None if args.no_parity else fmm_parity_check(field, eng, sch, n, world, rank, local_rank)
         if rank == 0:
+            cfg = make_config(args, n, world)
+            cfg["workload"] = (f"{FIELD_NAMES[args.field]}, UJ_fmm p=4 ncrit=50 theta=0.4 nonzero_sigma=false, gaussianerf, rVPM, "
+                               f"rungekutta3 + pedrizzetti, sfs={args.sfs}")
             print(json.dumps({
                 "metric": "particle U/J evaluations per second (UJ_fmm step: RK3 + pedrizzetti%s)" % (
                     " + dynamic SFS" if args.sfs == "dynamic" else ""),
                 "value": evals * float(n) / (ms_per_step * 1e-3), "unit": "particle-evaluations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "s_per_timestep": ms_per_step * 1e-3,
+                "ms_per_evaluation_with_estr": eval_ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{args.field} field, UJ_fmm p=4 ncrit=50 theta=0.4 nonzero_sigma=false, gaussianerf, rVPM",
-                           "particles": n, "sfs": args.sfs, "evaluations_per_step": evals,
-                           "parallelism": f"replicated tree, leaves split over {world} GPU(s)"},
-                "gpu_launches": int(launches), "clocks": clocks, "fmm_tree": eng.fmm_stats()}), flush=True)
+                "config": cfg,
+                "config_notes": {"parallelism": ("local essential tree: Morton-range ownership, all-to-all of particles, all-gather of "
+                                                 "skeletons / multipoles / records, inverse all-to-all of results"
+                                                 if args.fmm_mode == "let" else "replicated tree, leaves split, all-reduce")
+                                 + f" over {world} GPU(s)"},
+                "parity": parity, "gpu_launches": int(launches), "clocks": clocks, "fmm_tree_rank0": eng.fmm_stats()}), flush=True)
+        failed = bool(rank == 0 and parity is not None and not parity["ok"])
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+        if failed:
+            print(f"[bench] PARITY FAILED: {parity}", file=sys.stderr)
+            sys.exit(3)
         return
 
     # ---- dominant kernel alone: one U/J evaluation (K1 + its pack kernel), and the same with the E_str pass (K2) -----

@@ -70,6 +70,10 @@ SYMBOLS = {
     "vpmb200_set_option": (C.c_int32, [_H, C.c_char_p, C.c_int64]),
     "vpmb200_fmm_stats": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "vpmb200_direct_tile_stats": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "vpmb200_uj_probe_ex": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vpmb200_set_statics": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
+    "vpmb200_get_statics": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "vpmb200_set_mirror": (C.c_int32, [_H, C.c_int32, _dp, _dp]),
     "vpmb200_let_cell_bytes": (C.c_int32, []),
     "vpmb200_let_bounds": (C.c_int32, [_H, _dp]),
     "vpmb200_let_keys": (C.c_int32, [_H, _dp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

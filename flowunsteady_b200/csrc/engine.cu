@@ -53,6 +53,12 @@ struct vpmb200_engine {
     int fmm_hint = 0;           // 1: the next UJ_fmm call should keep its far field; 2: the next call may reuse it
     bool fmm_far_valid = false;
     int64_t fmm_far_np = -1;
+    // Static-particle fast path (simulation.jl:355-365): the embedded particles of the current step parked in the state
+    // columns [np, np + nstatic) instead of add_particle -> nextstep -> remove_particle; valid while nt == static_gen.
+    int64_t nstatic = 0;
+    int64_t static_gen = -1;
+    int mirror_on = 0;          // method of images (vehicle_vlm_unsteady.jl:245-260): images of every particle join the static set
+    double mirror_X[3] = {0, 0, 0}, mirror_n[3] = {0, 0, 1};
     uint64_t launches = 0;      // kernels enqueued by this handle (bench.py's gpu_launches)
     vpmb200_schemes sch;
     std::string err;
@@ -689,6 +695,95 @@ __global__ void join_rows_kernel(const double* __restrict__ soa, int64_t ld, int
     for (int c = 0; c < nc; ++c) aos[i * nc + c] = soa[(size_t)c * ld + i];
 }
 
+// ---- static-particle fast path + method of images -----------------------------------------------------------------------
+__global__ void set_static_flag_kernel(double* __restrict__ soa, int64_t ld, int64_t i0, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) soa[(size_t)F_STATIC * ld + i0 + i] = 1.0;
+}
+
+// Image of particle i (i < n) in the plane (X0, nrm) -> column n + i, exactly as the reference writes it
+// (src/FLOWUnsteady_vehicle_vlm_unsteady.jl:248-258, src/FLOWUnsteady_simulation.jl:520-533):
+//   Xm = X - dot(2 (X - X0), nrm) nrm,   Gm = 2 dot(G, nrm) G / |G| - G   (sic),   sigma, vol, circulation, C copied, static.
+__global__ void mirror_images_kernel(double* __restrict__ soa, int64_t ld, int64_t n, Vec3 X0, Vec3 nrm) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = n + i;
+    for (int f = 0; f < NFIELDS; ++f) soa[(size_t)f * ld + o] = 0.0;
+    double x[3], g[3];
+    for (int c = 0; c < 3; ++c) { x[c] = soa[(size_t)(F_X + c) * ld + i]; g[c] = soa[(size_t)(F_GAMMA + c) * ld + i]; }
+    // no contraction: the oracle (and the reference's Julia) round every product and sum
+    double a[3];
+    for (int c = 0; c < 3; ++c) a[c] = __dmul_rn(2.0, __dsub_rn(x[c], X0.v[c]));
+    const double d = __dadd_rn(__dadd_rn(__dmul_rn(a[0], nrm.v[0]), __dmul_rn(a[1], nrm.v[1])), __dmul_rn(a[2], nrm.v[2]));
+    const double gn = __dadd_rn(__dadd_rn(__dmul_rn(g[0], nrm.v[0]), __dmul_rn(g[1], nrm.v[1])), __dmul_rn(g[2], nrm.v[2]));
+    const double gnorm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(g[0], g[0]), __dmul_rn(g[1], g[1])), __dmul_rn(g[2], g[2])));
+    for (int c = 0; c < 3; ++c) {
+        soa[(size_t)(F_X + c) * ld + o] = __dsub_rn(x[c], __dmul_rn(d, nrm.v[c]));
+        soa[(size_t)(F_GAMMA + c) * ld + o] = __dsub_rn(__ddiv_rn(__dmul_rn(__dmul_rn(2.0, gn), g[c]), gnorm), g[c]);
+        soa[(size_t)(F_C + c) * ld + o] = soa[(size_t)(F_C + c) * ld + i];
+    }
+    soa[(size_t)F_SIGMA * ld + o] = soa[(size_t)F_SIGMA * ld + i];
+    soa[(size_t)F_VOL * ld + o] = soa[(size_t)F_VOL * ld + i];
+    soa[(size_t)F_CIRC * ld + o] = soa[(size_t)F_CIRC * ld + i];
+    soa[(size_t)F_STATIC * ld + o] = 1.0;
+}
+
+// sigma of particle 0 times (or over) `f`, k times in sequence — the reference's Vvpm_on_Xs quirk (simulation.jl:507-513, 555-561)
+__global__ void scale_sigma0_kernel(double* __restrict__ soa, int64_t ld, double f, int64_t k, int divide) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = soa[(size_t)F_SIGMA * ld];
+    for (int64_t j = 0; j < k; ++j) s = divide ? __ddiv_rn(s, f) : __dmul_rn(s, f);
+    soa[(size_t)F_SIGMA * ld] = s;
+}
+
+__global__ void count_static_kernel(const double* __restrict__ soa, int64_t ld, int64_t n, unsigned long long* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool st = i < n && soa[(size_t)F_STATIC * ld + i] > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, st);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+inline void drop_statics(vpmb200_engine* e) {
+    e->nstatic = 0;
+    e->static_gen = -1;
+}
+
+// images of the first n columns -> columns [n, 2n)
+int32_t append_images(vpmb200_engine* e, int64_t n) {
+    if (n <= 0) return VPMB200_OK;
+    if (2 * n > e->maxp) return fail(e, VPMB200_ECAPACITY, "mirroring needs room for one image per particle (max_particles >= 2 x particles)");
+    Vec3 X0, nr;
+    for (int c = 0; c < 3; ++c) { X0.v[c] = e->mirror_X[c]; nr.v[c] = e->mirror_n[c]; }
+    mirror_images_kernel<<<blocks_for(n, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, n, X0, nr);
+    CU_TRY(e, cudaGetLastError());
+    e->launches++;
+    return VPMB200_OK;
+}
+
+// The parked static set (while it belongs to the current step) and, with mirroring on, the images of every particle become
+// part of the field for the duration of one call; statics_end restores the particle count (and consumes the set).
+int32_t statics_begin(vpmb200_engine* e, int64_t* np_saved) {
+    *np_saved = e->np;
+    if (e->nstatic > 0 && e->static_gen != e->nt) drop_statics(e);   // a stale set is never used
+    int64_t n = e->np + e->nstatic;
+    if (e->mirror_on && n > 0) {
+        int32_t rc = append_images(e, n);
+        if (rc) return rc;
+        n *= 2;
+    }
+    if (n != e->np) {
+        e->np = n;
+        e->shard_sorted_np = -1;
+    }
+    return VPMB200_OK;
+}
+
+void statics_end(vpmb200_engine* e, int64_t np_saved, bool consume) {
+    if (e->np != np_saved) e->shard_sorted_np = -1;
+    e->np = np_saved;
+    if (consume) drop_statics(e);
+}
+
 // Instrumentation (not on the hot path): how many (target block, source tile) pairs K1 sends to its branch-free far loop —
 // and K2 skips — for the CURRENT field.  One CTA per target block recomputes the box exactly as the pair kernels do.
 __global__ void __launch_bounds__(UJ_BT) tile_class_count_kernel(const double* __restrict__ srec, int ntiles,
@@ -871,6 +966,7 @@ static int mask_runs(uint32_t mask, int runs[13][2]) {
 
 static int32_t upload_block(vpmb200_engine* e, const double* particles, int64_t ld, int64_t n, int64_t dst0, uint32_t mask) {
     e->shard_sorted_np = -1;
+    drop_statics(e);   // the columns behind np are about to change hands
     if (n <= 0) return VPMB200_OK;
     if (ld < NFIELDS) return fail(e, VPMB200_EINVAL, "ld < 43");
     CU_TRY(e, cudaSetDevice(e->device));
@@ -965,6 +1061,7 @@ int32_t vpmb200_remove_particle(vpmb200_handle e, int64_t i) {
     CHECK_HANDLE(e);
     if (i < 0 || i >= e->np) return fail(e, VPMB200_EINVAL, "particle index out of range");
     e->shard_sorted_np = -1;
+    drop_statics(e);
     CU_TRY(e, cudaSetDevice(e->device));
     if (i != e->np - 1) {
         move_column_kernel<<<1, 64, 0, e->stream>>>(e->state, e->ld, i, e->np - 1);
@@ -981,6 +1078,7 @@ int32_t vpmb200_remove_where(vpmb200_handle e, int32_t criterion, const double* 
     static const int nparams[5] = {0, 2, 2, 9, 4};
     if (criterion < 1 || criterion > 4) return fail(e, VPMB200_EINVAL, "unknown removal criterion");
     e->shard_sorted_np = -1;
+    drop_statics(e);
     if (removed) *removed = 0;
     const int64_t n = e->np;
     if (n <= 0) return VPMB200_OK;
@@ -1090,15 +1188,15 @@ int32_t vpmb200_reset_particles_sfs(vpmb200_handle e) {
 int32_t vpmb200_uj(vpmb200_handle e, int32_t reset, int32_t reset_sfs, int32_t sfs) {
     CHECK_HANDLE(e);
     CU_TRY(e, cudaSetDevice(e->device));
-    return do_uj(e, reset, reset_sfs, sfs);
+    int64_t np0;
+    int32_t rc = statics_begin(e, &np0);
+    if (rc == VPMB200_OK) rc = do_uj(e, reset, reset_sfs, sfs);
+    statics_end(e, np0, false);
+    return rc;
 }
 
-int32_t vpmb200_uj_probe(vpmb200_handle e, const double* X, int64_t m, double* U, double* J) {
-    CHECK_HANDLE(e);
-    if (m < 0) return fail(e, VPMB200_EINVAL, "m < 0");
-    if (m == 0) return VPMB200_OK;
-    if (!X || !U) return fail(e, VPMB200_EINVAL, "X or U is NULL");
-    CU_TRY(e, cudaSetDevice(e->device));   // probes always use the direct kernel: m targets x np sources
+static int32_t probe_eval(vpmb200_engine* e, const double* X, int64_t m, double* U, double* J) {
+    // probes always use the direct kernel: m targets x np sources
     int32_t rc = ensure_probe(e, m);
     if (rc) return rc;
     const int64_t pl = e->probe_cap;
@@ -1121,11 +1219,58 @@ int32_t vpmb200_uj_probe(vpmb200_handle e, const double* X, int64_t m, double* U
         double* stageJ = stage + 3 * pl;
         join_rows_kernel<<<blocks_for(m, PK_BT), PK_BT, 0, e->stream>>>(soaJ, pl, 9, m, stageJ);
         CU_TRY(e, cudaGetLastError());
-    e->launches++;
+        e->launches++;
         CU_TRY(e, cudaMemcpyAsync(J, stageJ, sizeof(double) * 9 * (size_t)m, cudaMemcpyDeviceToHost, e->stream));
     }
     CU_TRY(e, cudaStreamSynchronize(e->stream));
     return VPMB200_OK;
+}
+
+int32_t vpmb200_uj_probe(vpmb200_handle e, const double* X, int64_t m, double* U, double* J) {
+    return vpmb200_uj_probe_ex(e, X, m, 1.0, 0, U, J);
+}
+
+int32_t vpmb200_uj_probe_ex(vpmb200_handle e, const double* X, int64_t m, double fsgm, int32_t mirror, double* U, double* J) {
+    CHECK_HANDLE(e);
+    if (m < 0) return fail(e, VPMB200_EINVAL, "m < 0");
+    if (m == 0) return VPMB200_OK;
+    if (!X || !U) return fail(e, VPMB200_EINVAL, "X or U is NULL");
+    if (!(fsgm > 0)) return fail(e, VPMB200_EINVAL, "fsgm must be positive (simulation.jl:211-213)");
+    CU_TRY(e, cudaSetDevice(e->device));
+    // Vvpm_on_Xs's "singularize" loop (simulation.jl:507-513) indexes the particle MATRIX with one subscript, so instead of
+    // scaling every static particle's core it multiplies sigma of particle 1 by fsgm once per static particle present in the
+    // field at that moment (normally none: the statics are added after the loop).  Reproduced literally, undone after.
+    int64_t k = 0;
+    if (std::fabs(fsgm) != 1.0 && e->np > 0) {
+        CU_TRY(e, cudaMemsetAsync(e->counter, 0, sizeof(unsigned long long), e->stream));
+        count_static_kernel<<<blocks_for(round_up(e->np, 32), PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, e->counter);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+        unsigned long long c = 0;
+        CU_TRY(e, cudaMemcpyAsync(&c, e->counter, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(e, cudaStreamSynchronize(e->stream));
+        k = (int64_t)c;
+        if (k > 0) {
+            scale_sigma0_kernel<<<1, 32, 0, e->stream>>>(e->state, e->ld, fsgm, k, 0);
+            CU_TRY(e, cudaGetLastError());
+            e->launches++;
+        }
+    }
+    int64_t np0;
+    int32_t rc = statics_begin(e, &np0);          // static_particles_fun (+ its images)
+    if (rc == VPMB200_OK && mirror && e->np > 0) {   // Vvpm_on_Xs's own method of images on top (simulation.jl:518-535)
+        rc = append_images(e, e->np);
+        if (rc == VPMB200_OK) e->np *= 2;
+    }
+    if (rc == VPMB200_OK) rc = probe_eval(e, X, m, U, J);
+    statics_end(e, np0, false);
+    if (k > 0) {
+        scale_sigma0_kernel<<<1, 32, 0, e->stream>>>(e->state, e->ld, fsgm, k, 1);
+        cudaError_t st = cudaGetLastError();
+        if (st != cudaSuccess && rc == VPMB200_OK) rc = fail(e, VPMB200_ECUDA, cudaGetErrorString(st));
+        e->launches++;
+    }
+    return rc;
 }
 
 int32_t vpmb200_sfs(vpmb200_handle e, double a, double b) {
@@ -1134,10 +1279,7 @@ int32_t vpmb200_sfs(vpmb200_handle e, double a, double b) {
     return do_sfs(e, a, b);
 }
 
-int32_t vpmb200_nextstep(vpmb200_handle e, double dt, const double* Uinf, int32_t relax) {
-    CHECK_HANDLE(e);
-    if (!Uinf) return fail(e, VPMB200_EINVAL, "Uinf is NULL");
-    CU_TRY(e, cudaSetDevice(e->device));
+static int32_t nextstep_body(vpmb200_engine* e, double dt, const double* Uinf, int32_t relax) {
     int32_t rc;
     if (e->np > 0) {
         if (e->sch.integration == VPMB200_INTEGRATION_EULER) {
@@ -1159,8 +1301,55 @@ int32_t vpmb200_nextstep(vpmb200_handle e, double dt, const double* Uinf, int32_
             }
         }
     }
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_nextstep(vpmb200_handle e, double dt, const double* Uinf, int32_t relax) {
+    CHECK_HANDLE(e);
+    if (!Uinf) return fail(e, VPMB200_EINVAL, "Uinf is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    // the reference's loop: static_particles_function -> nextstep -> remove the statics (simulation.jl:355-365); here the
+    // parked set (vpmb200_set_statics) joins the field for the step and is dropped with it
+    int64_t np0;
+    int32_t rc = statics_begin(e, &np0);
+    if (rc == VPMB200_OK) rc = nextstep_body(e, dt, Uinf, relax);
+    statics_end(e, np0, true);
+    if (rc) return rc;
     e->t += dt;
     e->nt += 1;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_set_statics(vpmb200_handle e, const double* cols, int64_t ld, int64_t n, int64_t generation) {
+    CHECK_HANDLE(e);
+    if (n < 0 || (n > 0 && !cols)) return fail(e, VPMB200_EINVAL, "set_statics: bad arguments");
+    if (e->np + n > e->maxp) return fail(e, VPMB200_ECAPACITY, "static particles would exceed max_particles");
+    CU_TRY(e, cudaSetDevice(e->device));
+    int32_t rc = upload_block(e, cols, ld, n, e->np, VPMB200_FM_ALL);   // (drops the previous set)
+    if (rc) return rc;
+    if (n > 0) {
+        set_static_flag_kernel<<<blocks_for(n, PK_BT), PK_BT, 0, e->stream>>>(e->state, e->ld, e->np, n);
+        CU_TRY(e, cudaGetLastError());
+        e->launches++;
+    }
+    e->nstatic = n;
+    e->static_gen = generation;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_get_statics(vpmb200_handle e, int64_t* n, int64_t* generation) {
+    CHECK_HANDLE(e);
+    if (n) *n = e->nstatic;
+    if (generation) *generation = e->static_gen;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_set_mirror(vpmb200_handle e, int32_t enabled, const double* X0, const double* normal) {
+    CHECK_HANDLE(e);
+    if (enabled && (!X0 || !normal)) return fail(e, VPMB200_EINVAL, "set_mirror: plane point or normal is NULL");
+    e->mirror_on = enabled != 0;
+    if (X0 && normal)   // the plane is also what vpmb200_uj_probe_ex(mirror = 1) uses
+        for (int c = 0; c < 3; ++c) { e->mirror_X[c] = X0[c]; e->mirror_n[c] = normal[c]; }
     return VPMB200_OK;
 }
 

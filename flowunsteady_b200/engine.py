@@ -50,6 +50,8 @@ def default_schemes(**kw) -> Schemes:
 
 
 def _as_matrix(a: np.ndarray) -> np.ndarray:
+    if isinstance(a, np.ndarray) and a.ndim == 2 and a.shape[0] == 0 and a.dtype == np.float64 and a.shape[1] >= NFIELDS:
+        return a                                   # an empty shard (strides of a 0-row array carry no information)
     if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 2 and a.shape[1] >= NFIELDS
             and a.strides[1] == 8 and a.strides[0] >= 8 * NFIELDS and a.strides[0] % 8 == 0):
         raise ValueError("particles must be a float64 (np, >=43) array with contiguous rows")
@@ -122,7 +124,8 @@ class Engine:
     def upload(self, particles: np.ndarray, np_: int | None = None, field_mask: int = FM_ALL):
         P = _as_matrix(particles)
         n = P.shape[0] if np_ is None else int(np_)
-        self._check(self._L.vpmb200_upload(self._h, P.ctypes.data, P.strides[0] // 8, n, field_mask))
+        ld = P.strides[0] // 8 if P.shape[0] else NFIELDS
+        self._check(self._L.vpmb200_upload(self._h, P.ctypes.data if n else None, ld, n, field_mask))
 
     def download(self, particles: np.ndarray, np_: int | None = None, field_mask: int = FM_ALL):
         P = _as_matrix(particles)
@@ -183,6 +186,32 @@ class Engine:
         self._check(self._L.vpmb200_uj_probe(self._h, Xp.ctypes.data, m, Uo.ctypes.data,
                                              Jo.ctypes.data if want_J else None))
         return (Uo, Jo) if want_J else Uo
+
+    def uj_probe_ex(self, Xp: np.ndarray, fsgm: float = 1.0, mirror: bool = False, want_J: bool = False):
+        """Vvpm_on_Xs with its `fsgm` (reference quirk reproduced) and `mirror` options (include/vpmb200.h)."""
+        Xp = np.ascontiguousarray(Xp, dtype=np.float64).reshape(-1, 3)
+        m = Xp.shape[0]
+        Uo = np.zeros((m, 3))
+        Jo = np.zeros((m, 9)) if want_J else None
+        self._check(self._L.vpmb200_uj_probe_ex(self._h, Xp.ctypes.data, m, float(fsgm), int(mirror), Uo.ctypes.data,
+                                                Jo.ctypes.data if want_J else None))
+        return (Uo, Jo) if want_J else Uo
+
+    def set_statics(self, cols: np.ndarray, generation: int | None = None):
+        """Park the step's static particles behind the field (vpmb200_set_statics); generation defaults to the current nt."""
+        P = _as_matrix(np.atleast_2d(cols)) if len(cols) else np.zeros((0, NFIELDS))
+        gen = self.get_time()[1] if generation is None else int(generation)
+        self._check(self._L.vpmb200_set_statics(self._h, P.ctypes.data if P.shape[0] else None, P.strides[0] // 8 if P.shape[0] else NFIELDS,
+                                                P.shape[0], gen))
+
+    def get_statics(self):
+        n, g = C.c_int64(), C.c_int64()
+        self._check(self._L.vpmb200_get_statics(self._h, C.byref(n), C.byref(g)))
+        return n.value, g.value
+
+    def set_mirror(self, enabled: bool, X0=(0.0, 0.0, 0.0), normal=(0.0, 0.0, 1.0)):
+        a, b = (C.c_double * 3)(*[float(v) for v in X0]), (C.c_double * 3)(*[float(v) for v in normal])
+        self._check(self._L.vpmb200_set_mirror(self._h, int(enabled), a, b))
 
     def sfs(self, a: float = 1.0, b: float = 1.0):
         self._check(self._L.vpmb200_sfs(self._h, float(a), float(b)))

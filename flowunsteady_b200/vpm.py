@@ -349,6 +349,7 @@ class ParticleField:
         self._host_dirty = True     # host matrix holds changes (to rows the device already has) the device has not seen
         self._dev_dirty = 0         # field-group mask the device holds newer than the host
         self._dev_np = 0            # particles the device holds; rows [_dev_np, np) are host-side appends not yet sent
+        self._statics = None        # (columns, nt) of the static-particle fast path (set_statics)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.h2d_seconds = 0.0      # wall time inside upload calls
@@ -453,10 +454,31 @@ class ParticleField:
             self.d2h_bytes += n * 8 * _rows(mask)
         self._dev_dirty &= ~mask
 
+    # ---- static-particle fast path (simulation.jl:355-365 without add_particle / remove_particle) ------------------
+    def set_statics(self, cols):
+        """The embedded (static) particles of the CURRENT step — what `static_particles_function(pfield, t, dt)` would append
+        (simulation.jl:355) — as an (n, 43) block of particle columns.  They are parked device-side behind the field for the
+        next `nextstep` / `UJ` / `U_at` of this step and never enter `particles` (include/vpmb200.h: vpmb200_set_statics)."""
+        cols = np.ascontiguousarray(np.atleast_2d(np.asarray(cols, dtype=np.float64)))
+        if cols.shape[0] and cols.shape[1] != NFIELDS:
+            raise ValueError("static particles must be (n, 43) particle columns")
+        if self.np + cols.shape[0] > self.maxparticles:
+            raise RuntimeError(f"PARTICLE OVERFLOW. Max number of particles {self.maxparticles} has been reached")
+        self._statics = (cols.copy(), self.nt) if cols.shape[0] else None
+
+    def _apply_statics(self):
+        """After the field itself is on the device: park the step's statics behind it (a stale set is dropped)."""
+        if self._statics is not None and self._statics[1] == self.nt:
+            self._engine.set_statics(self._statics[0], self.nt)
+            self.h2d_bytes += self._statics[0].shape[0] * 8 * NFIELDS
+        else:
+            self._statics = None
+
     # ---- hot-path entry points (called by the scheme objects) -----------------------------------------------------
     def _call_uj(self, uj_id: int, reset: bool, reset_sfs: bool, sfs: bool):
         self._engine.set_schemes(self._schemes(uj_id))
         self._push(_E.FM_ALL if not (reset and reset_sfs) else _E.FM_STATE | _E.FM_SFS | _E.FM_U | _E.FM_J)
+        self._apply_statics()
         self._engine.uj(reset, reset_sfs, sfs)
         self._pulled(_E.FM_U | _E.FM_J | _E.FM_PSE | (_E.FM_SFS if (sfs or reset_sfs) else 0))
 
@@ -477,7 +499,9 @@ class ParticleField:
             raise NotImplementedError("custom_UJ cannot run inside the GPU engine")
         self._engine.set_schemes(self._schemes(self._uj_id(), integration_id))
         self._push(_E.FM_STATE | _E.FM_M)
-        self._engine.nextstep(dt, tuple(self.Uinf(self.t)), relax)
+        self._apply_statics()
+        self._engine.nextstep(dt, tuple(self.Uinf(self.t)), relax)     # consumes the static set
+        self._statics = None
         self._pulled(_E.FM_ALL & ~(_E.FM_VOL | _E.FM_CIRCULATION | _E.FM_STATIC))
 
     # ---- wake treatments / monitors on the device ---------------------------------------------------------------
@@ -498,10 +522,17 @@ class ParticleField:
         return self._engine.monitors()
 
     # ---- probes: Vvpm_on_Xs without evaluating every target (simulation.jl:494-570) -------------------------------
-    def U_at(self, Xs, want_J: bool = False):
+    def U_at(self, Xs, want_J: bool = False, fsgm: float = 1.0, mirror: bool = False):
+        """Vvpm_on_Xs(pfield, Xs; fsgm, mirror) (simulation.jl:494-570) on the probe fast path; the static set given with
+        `set_statics` stands in for `static_particles_fun`."""
         self._engine.set_schemes(self._schemes(_E.UJ_IDS["direct"]))
         self._push(_E.FM_STATE)
-        return self._engine.uj_probe(np.asarray(Xs, dtype=np.float64), want_J)
+        self._apply_statics()
+        return self._engine.uj_probe_ex(np.asarray(Xs, dtype=np.float64), fsgm, mirror, want_J)
+
+    def set_mirror(self, enabled: bool, X0=(0.0, 0.0, 0.0), normal=(0.0, 0.0, 1.0)):
+        """run_simulation's mirror / mirror_X / mirror_normal (simulation.jl:149-151): images join the static set on the device."""
+        self._engine.set_mirror(enabled, X0, normal)
 
     def fluiddomain(self, Xs, method: str = "direct"):
         """U and W = curl u at arbitrary nodes (what vpm.computefluiddomain evaluates on its grids,

@@ -196,6 +196,30 @@ int32_t vpmb200_uj(vpmb200_handle h, int32_t reset, int32_t reset_sfs, int32_t s
  * targets.  U: 3 x m.  J: 9 x m or NULL. */
 int32_t vpmb200_uj_probe(vpmb200_handle h, const double* X, int64_t m, double* U, double* J);
 
+/* The same with Vvpm_on_Xs's two options (simulation.jl:494-570):
+ *   fsgm   — `sigmafactor_vpmonvlm`.  The reference's loop (simulation.jl:507-513, undone at :555-561) indexes the particle
+ *            matrix with ONE subscript, so it multiplies sigma of the FIRST particle by fsgm once per static particle present
+ *            in the field when it runs (normally none — the statics are added after it — which makes the option a no-op in
+ *            the reference).  Reproduced literally, including the k sequential roundings of *= and /=.
+ *   mirror — method of images in the plane set with vpmb200_set_mirror: images of every source (field, statics, and the images
+ *            vpmb200_set_mirror(enabled) already added) join the sources for this call (simulation.jl:518-535).
+ * The static set parked with vpmb200_set_statics takes the place of `static_particles_fun(pfield, t, dt)`. */
+int32_t vpmb200_uj_probe_ex(vpmb200_handle h, const double* X, int64_t m, double fsgm, int32_t mirror, double* U, double* J);
+
+/* Static-particle fast path.  FLOWUnsteady appends the embedded (static) particles to the field before every nextstep and
+ * removes them after it (simulation.jl:355-365), and again around every probe evaluation (:515).  vpmb200_set_statics parks
+ * the n columns `cols` (leading dimension ld; their static flag is forced to 1) device-side BEHIND the field instead:
+ * vpmb200_nextstep (which consumes the set), vpmb200_uj and vpmb200_uj_probe[_ex] treat them as part of the field while the
+ * field's step counter nt equals `generation` — a set left over from another step is ignored.  Any call that changes the
+ * field's particles (upload, add, remove) drops the set.  Equivalent to add_particle x n -> call -> remove_particle x n. */
+int32_t vpmb200_set_statics(vpmb200_handle h, const double* cols, int64_t ld, int64_t n, int64_t generation);
+int32_t vpmb200_get_statics(vpmb200_handle h, int64_t* n, int64_t* generation);
+/* Method of images (run_simulation's mirror, mirror_X, mirror_normal; vehicle_vlm_unsteady.jl:245-260): while enabled, the
+ * image of EVERY particle (field + static set) joins the static set wherever that set is used, built on the device with the
+ * reference's expressions  Xm = X - dot(2 (X - X0), n) n,  Gm = 2 dot(G, n) G / |G| - G  (sic).  Needs max_particles >= twice
+ * the particle count.  The plane is stored even when enabled = 0 (vpmb200_uj_probe_ex's mirror flag uses it). */
+int32_t vpmb200_set_mirror(vpmb200_handle h, int32_t enabled, const double* X0, const double* normal);
+
 /* pfield.SFS(pfield; a, b): evaluates U, J (+ SFS, C_d) as the SFS scheme prescribes for RK coefficients (a, b). */
 int32_t vpmb200_sfs(vpmb200_handle h, double a, double b);
 

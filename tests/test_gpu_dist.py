@@ -1,4 +1,7 @@
-"""2-GPU NCCL test of the sharded direct path against the single-GPU engine (skipped when < 2 GPUs are visible)."""
+"""2-GPU NCCL tests of the sharded field against the single-GPU engine (skipped when < 2 GPUs are visible): the direct path
+(all-gather of source tiles) and UJ_fmm with the local essential tree (all-to-all of particle rows, all-gather of skeletons /
+multipoles / records, inverse all-to-all) and with round 1's replicated tree.  The same LET logic runs on ONE GPU with
+in-process collectives in tests/test_gpu_let.py."""
 import os
 import socket
 
@@ -17,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, kw, out_dir):
+def _worker(rank, world, port, n, kw, out_dir, fmm_mode="let"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -32,7 +35,7 @@ def _worker(rank, world, port, n, kw, out_dir):
         lo, hi = partition(n, world)[rank]
         eng = fb.Engine(hi - lo + 8, device=rank, schemes=fb.default_schemes(**kw))
         eng.upload(P[lo:hi].copy())
-        sf = ShardedField(eng, max_local=hi - lo + 8, device=f"cuda:{rank}")
+        sf = ShardedField(eng, max_local=hi - lo + 8, device=f"cuda:{rank}", fmm=fmm_mode)
         for _ in range(2):
             sf.nextstep(2e-3, (1.0, -0.5, 0.25), relax=True)
         eng.synchronize()
@@ -42,17 +45,20 @@ def _worker(rank, world, port, n, kw, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kw", [dict(integration="rungekutta3"),
-                                dict(integration="rungekutta3", sfs="dynamic", force_positive=1, clippings=1),
-                                dict(integration="rungekutta3", uj="fmm", fmm_nonzero_sigma=1, sfs="constant", clippings=1)])
-def test_two_gpu_matches_one_gpu(kw, tmp_path):
+@pytest.mark.parametrize("kw,fmm_mode", [
+    (dict(integration="rungekutta3"), "let"),
+    (dict(integration="rungekutta3", sfs="dynamic", force_positive=1, clippings=1), "let"),
+    (dict(integration="rungekutta3", uj="fmm", fmm_nonzero_sigma=1, sfs="constant", clippings=1), "let"),
+    (dict(integration="rungekutta3", uj="fmm", sfs="dynamic", force_positive=1, clippings=1), "let"),
+    (dict(integration="rungekutta3", uj="fmm", fmm_nonzero_sigma=1, sfs="constant", clippings=1), "replicated")])
+def test_two_gpu_matches_one_gpu(kw, fmm_mode, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
     import flowunsteady_b200 as fb
     n = 3001
-    mp.spawn(_worker, args=(2, _free_port(), n, kw, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n, kw, str(tmp_path), fmm_mode), nprocs=2, join=True)
     x, g, s, static = mixed_field(n, seed=23)
     g = g * 50.0
     static = np.where(np.all(g == 0, axis=1), 1.0, static)

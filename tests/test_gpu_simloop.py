@@ -24,16 +24,26 @@ def _script(rng, nsteps=3, nshed=40, nstatic=12, nprobe=9):
     return steps
 
 
-def _run_engine(steps, dt, Uinf, sfs, integration):
+def _static_cols(X, G, s):
+    c = np.zeros((X.shape[0], 43))
+    c[:, 0:3], c[:, 3:6], c[:, 6], c[:, 8], c[:, 42] = X, G, s, np.linalg.norm(G, axis=1), 1.0
+    return c
+
+
+def _run_engine(steps, dt, Uinf, sfs, integration, fast_statics=False, sync="always"):
     from flowunsteady_b200 import vpm, wake
     pf = vpm.ParticleField(2000, Uinf=lambda t: Uinf, UJ=vpm.UJ_direct, SFS=sfs, integration=integration,
-                           relaxation=vpm.pedrizzetti)
+                           relaxation=vpm.pedrizzetti, sync=sync)
     sim = types.SimpleNamespace(nt=0, vehicle=types.SimpleNamespace(system=types.SimpleNamespace(O=np.zeros(3))))
     treatment = wake.remove_particles_sphere(1.2 ** 2, 1, Xoff=[0.3, 0.5, 0.5])
     V = []
     for k, st in enumerate(steps):
         org_np = vpm.get_np(pf)
-        if k > 0:
+        if k > 0 and fast_statics:
+            pf.set_statics(_static_cols(*st["statics"]))               # parked behind the field, consumed by nextstep
+            vpm.nextstep(pf, dt, relax=True)
+            assert vpm.get_np(pf) == org_np and pf.engine.get_statics()[0] == 0
+        elif k > 0:
             for X, G, s in zip(*st["statics"]):
                 vpm.add_particle(pf, X, G, s, vol=0, circulation=np.linalg.norm(G), static=True)
             vpm.nextstep(pf, dt, relax=True)
@@ -54,6 +64,8 @@ def _run_engine(steps, dt, Uinf, sfs, integration):
         V.append(Vref)
         sim.nt = k
         treatment(sim, pf, pf.t, dt)
+    if sync == "lazy":
+        pf.pull()
     return pf.particles[:pf.np].copy(), np.array(V), pf.t, pf.nt
 
 
@@ -118,6 +130,103 @@ def test_simulation_loop_matches_oracle(variant):
     assert np.allclose(Pg[:, 7:9], Po[:, 7:9], rtol=1e-14) and np.array_equal(Pg[:, 42], Po[:, 42])
 
 
+@pytest.mark.parametrize("sync", ["always", "lazy"])
+def test_static_particle_fast_path_matches_add_nextstep_remove(sync):
+    """vpmb200_set_statics (the static set parked device-side, consumed by nextstep) against the reference's own sequence
+    add_particle x n -> nextstep -> remove_particle x n (simulation.jl:355-365) and against the oracle replay of that loop."""
+    from flowunsteady_b200 import vpm
+    steps = _script(np.random.default_rng(11))
+    dt, Uinf = 0.02, (1.0, 0.0, 0.1)
+    slow = _run_engine(steps, dt, Uinf, vpm.SFS_none, vpm.rungekutta3)
+    fast = _run_engine(steps, dt, Uinf, vpm.SFS_none, vpm.rungekutta3, fast_statics=True, sync=sync)
+    assert fast[0].shape == slow[0].shape and fast[2:] == slow[2:]
+    for sl in (slice(0, 9), slice(9, 12), slice(15, 24), slice(42, 43)):
+        assert np.array_equal(fast[0][:, sl], slow[0][:, sl])           # same kernels, same order of sources: same bits
+    assert np.array_equal(fast[1], slow[1])
+    exp = _run_oracle(steps, dt, Uinf, dict(integration="rungekutta3"))
+    for sl in (slice(0, 3), slice(3, 6), slice(6, 7), slice(9, 12), slice(15, 24)):
+        assert relmax(fast[0][:, sl], exp[0][:, sl]) < 1e-11
+
+
+def test_probe_statics_fsgm_quirk_and_mirror_vs_oracle_replay():
+    """Vvpm_on_Xs(pfield, Xs; static_particles_fun, fsgm, mirror) (simulation.jl:494-570) through vpmb200_uj_probe_ex:
+    the reference's sequence replayed literally on a numpy matrix with the oracle's UJ — including the single-subscript
+    `particles[SIGMA_INDEX] *= fsgm` that scales the FIRST particle's core once per static particle in the field."""
+    import flowunsteady_b200 as fb
+    from oracle import oracle as o
+    from tests.util import mixed_field
+    x, g, s, static = mixed_field(700, seed=8)
+    g = g * 30 + 1e-9
+    static[:] = 0
+    static[[5, 90, 400]] = 1                                            # three statics IN the field: sigma[0] *= fsgm^3
+    P = fb.new_particles(x, g, s, static=static)
+    rng = np.random.default_rng(3)
+    statics = _static_cols(rng.random((20, 3)), rng.standard_normal((20, 3)) * 0.01, np.full(20, 0.07))
+    probes = rng.random((33, 3))
+    X0, nrm, fsgm = np.array([0.5, 0.5, -0.2]), np.array([0.0, 0.6, 0.8]), 5.5
+
+    def images(Q):                                                      # vehicle_vlm_unsteady.jl:248-258, simulation.jl:520-533
+        out = np.zeros_like(Q)
+        for i in range(Q.shape[0]):
+            X, G = Q[i, 0:3], Q[i, 3:6]
+            a = 2 * (X - X0)
+            d = a[0] * nrm[0] + a[1] * nrm[1] + a[2] * nrm[2]
+            gn = G[0] * nrm[0] + G[1] * nrm[1] + G[2] * nrm[2]
+            out[i, 0:3] = X - d * nrm
+            out[i, 3:6] = 2 * gn * G / np.sqrt(G[0] * G[0] + G[1] * G[1] + G[2] * G[2]) - G
+            out[i, 6:9], out[i, 36:39], out[i, 42] = Q[i, 6:9], Q[i, 36:39], 1.0
+        return out
+
+    for static_mirror in (False, True):
+        for probe_mirror in (False, True):
+            Q = P.copy()
+            k = int((Q[:, 42] > 0).sum())
+            for _ in range(k):
+                Q[0, 6] *= fsgm
+            S = np.concatenate([Q, statics])
+            if static_mirror:
+                S = np.concatenate([S, images(S)])
+            if probe_mirror:
+                S = np.concatenate([S, images(S)])
+            Uo, Jo = o.uj_direct("gaussianerf", S[:, 0:3], S[:, 3:6], S[:, 6], probes, accum=1)
+            with fb.Engine(4 * (P.shape[0] + 20) + 8, schemes=fb.default_schemes()) as eng:
+                eng.upload(P)
+                eng.set_mirror(static_mirror, X0, nrm)
+                eng.set_statics(statics)
+                Ug, Jg = eng.uj_probe_ex(probes, fsgm=fsgm, mirror=probe_mirror, want_J=True)
+                after = eng.download(np.zeros_like(P))
+                assert eng.np == P.shape[0] and eng.get_statics()[0] == 20        # probes do not consume the set
+            assert relmax(Ug, Uo) < 1e-12 and relmax(Jg, Jo) < 1e-12
+            s0 = P[0, 6]
+            for _ in range(k):
+                s0 *= fsgm
+            for _ in range(k):
+                s0 /= fsgm
+            assert after[0, 6] == s0 and np.array_equal(after[1:, 6], P[1:, 6])    # the reference's round trip, bit for bit
+
+
+def test_stale_static_set_is_ignored_and_mutation_drops_it():
+    import flowunsteady_b200 as fb
+    from tests.util import mixed_field
+    x, g, s, _ = mixed_field(300, seed=1)
+    P = fb.new_particles(x, g * 30 + 1e-9, s)
+    statics = _static_cols(x[:10] + 0.01, g[:10], s[:10])
+    with fb.Engine(400, schemes=fb.default_schemes()) as eng:
+        eng.upload(P)
+        eng.uj()
+        base = eng.download(np.zeros_like(P))
+        eng.set_statics(statics, generation=7)                                    # belongs to another step: never used
+        eng.uj()
+        assert np.array_equal(eng.download(np.zeros_like(P)), base) and eng.get_statics()[0] == 0
+        eng.set_statics(statics)
+        eng.uj()
+        assert not np.array_equal(eng.download(np.zeros_like(P))[:, 9:12], base[:, 9:12])
+        eng.add_particles(P[:1])                                                   # the columns behind np change hands
+        assert eng.get_statics() == (0, -1)
+        with pytest.raises(fb.EngineError):
+            eng.set_statics(np.zeros((200, 43)))                                   # capacity
+
+
 def test_lazy_sync_keeps_field_on_device():
     """sync='lazy': no host traffic between calls until pull(); results equal the always-synchronised field."""
     import flowunsteady_b200 as fb
@@ -169,7 +278,7 @@ def test_lazy_sync_with_shedding_and_removal_between_steps():
             pf.pull()
         outs.append(pf.particles[:pf.np].copy())
         traffic.append(pf.h2d_bytes)
-    assert outs[0].shape == outs[1].shape == (896, 43)
+    assert outs[0].shape == outs[1].shape == (894, 43)      # 600 + 3 x 100 shed - 3 x 2 removed
     assert np.array_equal(outs[0], outs[1])
     assert traffic[1] < traffic[0] / 3
 
