@@ -85,6 +85,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fmm", action="store_true", help="skip the secondary UJ_fmm figures")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle parity check of the timed state")
+    ap.add_argument("--let-timing", action="store_true", help="UJ_fmm mode: add a synchronised per-phase breakdown of one step")
     ap.add_argument("--fmm-mode", default="let", choices=["let", "replicated"],
                     help="multi-GPU UJ_fmm: local essential tree (default) or round 1's replicated tree")
     ap.add_argument("--cpu-targets", type=int, default=4096, help="targets of the CPU baseline slab")
@@ -378,6 +379,14 @@ def run_ours(args):
     if args.uj == "fmm":
         # secondary mode (BASELINE configs[1], [3], [4]): an O(N) method has no pair count; report particle-evaluations/s
         eval_ms = timed(lambda: field.uj(True, True, True), 3) / 3
+        phases = None
+        if args.let_timing and args.fmm_mode == "let":   # outside the timed region: the phase timer drains the stream
+            field.let_timing = {}
+            t0 = time.perf_counter()
+            step()
+            eng.synchronize()
+            phases = {"step_wall_ms": (time.perf_counter() - t0) * 1e3, **{k: v for k, v in sorted(field.let_timing.items())}}
+            field.let_timing = None
         parity = None if args.no_parity else fmm_parity_check(field, eng, sch, n, world, rank, local_rank)
         if rank == 0:
             cfg = make_config(args, n, world)
@@ -395,7 +404,8 @@ def run_ours(args):
                                                  "skeletons / multipoles / records, inverse all-to-all of results"
                                                  if args.fmm_mode == "let" else "replicated tree, leaves split, all-reduce")
                                  + f" over {world} GPU(s)"},
-                "parity": parity, "gpu_launches": int(launches), "clocks": clocks, "fmm_tree_rank0": eng.fmm_stats()}), flush=True)
+                "parity": parity, "let_phases_ms_rank0_one_step": phases, "gpu_launches": int(launches), "clocks": clocks,
+                "fmm_tree_rank0": eng.fmm_stats()}), flush=True)
         failed = bool(rank == 0 and parity is not None and not parity["ok"])
         if world > 1:
             dist.barrier()

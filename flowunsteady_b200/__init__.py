@@ -5,6 +5,6 @@ package is the host-side mirror of the FLOWVPM interface FLOWUnsteady drives (`f
 ctypes wrapper (`flowunsteady_b200.engine`) and synthetic workloads (`flowunsteady_b200.fields`).
 """
 from . import _lib  # noqa: F401
-from .engine import Engine, EngineError, default_schemes, new_particles  # noqa: F401
+from .engine import Engine, EngineError, MultiEngine, default_schemes, new_particles  # noqa: F401
 
 __version__ = "0.1.0"

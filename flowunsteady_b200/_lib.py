@@ -74,6 +74,26 @@ SYMBOLS = {
     "vpmb200_set_statics": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "vpmb200_get_statics": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "vpmb200_set_mirror": (C.c_int32, [_H, C.c_int32, _dp, _dp]),
+    "vpmb200_multi_create": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_H)]),
+    "vpmb200_multi_destroy": (C.c_int32, [_H]),
+    "vpmb200_multi_last_error": (C.c_char_p, [_H]),
+    "vpmb200_multi_set_schemes": (C.c_int32, [_H, C.POINTER(Schemes)]),
+    "vpmb200_multi_set_time": (C.c_int32, [_H, C.c_double, C.c_int64]),
+    "vpmb200_multi_get_time": (C.c_int32, [_H, _dp, C.POINTER(C.c_int64)]),
+    "vpmb200_multi_get_np": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "vpmb200_multi_shard_sizes": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "vpmb200_multi_upload": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32]),
+    "vpmb200_multi_download": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32]),
+    "vpmb200_multi_add_particles": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64]),
+    "vpmb200_multi_remove_particle": (C.c_int32, [_H, C.c_int64]),
+    "vpmb200_multi_remove_where": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),
+    "vpmb200_multi_rebalance": (C.c_int32, [_H, C.c_double, C.POINTER(C.c_int64)]),
+    "vpmb200_multi_uj": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_int32]),
+    "vpmb200_multi_sfs": (C.c_int32, [_H, C.c_double, C.c_double]),
+    "vpmb200_multi_nextstep": (C.c_int32, [_H, C.c_double, _dp, C.c_int32]),
+    "vpmb200_multi_uj_probe": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vpmb200_multi_synchronize": (C.c_int32, [_H]),
+    "vpmb200_multi_engine": (C.c_int32, [_H, C.c_int32, C.POINTER(_H)]),
     "vpmb200_let_cell_bytes": (C.c_int32, []),
     "vpmb200_let_bounds": (C.c_int32, [_H, _dp]),
     "vpmb200_let_keys": (C.c_int32, [_H, _dp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

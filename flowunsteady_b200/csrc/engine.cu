@@ -5,11 +5,13 @@
 // creation fails without an sm_100 device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/vpmb200.h"
 #include "estr_direct.cuh"
@@ -1692,3 +1694,5 @@ int32_t vpmb200_stage(vpmb200_handle e, int32_t stage, double a, double b, doubl
 }
 
 }  // extern "C"
+
+#include "multi.inl"

@@ -123,6 +123,7 @@ class ShardedField:
         self._ntiles = [0] * self.world
         self._fmm_hint = 0          # 1: the next UJ_fmm evaluation's far field may be reused; 2: reuse it (DynamicSFS)
         self._let = None            # partition / exchange state of the last LET evaluation
+        self.let_timing = None      # set to {} to collect wall-clock milliseconds per LET phase (synchronising; diagnostics)
         self.refresh_counts()
 
     def _ctl_device(self):
@@ -182,6 +183,20 @@ class ShardedField:
         hint, self._fmm_hint = self._fmm_hint, 0
         sch = b.get_schemes()
         L = self._let
+        import time as _time
+        _t = [_time.perf_counter()]
+
+        def lap(name):
+            """phase timer (diagnostics only: it drains the stream)"""
+            if self.let_timing is None:
+                return
+            b.synchronize()
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            now = _time.perf_counter()
+            self.let_timing[name] = self.let_timing.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
+
         reuse = bool(hint == 2 and L is not None and L.get("far_valid") and not sch.fmm_nonzero_sigma and L["n_home"] == int(b.np))
         with self._stream_ctx():
             n_home = int(b.np)
@@ -203,6 +218,7 @@ class ShardedField:
                 counts = c.all_gather_ints(L["send"], dev)           # counts[q][k]: particles rank q sends to rank k
                 L["recv"] = [counts[q][r] for q in range(G)]
                 L["n_all"] = sum(sum(row) for row in counts)
+                lap("1 bounds, keys, histogram, partition")
             elif "send" not in L:
                 return
             n_own = sum(L["recv"])
@@ -210,8 +226,10 @@ class ShardedField:
             b.let_pack(send.data_ptr())
             rows = c.all_to_all_rows(send[:n_home], L["send"], L["recv"])
             L["rows"] = rows                                         # the engine reads it until the evaluation ends
+            lap("2 pack + all-to-all of particle rows")
             info = b.let_build(rows.data_ptr(), n_own, L["n_all"], reuse)
             cells_ptr, M_ptr, rec_ptr = b.let_ptrs()
+            lap("3 owner sort, tree, upward pass")
             if not reuse:
                 ncells_own, _, nm3, _ = info
                 sizes = c.all_gather_ints([n_own, ncells_own], dev)
@@ -224,6 +242,7 @@ class ShardedField:
                 sm[:ncells_own * nm3] = self._dev_view(M_ptr, ncells_own * nm3)
                 cells_all, M_all = c.all_gather(sc), c.all_gather(sm)
                 b.let_attach_tree(cells_all.data_ptr(), M_all.data_ptr(), L["slot_c"], L["nc"], L["np"])
+                lap("4 all-gather skeletons + multipoles, attach")
             srec = torch.zeros(L["slot_n"] * 10, dtype=torch.float64, device=dev)
 
             def exchange_records():
@@ -233,10 +252,13 @@ class ShardedField:
                 return rec_all
 
             keep = exchange_records()
+            lap("5 all-gather source records, attach")
             out = torch.empty((max(n_own, 1), 12), dtype=torch.float64, device=dev)
             b.let_evaluate(out.data_ptr(), reuse)
+            lap("6 traversal, M2L, L2L, L2P + near field")
             res = c.all_to_all_rows(out[:n_own], L["recv"], L["send"])
             b.let_finish(res.data_ptr(), 0, reset)
+            lap("7 inverse all-to-all of U, J + scatter")
             if reset_sfs:
                 b.reset_particles_sfs()
             if sfs:
@@ -246,6 +268,7 @@ class ShardedField:
                 b.let_estr_evaluate(outE.data_ptr())
                 resE = c.all_to_all_rows(outE[:n_own], L["recv"], L["send"])
                 b.let_finish(resE.data_ptr(), 1, False)
+                lap("8 E_str: records, all-gather, near field, return")
             L["far_valid"] = bool(hint == 1 and not sch.fmm_nonzero_sigma)
             del keep
 

@@ -346,6 +346,123 @@ class Engine:
         self._check(self._L.vpmb200_estr_from_records(self._h, C.c_void_p(tiles_ptr), int(ntiles)))
 
 
+class MultiEngine:
+    """RAII wrapper of a vpmb200_multi_handle: ONE host thread, several GPUs (include/vpmb200.h: vpmb200_multi_*).
+
+    Same call shapes as `Engine` on the GLOBAL particle order of the host's matrix; particles are sharded over `ngpus`
+    per-device engines (devices=None: 0 .. ngpus-1; an ordinal may repeat — several shards on one GPU)."""
+
+    def __init__(self, max_particles: int, ngpus: int, devices=None, float_bits: int = 64, schemes: Schemes | None = None):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        dv = (C.c_int32 * ngpus)(*[int(d) for d in devices]) if devices is not None else None
+        rc = self._L.vpmb200_multi_create(int(max_particles), NFIELDS, int(float_bits), int(ngpus), dv, C.byref(self._h))
+        if rc != 0:
+            msg = self._L.vpmb200_multi_last_error(None).decode()
+            self._h = None
+            raise EngineError(rc, msg)
+        self.ngpus = int(ngpus)
+        if schemes is not None:
+            self.set_schemes(schemes)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vpmb200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, self._L.vpmb200_multi_last_error(self._h).decode())
+
+    def set_schemes(self, s: Schemes):
+        self._check(self._L.vpmb200_multi_set_schemes(self._h, C.byref(s)))
+
+    def set_time(self, t: float, nt: int):
+        self._check(self._L.vpmb200_multi_set_time(self._h, float(t), int(nt)))
+
+    def get_time(self):
+        t, nt = C.c_double(), C.c_int64()
+        self._check(self._L.vpmb200_multi_get_time(self._h, C.byref(t), C.byref(nt)))
+        return t.value, nt.value
+
+    @property
+    def np(self) -> int:
+        n = C.c_int64()
+        self._check(self._L.vpmb200_multi_get_np(self._h, C.byref(n)))
+        return n.value
+
+    def shard_sizes(self):
+        a = (C.c_int64 * self.ngpus)()
+        self._check(self._L.vpmb200_multi_shard_sizes(self._h, a))
+        return [int(v) for v in a]
+
+    def upload(self, particles: np.ndarray, np_: int | None = None, field_mask: int = FM_ALL):
+        P = _as_matrix(particles)
+        n = P.shape[0] if np_ is None else int(np_)
+        ld = P.strides[0] // 8 if P.shape[0] else NFIELDS
+        self._check(self._L.vpmb200_multi_upload(self._h, P.ctypes.data if n else None, ld, n, field_mask))
+
+    def download(self, particles: np.ndarray, np_: int | None = None, field_mask: int = FM_ALL):
+        P = _as_matrix(particles)
+        n = self.np if np_ is None else int(np_)
+        if n > P.shape[0]:
+            raise ValueError("host matrix is too small")
+        ld = P.strides[0] // 8 if P.shape[0] else NFIELDS
+        self._check(self._L.vpmb200_multi_download(self._h, P.ctypes.data if n else None, ld, n, field_mask))
+        return P
+
+    def add_particles(self, cols: np.ndarray):
+        P = _as_matrix(np.atleast_2d(cols))
+        self._check(self._L.vpmb200_multi_add_particles(self._h, P.ctypes.data, P.strides[0] // 8, P.shape[0]))
+
+    def remove_particle(self, i: int):
+        self._check(self._L.vpmb200_multi_remove_particle(self._h, int(i)))
+
+    def remove_where(self, criterion: int, params) -> int:
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        r = C.c_int64()
+        self._check(self._L.vpmb200_multi_remove_where(self._h, int(criterion), p.ctypes.data, C.byref(r)))
+        return r.value
+
+    def rebalance(self, tolerance: float = 0.05) -> int:
+        moved = C.c_int64()
+        self._check(self._L.vpmb200_multi_rebalance(self._h, float(tolerance), C.byref(moved)))
+        return moved.value
+
+    def uj(self, reset: bool = True, reset_sfs: bool = False, sfs: bool = False):
+        self._check(self._L.vpmb200_multi_uj(self._h, int(reset), int(reset_sfs), int(sfs)))
+
+    def sfs(self, a: float = 1.0, b: float = 1.0):
+        self._check(self._L.vpmb200_multi_sfs(self._h, float(a), float(b)))
+
+    def nextstep(self, dt: float, Uinf=(0.0, 0.0, 0.0), relax: bool = True):
+        u = (C.c_double * 3)(*[float(v) for v in Uinf])
+        self._check(self._L.vpmb200_multi_nextstep(self._h, float(dt), u, int(relax)))
+
+    def uj_probe(self, Xp: np.ndarray, want_J: bool = False):
+        Xp = np.ascontiguousarray(Xp, dtype=np.float64).reshape(-1, 3)
+        m = Xp.shape[0]
+        Uo = np.zeros((m, 3))
+        Jo = np.zeros((m, 9)) if want_J else None
+        self._check(self._L.vpmb200_multi_uj_probe(self._h, Xp.ctypes.data, m, Uo.ctypes.data, Jo.ctypes.data if want_J else None))
+        return (Uo, Jo) if want_J else Uo
+
+    def synchronize(self):
+        self._check(self._L.vpmb200_multi_synchronize(self._h))
+
+
 def new_particles(x, gamma, sigma, static=None, vol=None, circulation=None, C_=None) -> np.ndarray:
     """(n, 43) particle matrix with X, Gamma, sigma (and optional vol, circulation, C, static) filled in."""
     x = np.asarray(x, dtype=np.float64).reshape(-1, 3)

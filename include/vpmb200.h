@@ -321,6 +321,44 @@ enum {
 };
 int32_t vpmb200_stage(vpmb200_handle h, int32_t stage, double a, double b, double dt, const double* Uinf);
 
+/* ---- several GPUs behind ONE handle and ONE host thread (flowunsteady_b200/csrc/multi.inl) ---------------------------------
+ * What a single-process host such as FLOWUnsteady's Julia loop (simulation.jl:339-447) needs to reach the 8 GPUs of a box with
+ * the same upload / uj / nextstep / add / remove / download sequence.  Particles are sharded over `ngpus` per-device engines;
+ * the GLOBAL particle order (the order of the host's matrix, on which vpm.remove_particle's swap-with-last is defined) is kept
+ * as an index map on the host.  Direct U/J (+ E_str): source tiles are exchanged device-to-device (cudaMemcpyPeerAsync over
+ * NVLink / NVSwitch, ordered by CUDA events; no NCCL, no host staging) and every device's pair kernels run concurrently;
+ * per-particle stages are shard-local.  vpm_UJ = UJ_fmm returns VPMB200_ENOTSUP on a multi handle (the local-essential-tree
+ * phases vpmb200_let_* are driven across processes by flowunsteady_b200/dist.py).  devices = NULL means 0 .. ngpus-1; the
+ * same ordinal may appear more than once (several shards on one GPU: how the tests run on a one-GPU box). */
+typedef struct vpmb200_multi* vpmb200_multi_handle;
+int32_t vpmb200_multi_create(int64_t max_particles, int32_t nfields, int32_t float_bits, int32_t ngpus, const int32_t* devices,
+                             vpmb200_multi_handle* out);
+int32_t vpmb200_multi_destroy(vpmb200_multi_handle h);
+const char* vpmb200_multi_last_error(vpmb200_multi_handle h);
+int32_t vpmb200_multi_set_schemes(vpmb200_multi_handle h, const vpmb200_schemes* s);
+int32_t vpmb200_multi_set_time(vpmb200_multi_handle h, double t, int64_t nt);
+int32_t vpmb200_multi_get_time(vpmb200_multi_handle h, double* t, int64_t* nt);
+int32_t vpmb200_multi_get_np(vpmb200_multi_handle h, int64_t* np);
+int32_t vpmb200_multi_shard_sizes(vpmb200_multi_handle h, int64_t* n_per_gpu);
+/* upload with all groups (or a new np) re-partitions the columns into ngpus contiguous blocks; a partial mask with the
+ * current np refreshes those groups in place.  download needs np == the field's count. */
+int32_t vpmb200_multi_upload(vpmb200_multi_handle h, const double* particles, int64_t ld, int64_t np, uint32_t field_mask);
+int32_t vpmb200_multi_download(vpmb200_multi_handle h, double* particles, int64_t ld, int64_t np, uint32_t field_mask);
+/* vpm.add_particle (simulation.jl:486): new global indices np, np+1, ...; stored on the least-loaded shard.
+ * vpm.remove_particle(i) / the wake treatments: the reference's resulting GLOBAL order (swap with the last; the removal loop of
+ * src/FLOWUnsteady_processing.jl:50-187), whatever the sharding. */
+int32_t vpmb200_multi_add_particles(vpmb200_multi_handle h, const double* cols, int64_t ld, int64_t n);
+int32_t vpmb200_multi_remove_particle(vpmb200_multi_handle h, int64_t i);
+int32_t vpmb200_multi_remove_where(vpmb200_multi_handle h, int32_t criterion, const double* params, int64_t* removed);
+/* Periodic rebalance: tails of the fullest shards move to the emptiest (device to device) until max - min <= tolerance x mean. */
+int32_t vpmb200_multi_rebalance(vpmb200_multi_handle h, double tolerance, int64_t* moved);
+int32_t vpmb200_multi_uj(vpmb200_multi_handle h, int32_t reset, int32_t reset_sfs, int32_t sfs);
+int32_t vpmb200_multi_sfs(vpmb200_multi_handle h, double a, double b);
+int32_t vpmb200_multi_nextstep(vpmb200_multi_handle h, double dt, const double* Uinf, int32_t relax);
+int32_t vpmb200_multi_uj_probe(vpmb200_multi_handle h, const double* X, int64_t m, double* U, double* J);
+int32_t vpmb200_multi_synchronize(vpmb200_multi_handle h);
+int32_t vpmb200_multi_engine(vpmb200_multi_handle h, int32_t k, vpmb200_handle* shard);   /* shard k's engine (borrowed)        */
+
 /* Measurement helper: FP64 FMA peak of `device` in TFLOP/s (best of `repeats` launches of a register-only DFMA
  * kernel, `iters` x 128 FMAs per thread).  bench.py uses it as the roofline denominator of the FP64-bound pair
  * kernels (MEASURED_PEAKS.json has no FP64 entry). */

@@ -123,7 +123,8 @@ def test_let_rk3_dynamic_sfs_steps_match_one_gpu(world):
     ref = _single(P, kw, steps)
     got = _sharded(P, kw, world, steps)
     _assert_same(got, ref, ["X", "U", "J"], 1e-11)
-    _assert_same(got, ref, ["Gamma", "sigma", "C"], 1e-9)   # through the dynamic procedure
+    # through the dynamic procedure: 1e-12 x 1/(1 - alpha) = 1e-9 per evaluation, two steps (measured 1.1e-9 on C)
+    _assert_same(got, ref, ["Gamma", "sigma", "C"], 5e-9)
 
 
 def test_let_accumulate_flag():
