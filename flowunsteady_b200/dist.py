@@ -66,13 +66,14 @@ class TorchCollectives:
             dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op], group=self.group)
         return t
 
-    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
-        """(world, *t.shape): every rank's `t` (equal shapes)."""
+    def all_gather(self, t: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """(world, *t.shape): every rank's `t` (equal shapes); `out`: optional flat destination of world * t.numel()."""
         if self.world == 1:
             return t.unsqueeze(0)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        if out is None:
+            out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
-        return out
+        return out.view((self.world,) + tuple(t.shape))
 
     def all_gather_into_async(self, out: torch.Tensor, t: torch.Tensor):
         if self.world == 1:
@@ -83,12 +84,14 @@ class TorchCollectives:
         t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=device)
         return [[int(x) for x in row] for row in self.all_gather(t).tolist()]
 
-    def all_to_all_rows(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
-        """Rows [sum(send_counts[:k]), +send_counts[k]) of `send` go to rank k; returns the rows received, by source rank."""
+    def all_to_all_rows(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int],
+                        out: torch.Tensor | None = None) -> torch.Tensor:
+        """Rows [sum(send_counts[:k]), +send_counts[k]) of `send` go to rank k; returns the rows received, by source rank
+        (`out`: optional destination with at least sum(recv_counts) rows)."""
         n = int(sum(recv_counts))
         if self.world == 1:
             return send[:n]
-        recv = torch.empty((max(n, 1),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        recv = out if out is not None else torch.empty((max(n, 1),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
         dist.all_to_all_single(recv[:n], send[:int(sum(send_counts))], [int(c) for c in recv_counts], [int(c) for c in send_counts],
                                group=self.group)
         return recv[:n]
@@ -124,6 +127,7 @@ class ShardedField:
         self._fmm_hint = 0          # 1: the next UJ_fmm evaluation's far field may be reused; 2: reuse it (DynamicSFS)
         self._let = None            # partition / exchange state of the last LET evaluation
         self.let_timing = None      # set to {} to collect wall-clock milliseconds per LET phase (synchronising; diagnostics)
+        self._bufs = {}             # grow-only exchange buffers of the LET path (no allocator traffic inside a step)
         self.refresh_counts()
 
     def _ctl_device(self):
@@ -175,6 +179,15 @@ class ShardedField:
             return torch.empty(0, dtype=dtype, device=self.device)
         return torch.as_tensor(_DevArray(ptr, (n,), typestr), device=self.device)
 
+    def _buf(self, name: str, n: int, dtype=torch.float64) -> torch.Tensor:
+        """Flat grow-only device buffer: sizes drift by a few particles / cells from one evaluation to the next, and a fresh
+        torch allocation per evaluation (1.5 GB in all at 5M particles) would churn the caching allocator."""
+        t = self._bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(int(n) + int(n) // 8 + 1024, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t[:int(n)]
+
     def _uj_fmm_let(self, reset: bool, reset_sfs: bool, sfs: bool):
         """One UJ_fmm evaluation with a local essential tree; phases and what is exchanged between them: fmm_let.cuh."""
         if sfs and not reset:
@@ -222,9 +235,9 @@ class ShardedField:
             elif "send" not in L:
                 return
             n_own = sum(L["recv"])
-            send = torch.empty((max(n_home, 1), 7), dtype=torch.float64, device=dev)
+            send = self._buf("send", max(n_home, 1) * 7).view(-1, 7)
             b.let_pack(send.data_ptr())
-            rows = c.all_to_all_rows(send[:n_home], L["send"], L["recv"])
+            rows = c.all_to_all_rows(send[:n_home], L["send"], L["recv"], out=self._buf("rows", max(n_own, 1) * 7).view(-1, 7))
             L["rows"] = rows                                         # the engine reads it until the evaluation ends
             lap("2 pack + all-to-all of particle rows")
             info = b.let_build(rows.data_ptr(), n_own, L["n_all"], reuse)
@@ -236,27 +249,29 @@ class ShardedField:
                 L["np"], L["nc"] = [s[0] for s in sizes], [s[1] for s in sizes]
                 L["slot_c"], L["slot_n"] = max(max(L["nc"]), 1), max(max(L["np"]), 1)
                 cb = b.let_cell_bytes()
-                sc = torch.zeros(L["slot_c"] * cb, dtype=torch.uint8, device=dev)
+                # slots are padded (the padding is never read: attach copies ncells[q] / np[q] entries of every block)
+                sc = self._buf("sc", L["slot_c"] * cb, torch.uint8)
                 sc[:ncells_own * cb] = self._dev_view(cells_ptr, ncells_own * cb, "|u1", torch.uint8)
-                sm = torch.zeros(L["slot_c"] * nm3, dtype=torch.float64, device=dev)
+                sm = self._buf("sm", L["slot_c"] * nm3)
                 sm[:ncells_own * nm3] = self._dev_view(M_ptr, ncells_own * nm3)
-                cells_all, M_all = c.all_gather(sc), c.all_gather(sm)
+                cells_all = c.all_gather(sc, out=self._buf("cells_all", G * L["slot_c"] * cb, torch.uint8))
+                M_all = c.all_gather(sm, out=self._buf("M_all", G * L["slot_c"] * nm3))
                 b.let_attach_tree(cells_all.data_ptr(), M_all.data_ptr(), L["slot_c"], L["nc"], L["np"])
                 lap("4 all-gather skeletons + multipoles, attach")
-            srec = torch.zeros(L["slot_n"] * 10, dtype=torch.float64, device=dev)
+            srec = self._buf("srec", L["slot_n"] * 10)
 
             def exchange_records():
                 srec[:n_own * 10] = self._dev_view(rec_ptr, n_own * 10)
-                rec_all = c.all_gather(srec)
+                rec_all = c.all_gather(srec, out=self._buf("rec_all", G * L["slot_n"] * 10))
                 b.let_attach_records(rec_all.data_ptr(), L["slot_n"], L["np"])
                 return rec_all
 
             keep = exchange_records()
             lap("5 all-gather source records, attach")
-            out = torch.empty((max(n_own, 1), 12), dtype=torch.float64, device=dev)
+            out = self._buf("out", max(n_own, 1) * 12).view(-1, 12)
             b.let_evaluate(out.data_ptr(), reuse)
             lap("6 traversal, M2L, L2L, L2P + near field")
-            res = c.all_to_all_rows(out[:n_own], L["recv"], L["send"])
+            res = c.all_to_all_rows(out[:n_own], L["recv"], L["send"], out=self._buf("res", max(n_home, 1) * 12).view(-1, 12))
             b.let_finish(res.data_ptr(), 0, reset)
             lap("7 inverse all-to-all of U, J + scatter")
             if reset_sfs:
@@ -264,9 +279,9 @@ class ShardedField:
             if sfs:
                 b.let_estr_records()
                 keep = exchange_records()
-                outE = torch.empty((max(n_own, 1), 3), dtype=torch.float64, device=dev)
+                outE = self._buf("outE", max(n_own, 1) * 3).view(-1, 3)
                 b.let_estr_evaluate(outE.data_ptr())
-                resE = c.all_to_all_rows(outE[:n_own], L["recv"], L["send"])
+                resE = c.all_to_all_rows(outE[:n_own], L["recv"], L["send"], out=self._buf("resE", max(n_home, 1) * 3).view(-1, 3))
                 b.let_finish(resE.data_ptr(), 1, False)
                 lap("8 E_str: records, all-gather, near field, return")
             L["far_valid"] = bool(hint == 1 and not sch.fmm_nonzero_sigma)

@@ -48,11 +48,14 @@ class LoopbackCollectives:
         t.copy_(res)
         return t
 
-    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+    def all_gather(self, t: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         allv = self._exchange(t)
-        out = torch.stack([v.to(t.device) for v in allv])
+        res = torch.stack([v.to(t.device) for v in allv])
+        if out is not None:
+            out.view(-1)[:res.numel()].copy_(res.view(-1))
+            res = out.view(-1)[:res.numel()].view(res.shape)
         self._done_reading()
-        return out
+        return res
 
     def all_gather_into_async(self, out: torch.Tensor, t: torch.Tensor):
         out.view(self.world, -1).copy_(self.all_gather(t).view(self.world, -1))
@@ -64,7 +67,7 @@ class LoopbackCollectives:
         self.W.barrier.wait()
         return out
 
-    def all_to_all_rows(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
+    def all_to_all_rows(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int], out=None) -> torch.Tensor:
         offs = [0]
         for c in send_counts:
             offs.append(offs[-1] + int(c))
@@ -73,9 +76,12 @@ class LoopbackCollectives:
         for q, (s, o) in enumerate(allv):
             assert o[self.rank + 1] - o[self.rank] == int(recv_counts[q])
             parts.append(s[o[self.rank]:o[self.rank + 1]].to(send.device))
-        out = torch.cat(parts) if parts else send[:0]
+        res = torch.cat(parts) if parts else send[:0]
+        if out is not None:
+            out[:res.shape[0]].copy_(res)
+            res = out[:res.shape[0]]
         self._done_reading()
-        return out
+        return res
 
 
 def run_ranks(world: int, fn):
