@@ -85,6 +85,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fmm", action="store_true", help="skip the secondary UJ_fmm figures")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle parity check of the timed state")
+    ap.add_argument("--no-balance", action="store_true", help="UJ_fmm LET: cut the Morton curve by particle count, not by measured work")
     ap.add_argument("--let-timing", action="store_true", help="UJ_fmm mode: add a synchronised per-phase breakdown of one step")
     ap.add_argument("--fmm-mode", default="let", choices=["let", "replicated"],
                     help="multi-GPU UJ_fmm: local essential tree (default) or round 1's replicated tree")
@@ -330,6 +331,7 @@ def run_ours(args):
     eng = fb.Engine(hi - lo, float_bits=64, device=local_rank, schemes=sch)
     eng.upload(P_local)
     field = ShardedField(eng, max_local=hi - lo, device=f"cuda:{local_rank}", fmm=args.fmm_mode)
+    field.let_balance = not args.no_balance
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -387,6 +389,7 @@ def run_ours(args):
             eng.synchronize()
             phases = {"step_wall_ms": (time.perf_counter() - t0) * 1e3, **{k: v for k, v in sorted(field.let_timing.items())}}
             field.let_timing = None
+        field.uj(True, True, True)          # U, J, SFS rows consistent with the current X, Gamma, sigma
         parity = None if args.no_parity else fmm_parity_check(field, eng, sch, n, world, rank, local_rank)
         if rank == 0:
             cfg = make_config(args, n, world)
@@ -404,7 +407,9 @@ def run_ours(args):
                                                  "skeletons / multipoles / records, inverse all-to-all of results"
                                                  if args.fmm_mode == "let" else "replicated tree, leaves split, all-reduce")
                                  + f" over {world} GPU(s)"},
-                "parity": parity, "let_phases_ms_rank0_one_step": phases, "gpu_launches": int(launches), "clocks": clocks,
+                "parity": parity, "let_phases_ms_rank0_one_step": phases,
+                "let_rank_ms_last_evaluation": getattr(field, "let_rank_ms", None), "let_balance": not args.no_balance,
+                "gpu_launches": int(launches), "clocks": clocks,
                 "fmm_tree_rank0": eng.fmm_stats()}), flush=True)
         failed = bool(rank == 0 and parity is not None and not parity["ok"])
         if world > 1:

@@ -1441,6 +1441,21 @@ int32_t vpmb200_let_partition(vpmb200_handle e, int32_t nparts, int32_t part, in
     return VPMB200_OK;
 }
 
+int32_t vpmb200_let_set_costs(vpmb200_handle e, const double* cost_per_particle, int32_t nparts) {
+    CHECK_HANDLE(e);
+    if (nparts <= 0 || !cost_per_particle) {          // forget the measurements: the next cut is by particle count
+        e->let.cost_per_particle.clear();
+        e->let.cost_splitters.clear();
+        return VPMB200_OK;
+    }
+    if ((int)e->let.splitters.size() != nparts + 1) return fail(e, VPMB200_EINVAL, "let_set_costs: no previous partition of that size");
+    for (int k = 0; k < nparts; ++k)
+        if (!(cost_per_particle[k] > 0) || !std::isfinite(cost_per_particle[k])) return fail(e, VPMB200_EINVAL, "let_set_costs: costs must be positive");
+    e->let.cost_per_particle.assign(cost_per_particle, cost_per_particle + nparts);
+    e->let.cost_splitters = e->let.splitters;         // the key ranges the costs were measured on
+    return VPMB200_OK;
+}
+
 int32_t vpmb200_let_pack(vpmb200_handle e, double* rows) {
     CHECK_HANDLE(e);
     if (e->np > 0 && !rows) return fail(e, VPMB200_EINVAL, "rows is NULL");

@@ -48,6 +48,9 @@ struct FmmLet {
     int nparts = 1, part = 0;
     std::vector<uint64_t> splitters;   // nparts + 1 key bounds
     std::vector<int64_t> send_counts;
+    // work-weighted cut: measured cost per particle of every rank in the previous evaluation and the key ranges it refers to
+    std::vector<double> cost_per_particle;
+    std::vector<uint64_t> cost_splitters;
     // owner side
     const double* rows = nullptr;      // received rows (n_own x 7), owned by the caller, alive until the evaluation ends
     int64_t n_own = 0, n_all = 0;
@@ -364,15 +367,33 @@ inline cudaError_t let_partition(FmmLet& t, int nparts, int part, int ncrit, int
     FMM_TRY(cudaMemcpyAsync(t.hpre, pre.data(), sizeof(int) * (bins + 1), cudaMemcpyHostToDevice, st));
     std::vector<std::pair<uint64_t, int64_t>> units;
     if (ntot > 0) let_units(cnt, Lc, ncrit, 0, 0, units);
-    // rank k takes the units whose cumulative count (at the unit's START) falls in [k, k + 1) * ntot / nparts
+    // Weight of a unit = its particle count x the cost per particle measured on the rank that owned that part of the Morton
+    // curve in the previous evaluation (vpmb200_let_set_costs; uniform when nothing was measured): equal particle counts are
+    // not equal work — near-field cost follows the local particle density — and the slowest rank sets the pace.
+    const bool weighted = (int)t.cost_per_particle.size() == nparts && (int)t.cost_splitters.size() == nparts + 1;
+    std::vector<double> wgt(units.size());
+    double wtot = 0.0;
+    {
+        int prev = 0;
+        for (size_t u = 0; u < units.size(); ++u) {
+            double c = 1.0;
+            if (weighted) {
+                while (prev + 1 < nparts && units[u].first >= t.cost_splitters[prev + 1]) ++prev;
+                c = t.cost_per_particle[prev];
+            }
+            wgt[u] = c * (double)units[u].second;
+            wtot += wgt[u];
+        }
+    }
+    // rank k takes the units whose cumulative weight (at the unit's START) falls in [k, k + 1) * wtot / nparts
     t.splitters.assign(nparts + 1, ~0ull >> 1);
     t.splitters[0] = 0;
     {
-        int64_t cum = 0;
+        double cum = 0.0;
         int k = 1;
-        for (const auto& u : units) {
-            while (k < nparts && cum >= (ntot * k + nparts - 1) / nparts) t.splitters[k++] = u.first;
-            cum += u.second;
+        for (size_t u = 0; u < units.size(); ++u) {
+            while (k < nparts && cum >= wtot * k / nparts) t.splitters[k++] = units[u].first;
+            cum += wgt[u];
         }
         // ranks left without a unit get empty ranges at the end of the curve
     }

@@ -262,6 +262,13 @@ class Engine:
         self._check(self._L.vpmb200_let_partition(self._h, int(nparts), int(part), sc))
         return [int(v) for v in sc]
 
+    def let_set_costs(self, cost_per_particle=None):
+        if cost_per_particle is None:
+            self._check(self._L.vpmb200_let_set_costs(self._h, None, 0))
+            return
+        a = (C.c_double * len(cost_per_particle))(*[float(v) for v in cost_per_particle])
+        self._check(self._L.vpmb200_let_set_costs(self._h, a, len(cost_per_particle)))
+
     def let_pack(self, rows_ptr: int):
         self._check(self._L.vpmb200_let_pack(self._h, C.c_void_p(rows_ptr)))
 

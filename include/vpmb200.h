@@ -288,6 +288,10 @@ int32_t vpmb200_let_keys(vpmb200_handle h, const double* lohi6_global, int32_t L
 /* Cuts the Morton curve into nparts key ranges of equal count at top-tree unit boundaries; send_counts[k] = local
  * particles owned by rank k (contiguous in the packed order). */
 int32_t vpmb200_let_partition(vpmb200_handle h, int32_t nparts, int32_t part, int64_t* send_counts);
+/* Work-weighted cut: cost_per_particle[k] = device time of rank k's owner work in the previous evaluation / its particle
+ * count (the same nparts values on every rank).  The next vpmb200_let_partition weighs every unit of the Morton curve with the
+ * cost of the rank that owned it, so ranks end up with equal WORK, not equal counts.  NULL / 0 forgets the measurements. */
+int32_t vpmb200_let_set_costs(vpmb200_handle h, const double* cost_per_particle, int32_t nparts);
 int32_t vpmb200_let_pack(vpmb200_handle h, double* rows);           /* np rows of (x, y, z, Gamma, sigma), Morton order    */
 /* Owner side: sort the n_own received rows, build this rank's part of the global octree, upward pass.  n_all = particles of
  * all ranks.  reuse != 0: same positions / strengths as the previous evaluation (DynamicSFS's second filter): only the
