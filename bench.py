@@ -389,6 +389,12 @@ def run_ours(args):
             eng.synchronize()
             phases = {"step_wall_ms": (time.perf_counter() - t0) * 1e3, **{k: v for k, v in sorted(field.let_timing.items())}}
             field.let_timing = None
+            if world > 1:       # every rank's breakdown (diagnostics of load balance): rank 0 prints the table
+                mine = {"rank": rank, "n_own": int(sum(field._let["recv"])) if field._let and "recv" in field._let else None,
+                        "tree": eng.fmm_stats(), **{k[:1]: round(v, 1) for k, v in phases.items() if k[:1].isdigit()}}
+                allp = [None] * world
+                dist.all_gather_object(allp, mine)
+                phases["per_rank"] = allp
         field.uj(True, True, True)          # U, J, SFS rows consistent with the current X, Gamma, sigma
         parity = None if args.no_parity else fmm_parity_check(field, eng, sch, n, world, rank, local_rank)
         if rank == 0:
@@ -408,7 +414,7 @@ def run_ours(args):
                                                  if args.fmm_mode == "let" else "replicated tree, leaves split, all-reduce")
                                  + f" over {world} GPU(s)"},
                 "parity": parity, "let_phases_ms_rank0_one_step": phases,
-                "let_rank_ms_last_evaluation": getattr(field, "let_rank_ms", None), "let_balance": not args.no_balance,
+                "let_balance": "work-weighted cut" if not args.no_balance else "count-based cut",
                 "gpu_launches": int(launches), "clocks": clocks,
                 "fmm_tree_rank0": eng.fmm_stats()}), flush=True)
         failed = bool(rank == 0 and parity is not None and not parity["ok"])

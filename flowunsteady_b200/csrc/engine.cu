@@ -1432,27 +1432,19 @@ int32_t vpmb200_let_keys(vpmb200_handle e, const double* lohi6_global, int32_t L
     return VPMB200_OK;
 }
 
-int32_t vpmb200_let_partition(vpmb200_handle e, int32_t nparts, int32_t part, int64_t* send_counts) {
+int32_t vpmb200_let_partition(vpmb200_handle e, int32_t nparts, int32_t part, int32_t use_work, int64_t* send_counts) {
     CHECK_HANDLE(e);
     if (nparts < 1 || part < 0 || part >= nparts || !send_counts) return fail(e, VPMB200_EINVAL, "let_partition: bad arguments");
     if (!e->let.hist) return fail(e, VPMB200_EINVAL, "let_partition needs let_keys first");
     CU_TRY(e, cudaSetDevice(e->device));
-    LET_TRY(e, let_partition(e->let, nparts, part, e->sch.fmm_ncrit, send_counts, e->stream, e->launches, err));
+    LET_TRY(e, let_partition(e->let, nparts, part, e->sch.fmm_ncrit, use_work != 0, send_counts, e->stream, e->launches, err));
     return VPMB200_OK;
 }
 
-int32_t vpmb200_let_set_costs(vpmb200_handle e, const double* cost_per_particle, int32_t nparts) {
+int32_t vpmb200_let_work(vpmb200_handle e, void** work_dev) {
     CHECK_HANDLE(e);
-    if (nparts <= 0 || !cost_per_particle) {          // forget the measurements: the next cut is by particle count
-        e->let.cost_per_particle.clear();
-        e->let.cost_splitters.clear();
-        return VPMB200_OK;
-    }
-    if ((int)e->let.splitters.size() != nparts + 1) return fail(e, VPMB200_EINVAL, "let_set_costs: no previous partition of that size");
-    for (int k = 0; k < nparts; ++k)
-        if (!(cost_per_particle[k] > 0) || !std::isfinite(cost_per_particle[k])) return fail(e, VPMB200_EINVAL, "let_set_costs: costs must be positive");
-    e->let.cost_per_particle.assign(cost_per_particle, cost_per_particle + nparts);
-    e->let.cost_splitters = e->let.splitters;         // the key ranges the costs were measured on
+    if (!work_dev) return fail(e, VPMB200_EINVAL, "work_dev is NULL");
+    *work_dev = e->let.work;
     return VPMB200_OK;
 }
 
@@ -1522,6 +1514,7 @@ int32_t vpmb200_let_evaluate(vpmb200_handle e, double* out_rows, int32_t reuse) 
     CU_TRY(e, cudaSetDevice(e->device));
     const vpmb200_schemes& s = e->sch;
     if (reuse && (s.fmm_nonzero_sigma || !e->let.far_valid)) return fail(e, VPMB200_EINVAL, "let_evaluate: nothing to reuse");
+    if (!reuse && e->let.work) CU_TRY(e, cudaMemsetAsync(e->let.work, 0, sizeof(long long) * e->let.bins, e->stream));
     LET_TRY(e, let_evaluate(e->fmm, e->let, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, s.kernel, e->fmm_table_copies, e->gh_table,
                             out_rows, reuse != 0, e->stream, e->launches, err));
     return VPMB200_OK;

@@ -48,9 +48,9 @@ struct FmmLet {
     int nparts = 1, part = 0;
     std::vector<uint64_t> splitters;   // nparts + 1 key bounds
     std::vector<int64_t> send_counts;
-    // work-weighted cut: measured cost per particle of every rank in the previous evaluation and the key ranges it refers to
-    std::vector<double> cost_per_particle;
-    std::vector<uint64_t> cost_splitters;
+    // work-weighted cut: interaction work counted per level-Lc bin in the previous evaluation (let_count_work), all-reduced
+    // in place by the caller before the next let_partition
+    long long* work = nullptr;
     // owner side
     const double* rows = nullptr;      // received rows (n_own x 7), owned by the caller, alive until the evaluation ends
     int64_t n_own = 0, n_all = 0;
@@ -68,7 +68,7 @@ struct FmmLet {
 };
 
 inline void let_free(FmmLet& t) {
-    void* ptrs[] = {t.hkeys, t.hkeys_alt, t.hperm, t.hperm_alt, t.hist, t.hpre, t.binmax, t.split_idx, t.cells_all, t.M_all};
+    void* ptrs[] = {t.hkeys, t.hkeys_alt, t.hperm, t.hperm_alt, t.hist, t.hpre, t.binmax, t.split_idx, t.cells_all, t.M_all, t.work};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     t = FmmLet();
@@ -211,6 +211,27 @@ __global__ void let_leaf_counts_kernel(const FmmCell* __restrict__ cells, int c0
     if (v.nchild == 0) count_at[v.start] = v.count;
 }
 
+// Interaction work of the owner's cells, counted per level-Lc Morton bin (integer atomics: the sums are exact, so every rank
+// cuts the next partition from identical numbers).  A leaf's near field costs (its particles) x (particles of its P2P list),
+// twice with the E_str pass over the same pairs; an M2L costs about as much as LET_M2L_WORK particle pairs (measured: 0.25 ns
+// per M2L against 0.015 ns per pair at p = 4).  Cells above level Lc (a handful) are not counted.
+constexpr long long LET_M2L_WORK = 16;
+__global__ void let_count_work_kernel(const FmmCell* __restrict__ cells, int ncells, const unsigned int* __restrict__ p2p_off,
+                                      const int2* __restrict__ runs, const unsigned int* __restrict__ m2l_off,
+                                      const uint64_t* __restrict__ keys, int Lc, long long* __restrict__ work) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const FmmCell cell = cells[c];
+    if (cell.level < Lc) return;
+    long long w = LET_M2L_WORK * (long long)(m2l_off[c + 1] - m2l_off[c]);
+    if (cell.nchild == 0) {
+        long long srcs = 0;
+        for (unsigned int k = p2p_off[c]; k < p2p_off[c + 1]; ++k) srcs += runs[k].y;
+        w += (long long)cell.count * srcs;
+    }
+    if (w > 0) atomicAdd(reinterpret_cast<unsigned long long*>(work) + (keys[cell.start] >> (3 * (FMM_MAXLEVEL - Lc))), (unsigned long long)w);
+}
+
 // Morton order -> the order the rows arrived in: out[perm[i]][k] = src[k][i]
 __global__ void let_out_rows_kernel(const double* __restrict__ sA, int na, const double* __restrict__ sB, int nb, int64_t lds,
                                     int64_t n, const int* __restrict__ perm, double* __restrict__ out) {
@@ -255,11 +276,14 @@ inline cudaError_t let_reserve_home(FmmLet& t, int64_t n, int Lc, std::string& e
     }
     const int bins = 1 << (3 * Lc);
     if (bins != t.bins || !t.hist) {
-        void* ptrs[] = {t.hist, t.hpre, t.binmax, t.split_idx};
+        void* ptrs[] = {t.hist, t.hpre, t.binmax, t.split_idx, t.work};
         for (void* p : ptrs)
             if (p) cudaFree(p);
         t.hist = t.hpre = t.split_idx = nullptr;
         t.binmax = nullptr;
+        t.work = nullptr;
+        FMM_TRY(cudaMalloc(&t.work, sizeof(long long) * bins));
+        FMM_TRY(cudaMemset(t.work, 0, sizeof(long long) * bins));
         FMM_TRY(cudaMalloc(&t.hist, sizeof(int) * bins));
         FMM_TRY(cudaMalloc(&t.hpre, sizeof(int) * (bins + 1)));
         FMM_TRY(cudaMalloc(&t.binmax, sizeof(double) * bins));
@@ -349,7 +373,7 @@ inline void let_units(const std::vector<std::vector<int>>& cnt, int Lc, int ncri
 }
 
 // phase 3 (after the caller all-reduced t.hist in place): splitters, send counts, prefix sums for the forced top splits
-inline cudaError_t let_partition(FmmLet& t, int nparts, int part, int ncrit, int64_t* send_counts, cudaStream_t st,
+inline cudaError_t let_partition(FmmLet& t, int nparts, int part, int ncrit, bool use_work, int64_t* send_counts, cudaStream_t st,
                                  uint64_t& launches, std::string& err) {
     if (nparts > 1024) { err = "LET: more than 1024 ranks"; return cudaErrorInvalidValue; }
     const int bins = t.bins, Lc = t.Lc;
@@ -367,22 +391,35 @@ inline cudaError_t let_partition(FmmLet& t, int nparts, int part, int ncrit, int
     FMM_TRY(cudaMemcpyAsync(t.hpre, pre.data(), sizeof(int) * (bins + 1), cudaMemcpyHostToDevice, st));
     std::vector<std::pair<uint64_t, int64_t>> units;
     if (ntot > 0) let_units(cnt, Lc, ncrit, 0, 0, units);
-    // Weight of a unit = its particle count x the cost per particle measured on the rank that owned that part of the Morton
-    // curve in the previous evaluation (vpmb200_let_set_costs; uniform when nothing was measured): equal particle counts are
-    // not equal work — near-field cost follows the local particle density — and the slowest rank sets the pace.
-    const bool weighted = (int)t.cost_per_particle.size() == nparts && (int)t.cost_splitters.size() == nparts + 1;
+    // Weight of a unit: the interaction work counted in its bins during the previous evaluation (t.work, all-reduced by the
+    // caller) blended with its particle count — equal particle counts are not equal work (the near-field cost follows leaf
+    // occupancy: the ranks that own the densely packed parts of a wake had 2.5x the work of the others on the 5M-ring field,
+    // and every collective waits for the slowest rank).  Without counted work (first evaluation) the cut is by count.
     std::vector<double> wgt(units.size());
     double wtot = 0.0;
     {
-        int prev = 0;
+        std::vector<long long> hw;
+        double per_particle = 0.0;
+        std::vector<double> wpre;
+        if (use_work && t.work && ntot > 0) {
+            hw.resize(bins);
+            FMM_TRY(cudaMemcpyAsync(hw.data(), t.work, sizeof(long long) * bins, cudaMemcpyDeviceToHost, st));
+            FMM_TRY(cudaStreamSynchronize(st));
+            wpre.assign(bins + 1, 0.0);
+            for (int bq = 0; bq < bins; ++bq) wpre[bq + 1] = wpre[bq] + (double)hw[bq];
+            per_particle = wpre[bins] / (double)ntot;
+        }
         for (size_t u = 0; u < units.size(); ++u) {
-            double c = 1.0;
-            if (weighted) {
-                while (prev + 1 < nparts && units[u].first >= t.cost_splitters[prev + 1]) ++prev;
-                c = t.cost_per_particle[prev];
+            double w = (double)units[u].second;
+            if (per_particle > 0.0) {
+                // bins covered by the unit: [first key >> shift, + 8^(Lc - level)); the level follows from the next unit / the key
+                const uint64_t b0 = units[u].first >> (3 * (FMM_MAXLEVEL - Lc));
+                const uint64_t b1 = u + 1 < units.size() ? units[u + 1].first >> (3 * (FMM_MAXLEVEL - Lc)) : (uint64_t)bins;
+                // (units are consecutive in Morton order, so the bins up to the next unit's first bin hold no other particles)
+                w = (wpre[b1] - wpre[b0]) + 0.25 * per_particle * (double)units[u].second;
             }
-            wgt[u] = c * (double)units[u].second;
-            wtot += wgt[u];
+            wgt[u] = w;
+            wtot += w;
         }
     }
     // rank k takes the units whose cumulative weight (at the unit's START) falls in [k, k + 1) * wtot / nparts
@@ -566,6 +603,11 @@ inline cudaError_t let_evaluate(FmmWorkspace& w, FmmLet& t, double theta, double
             if (q != t.part && t.ncells_of[q] > 0) seeds.push_back((uint64_t)(unsigned int)t.cell_off[q]);
         cudaError_t e0 = fmm_lists(w, t.cells_all, t.ncells_own, theta, nzs_factor, nullptr, seeds.data(), (int)seeds.size(), 1, st, launches, err);
         if (e0 != cudaSuccess) return e0;
+        if (t.work) {   // (zeroed by the caller before the evaluation, so ranks without particles contribute zeros)
+            let_count_work_kernel<<<(t.ncells_own + 255) / 256, 256, 0, st>>>(t.cells_all, t.ncells_own, w.p2p_off, w.runs, w.m2l_off, w.keys,
+                                                                            t.Lc, t.work);
+            ++launches;
+        }
     }
     w.cells_eval = t.cells_all;
     w.M_eval = t.M_all;

@@ -128,10 +128,8 @@ class ShardedField:
         self._let = None            # partition / exchange state of the last LET evaluation
         self.let_timing = None      # set to {} to collect wall-clock milliseconds per LET phase (synchronising; diagnostics)
         self._bufs = {}             # grow-only exchange buffers of the LET path (no allocator traffic inside a step)
-        self.let_balance = True     # cut the Morton curve by measured WORK (device time per particle of the previous evaluation)
-        self._let_cost = None       # (events, n_own) of the last full evaluation, smoothed cost per particle by rank
-        self._let_cpp = None
-        self.let_rank_ms = None     # device ms of every rank's owner work in the last measured evaluation (diagnostics)
+        self.let_balance = True     # cut the Morton curve by counted WORK (per-bin interaction counts of the previous evaluation)
+        self._let_work_ready = False
         self.refresh_counts()
 
     def _ctl_device(self):
@@ -192,31 +190,6 @@ class ShardedField:
             self._bufs[name] = t
         return t[:int(n)]
 
-    def _let_feedback(self):
-        """Before a new cut of the Morton curve: every rank's device time for its owner work (traversal, M2L, L2L, L2P, near
-        field, E_str pass) in the last full evaluation, per particle, goes to the partitioner (vpmb200_let_set_costs), so
-        the ranges are cut by work.  Equal counts leave the ranks that own the dense parts of a wake with up to twice the
-        near-field work of the others, and every collective then waits for them."""
-        if not (self.let_balance and self.world > 1 and self._let_cost is not None and self.device.type == "cuda"):
-            return
-        ev, n_own = self._let_cost
-        self._let_cost = None
-        (ev[4] if len(ev) > 4 else ev[2]).synchronize()
-        ms = ev[1].elapsed_time(ev[2]) + (ev[3].elapsed_time(ev[4]) if len(ev) > 4 else 0.0)
-        t = torch.tensor([ms, float(n_own)], dtype=torch.float64, device=self.device)
-        allv = self.coll.all_gather(t).tolist()
-        self.let_rank_ms = [v[0] for v in allv]
-        cpp = [v[0] / v[1] if v[1] > 0 and v[0] > 0 else 0.0 for v in allv]
-        good = [c for c in cpp if c > 0]
-        if not good:
-            return
-        mean = sum(good) / len(good)
-        cpp = [c / mean if c > 0 else 1.0 for c in cpp]
-        if self._let_cpp is not None and len(self._let_cpp) == len(cpp):
-            cpp = [0.5 * a + 0.5 * b for a, b in zip(self._let_cpp, cpp)]     # damped: the measurement is one evaluation old
-        self._let_cpp = cpp
-        self.b.let_set_costs(cpp)
-
     def _uj_fmm_let(self, reset: bool, reset_sfs: bool, sfs: bool):
         """One UJ_fmm evaluation with a local essential tree; phases and what is exchanged between them: fmm_let.cuh."""
         if sfs and not reset:
@@ -256,8 +229,8 @@ class ShardedField:
                 c.all_reduce_(self._dev_view(hist_ptr, bins, "<i4", torch.int32), "sum")
                 if binmax_ptr:
                     c.all_reduce_(self._dev_view(binmax_ptr, bins), "max")
-                self._let_feedback()
-                L["send"] = b.let_partition(G, r)
+                use_work = bool(self.let_balance and self._let_work_ready and G > 1)
+                L["send"] = b.let_partition(G, r, use_work)
                 counts = c.all_gather_ints(L["send"], dev)           # counts[q][k]: particles rank q sends to rank k
                 L["recv"] = [counts[q][r] for q in range(G)]
                 L["n_all"] = sum(sum(row) for row in counts)
@@ -270,9 +243,6 @@ class ShardedField:
             rows = c.all_to_all_rows(send[:n_home], L["send"], L["recv"], out=self._buf("rows", max(n_own, 1) * 7).view(-1, 7))
             L["rows"] = rows                                         # the engine reads it until the evaluation ends
             lap("2 pack + all-to-all of particle rows")
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (dev.type == "cuda" and not reuse) else None
-            if ev:
-                ev[0].record()
             info = b.let_build(rows.data_ptr(), n_own, L["n_all"], reuse)
             cells_ptr, M_ptr, rec_ptr = b.let_ptrs()
             lap("3 owner sort, tree, upward pass")
@@ -302,11 +272,11 @@ class ShardedField:
             keep = exchange_records()
             lap("5 all-gather source records, attach")
             out = self._buf("out", max(n_own, 1) * 12).view(-1, 12)
-            if ev:
-                ev[1].record()          # (the exchanges above are excluded below only through the estimate: they are short)
             b.let_evaluate(out.data_ptr(), reuse)
-            if ev:
-                ev[2].record()
+            if not reuse and self.let_balance and G > 1:
+                # the interaction work this evaluation counted per Morton bin, summed over the ranks: the next cut equalises it
+                c.all_reduce_(self._dev_view(b.let_work(), 8 ** self.let_level, "<i8", torch.int64), "sum")
+                self._let_work_ready = True
             lap("6 traversal, M2L, L2L, L2P + near field")
             res = c.all_to_all_rows(out[:n_own], L["recv"], L["send"], out=self._buf("res", max(n_home, 1) * 12).view(-1, 12))
             b.let_finish(res.data_ptr(), 0, reset)
@@ -317,18 +287,11 @@ class ShardedField:
                 b.let_estr_records()
                 keep = exchange_records()
                 outE = self._buf("outE", max(n_own, 1) * 3).view(-1, 3)
-                if ev:
-                    ev[3].record()
                 b.let_estr_evaluate(outE.data_ptr())
-                if ev:
-                    ev.append(torch.cuda.Event(enable_timing=True))
-                    ev[4].record()
                 resE = c.all_to_all_rows(outE[:n_own], L["recv"], L["send"], out=self._buf("resE", max(n_home, 1) * 3).view(-1, 3))
                 b.let_finish(resE.data_ptr(), 1, False)
                 lap("8 E_str: records, all-gather, near field, return")
             L["far_valid"] = bool(hint == 1 and not sch.fmm_nonzero_sigma)
-            if ev:
-                self._let_cost = (ev, n_own)
             del keep
 
     # ---- UJ_fmm over the sharded field: replicated tree, leaves split over the ranks (round-1 scheme) ----------------

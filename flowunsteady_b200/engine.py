@@ -257,17 +257,16 @@ class Engine:
         self._check(self._L.vpmb200_let_keys(self._h, g, int(Lc), C.byref(h), C.byref(m)))
         return h.value, m.value
 
-    def let_partition(self, nparts: int, part: int):
+    def let_partition(self, nparts: int, part: int, use_work: bool = False):
         sc = (C.c_int64 * nparts)()
-        self._check(self._L.vpmb200_let_partition(self._h, int(nparts), int(part), sc))
+        self._check(self._L.vpmb200_let_partition(self._h, int(nparts), int(part), int(use_work), sc))
         return [int(v) for v in sc]
 
-    def let_set_costs(self, cost_per_particle=None):
-        if cost_per_particle is None:
-            self._check(self._L.vpmb200_let_set_costs(self._h, None, 0))
-            return
-        a = (C.c_double * len(cost_per_particle))(*[float(v) for v in cost_per_particle])
-        self._check(self._L.vpmb200_let_set_costs(self._h, a, len(cost_per_particle)))
+    def let_work(self) -> int:
+        """Device pointer of the int64 per-bin work counts of the last evaluation (0 before the first let_keys)."""
+        p = C.c_void_p()
+        self._check(self._L.vpmb200_let_work(self._h, C.byref(p)))
+        return p.value or 0
 
     def let_pack(self, rows_ptr: int):
         self._check(self._L.vpmb200_let_pack(self._h, C.c_void_p(rows_ptr)))

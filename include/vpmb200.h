@@ -285,13 +285,13 @@ int32_t vpmb200_let_bounds(vpmb200_handle h, double* lohi6);        /* min xyz, 
 /* Morton keys + sort of the local ("home") particles in the cube of the GLOBAL bounds, level-Lc histogram: *hist_dev = int32
  * [8^Lc] (all-reduce SUM in place), *binmax_dev = double [8^Lc] or NULL (all-reduce MAX in place; nonzero_sigma only). */
 int32_t vpmb200_let_keys(vpmb200_handle h, const double* lohi6_global, int32_t Lc, void** hist_dev, void** binmax_dev);
-/* Cuts the Morton curve into nparts key ranges of equal count at top-tree unit boundaries; send_counts[k] = local
- * particles owned by rank k (contiguous in the packed order). */
-int32_t vpmb200_let_partition(vpmb200_handle h, int32_t nparts, int32_t part, int64_t* send_counts);
-/* Work-weighted cut: cost_per_particle[k] = device time of rank k's owner work in the previous evaluation / its particle
- * count (the same nparts values on every rank).  The next vpmb200_let_partition weighs every unit of the Morton curve with the
- * cost of the rank that owned it, so ranks end up with equal WORK, not equal counts.  NULL / 0 forgets the measurements. */
-int32_t vpmb200_let_set_costs(vpmb200_handle h, const double* cost_per_particle, int32_t nparts);
+/* Cuts the Morton curve into nparts key ranges at top-tree unit boundaries; send_counts[k] = local particles owned by rank k
+ * (contiguous in the packed order).  use_work = 0: equal particle counts.  use_work != 0: equal WORK — vpmb200_let_evaluate
+ * counts the interaction work of every level-Lc bin (near-field particle pairs, M2L translations; exact integer sums) into
+ * the int64 [8^Lc] device array vpmb200_let_work returns; the caller all-reduces it (SUM, in place) after the evaluation and
+ * the NEXT partition weighs every unit by it (every rank must pass the same flag). */
+int32_t vpmb200_let_work(vpmb200_handle h, void** work_dev);
+int32_t vpmb200_let_partition(vpmb200_handle h, int32_t nparts, int32_t part, int32_t use_work, int64_t* send_counts);
 int32_t vpmb200_let_pack(vpmb200_handle h, double* rows);           /* np rows of (x, y, z, Gamma, sigma), Morton order    */
 /* Owner side: sort the n_own received rows, build this rank's part of the global octree, upward pass.  n_all = particles of
  * all ranks.  reuse != 0: same positions / strengths as the previous evaluation (DynamicSFS's second filter): only the
