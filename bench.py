@@ -390,8 +390,9 @@ def run_ours(args):
             phases = {"step_wall_ms": (time.perf_counter() - t0) * 1e3, **{k: v for k, v in sorted(field.let_timing.items())}}
             field.let_timing = None
             if world > 1:       # every rank's breakdown (diagnostics of load balance): rank 0 prints the table
+                field.uj(True, True, True)
                 mine = {"rank": rank, "n_own": int(sum(field._let["recv"])) if field._let and "recv" in field._let else None,
-                        "tree": eng.fmm_stats(), **{k[:1]: round(v, 1) for k, v in phases.items() if k[:1].isdigit()}}
+                        "tree": eng.fmm_stats(), "last_eval_ms": eng.fmm_times(), **{k[:1]: round(v, 1) for k, v in phases.items() if k[:1].isdigit()}}
                 allp = [None] * world
                 dist.all_gather_object(allp, mine)
                 phases["per_rank"] = allp

@@ -104,10 +104,11 @@ SYMBOLS = {
     "vpmb200_let_ptrs": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
     "vpmb200_let_attach_tree": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "vpmb200_let_attach_records": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
-    "vpmb200_let_evaluate": (C.c_int32, [_H, C.c_void_p, C.c_int32]),
+    "vpmb200_let_evaluate": (C.c_int32, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "vpmb200_let_estr_records": (C.c_int32, [_H]),
     "vpmb200_let_estr_evaluate": (C.c_int32, [_H, C.c_void_p]),
     "vpmb200_let_finish": (C.c_int32, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "vpmb200_fmm_times": (C.c_int32, [_H, _dp]),
     "vpmb200_launch_count": (C.c_int32, [_H, C.POINTER(C.c_uint64)]),
     "vpmb200_tiles_for": (C.c_int64, [C.c_int64]),
     "vpmb200_tile_doubles": (C.c_int64, []),

@@ -1508,15 +1508,16 @@ int32_t vpmb200_let_attach_records(vpmb200_handle e, const double* rec_recv, int
     return VPMB200_OK;
 }
 
-int32_t vpmb200_let_evaluate(vpmb200_handle e, double* out_rows, int32_t reuse) {
+int32_t vpmb200_let_evaluate(vpmb200_handle e, double* out_rows, int32_t reuse, int32_t stage) {
     CHECK_HANDLE(e);
-    if (e->let.n_own > 0 && !out_rows) return fail(e, VPMB200_EINVAL, "out_rows is NULL");
+    if (stage < 0 || stage > 2) return fail(e, VPMB200_EINVAL, "let_evaluate: stage must be 0, 1 or 2");
+    if (e->let.n_own > 0 && !out_rows && stage != 1) return fail(e, VPMB200_EINVAL, "out_rows is NULL");
     CU_TRY(e, cudaSetDevice(e->device));
     const vpmb200_schemes& s = e->sch;
     if (reuse && (s.fmm_nonzero_sigma || !e->let.far_valid)) return fail(e, VPMB200_EINVAL, "let_evaluate: nothing to reuse");
-    if (!reuse && e->let.work) CU_TRY(e, cudaMemsetAsync(e->let.work, 0, sizeof(long long) * e->let.bins, e->stream));
+    if (!reuse && stage != 2 && e->let.work) CU_TRY(e, cudaMemsetAsync(e->let.work, 0, sizeof(long long) * e->let.bins, e->stream));
     LET_TRY(e, let_evaluate(e->fmm, e->let, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, s.kernel, e->fmm_table_copies, e->gh_table,
-                            out_rows, reuse != 0, e->stream, e->launches, err));
+                            out_rows, reuse != 0, stage, e->stream, e->launches, err));
     return VPMB200_OK;
 }
 
@@ -1622,6 +1623,20 @@ int32_t vpmb200_direct_tile_stats(vpmb200_handle e, int64_t* stats) {
     stats[1] = ntiles;
     stats[2] = (int64_t)c;
     stats[3] = (int64_t)nblocks * ntiles;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_fmm_times(vpmb200_handle e, double* ms6) {
+    CHECK_HANDLE(e);
+    if (!ms6) return fail(e, VPMB200_EINVAL, "ms is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < 6; ++k) {
+        ms6[k] = 0.0;
+        float t = 0.f;
+        if (e->fmm.tset[k] && cudaEventElapsedTime(&t, e->fmm.tev[k][0], e->fmm.tev[k][1]) == cudaSuccess) ms6[k] = t;
+        else cudaGetLastError();
+    }
     return VPMB200_OK;
 }
 

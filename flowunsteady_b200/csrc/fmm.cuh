@@ -155,25 +155,43 @@ __device__ __forceinline__ int lower_bound_key(const uint64_t* __restrict__ keys
 // the all-reduced level-Lc histogram in Morton order, so a cell at level l with Morton prefix q holds
 // hpre[(q + 1) << 3 (Lc - l)] - hpre[q << 3 (Lc - l)] particles over all ranks — so that every rank's partial top tree has
 // exactly the structure of the one-GPU tree.
+// Sparse-leaf refinement (`rec` != nullptr): a cell that would be a leaf (<= ncrit particles) is split anyway while its half
+// side exceeds FMM_LEAF_SIGMAS core sizes of its own particles.  A few stray particles in a large empty cell next to a dense
+// wake otherwise make ONE leaf whose near-field list holds every source leaf within (R_leaf + R_src) / theta — hundreds of
+// thousands of particles for a single warp (measured: 10 ms tails on a 5 ms near-field launch once the padding particles of the
+// ring field drift off the axis).  Dense regions are untouched (their leaves are 1-2 core sizes wide); cells whose particles
+// carry no meaningful core size (probes: sigma = 1e-6, /root/reference/src/FLOWUnsteady_simulation.jl:572) are left alone.
+constexpr double FMM_LEAF_SIGMAS = 4.0;
+__device__ __forceinline__ bool fmm_sparse_leaf_splits(const FmmCell& cell, const double* __restrict__ rec) {
+    if (rec == nullptr || cell.count < 1) return false;
+    double m = 1.0e300;                      // min of 1/sigma^2 over the cell's (few) particles
+    for (int s = 0; s < cell.count; ++s) m = fmin(m, rec[(size_t)(cell.start + s) * REC_REALS + 9]);
+    const double smax2 = 1.0 / m;            // sigma_max^2
+    const double R2 = cell.R * cell.R;
+    return R2 > FMM_LEAF_SIGMAS * FMM_LEAF_SIGMAS * smax2 && smax2 * 16777216.0 > R2;   // sigma_max > R / 4096
+}
 __device__ __forceinline__ bool fmm_cell_splits(const FmmCell& cell, const uint64_t* __restrict__ keys, int ncrit,
-                                                const int* __restrict__ hpre, int Lc) {
+                                                const int* __restrict__ hpre, int Lc, const double* __restrict__ rec) {
     if (cell.level >= FMM_MAXLEVEL) return false;
     if (hpre != nullptr && cell.level < Lc) {
         const uint64_t q = keys[cell.start] >> (3 * (FMM_MAXLEVEL - cell.level));
         const int sh = 3 * (Lc - cell.level);
-        return hpre[(q + 1) << sh] - hpre[q << sh] > ncrit;
+        if (hpre[(q + 1) << sh] - hpre[q << sh] > ncrit) return true;
+        return fmm_sparse_leaf_splits(cell, rec);   // a leaf of the global top tree: wholly owned, so the local particles are all
     }
-    return cell.count > ncrit;
+    if (cell.count > ncrit) return true;
+    return fmm_sparse_leaf_splits(cell, rec);
 }
 
 // For each cell of the level: number of non-empty children (0 if the cell is a leaf).
 __global__ void fmm_split_count_kernel(const FmmCell* __restrict__ cells, int c0, int c1, const uint64_t* __restrict__ keys,
-                                       int ncrit, int* __restrict__ nchild, const int* __restrict__ hpre = nullptr, int Lc = 0) {
+                                       int ncrit, int* __restrict__ nchild, const int* __restrict__ hpre = nullptr, int Lc = 0,
+                                       const double* __restrict__ rec = nullptr) {
     int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
     const FmmCell cell = cells[c];
     int nc = 0;
-    if (fmm_cell_splits(cell, keys, ncrit, hpre, Lc)) {
+    if (fmm_cell_splits(cell, keys, ncrit, hpre, Lc, rec)) {
         const int shift = 3 * (FMM_MAXLEVEL - cell.level - 1);
         const uint64_t prefix = (keys[cell.start] >> (shift + 3)) << 3;
         int lo = cell.start;
@@ -189,11 +207,11 @@ __global__ void fmm_split_count_kernel(const FmmCell* __restrict__ cells, int c0
 
 __global__ void fmm_split_emit_kernel(FmmCell* __restrict__ cells, int c0, int c1, const uint64_t* __restrict__ keys,
                                       int ncrit, const int* __restrict__ child_off, int next0,
-                                      const int* __restrict__ hpre = nullptr, int Lc = 0) {
+                                      const int* __restrict__ hpre = nullptr, int Lc = 0, const double* __restrict__ rec = nullptr) {
     int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
     FmmCell cell = cells[c];
-    if (!fmm_cell_splits(cell, keys, ncrit, hpre, Lc)) {
+    if (!fmm_cell_splits(cell, keys, ncrit, hpre, Lc, rec)) {
         cells[c].child0 = -1;
         cells[c].nchild = 0;
         return;

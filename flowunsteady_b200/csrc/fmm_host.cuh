@@ -40,7 +40,27 @@ struct FmmWorkspace {
     // combined arrays ([own | other ranks']) instead of w.cells / w.M; targets are always the own cells [0, ncells)
     const FmmCell* cells_eval = nullptr;
     const double* M_eval = nullptr;
+    // device time of the sections of the LAST evaluation (CUDA events on the engine's stream; vpmb200_fmm_times):
+    // 0 sort + tree, 1 lists (traversal sweeps incl. their host read-backs, sorts), 2 upward, 3 M2L + L2L, 4 L2P + near field,
+    // 5 E_str near field
+    cudaEvent_t tev[6][2] = {};
+    bool tset[6] = {false, false, false, false, false, false};
 };
+
+inline void fmm_tic(FmmWorkspace& w, int k, cudaStream_t st) {
+    if (!w.tev[k][0]) {
+        cudaEventCreate(&w.tev[k][0]);
+        cudaEventCreate(&w.tev[k][1]);
+    }
+    cudaEventRecord(w.tev[k][0], st);
+    w.tset[k] = false;
+}
+inline void fmm_toc(FmmWorkspace& w, int k, cudaStream_t st) {
+    if (w.tev[k][1]) {
+        cudaEventRecord(w.tev[k][1], st);
+        w.tset[k] = true;
+    }
+}
 
 // Grid of the persistent near-field kernels: as many CTAs as are resident at once (occupancy of `kfn` x SMs), fewer when
 // there are not enough leaves; zeroes the leaf counter (counters->next is idle once the traversal is done).
@@ -60,6 +80,9 @@ inline cudaError_t fmm_leaf_grid(FmmWorkspace& w, K kfn, int threads, size_t sme
 }
 
 inline void fmm_free(FmmWorkspace& w) {
+    for (auto& pair : w.tev)
+        for (auto& ev : pair)
+            if (ev) cudaEventDestroy(ev);
     void* ptrs[] = {w.keys, w.keys_alt, w.perm, w.perm_alt, w.sx, w.sy, w.sz, w.rec, w.sU, w.sJ, w.sE, w.cells, w.nchild,
                     w.child_off, w.leaf_flag, w.leaf_pos, w.leaves, w.M, w.L, w.front_a, w.front_b, w.m2l, w.m2l_sorted,
                     w.p2p, w.p2p_sorted, w.m2l_off, w.p2p_off, w.counters, w.bounds, w.cub_tmp, w.runs, w.count_at, w.mine,
@@ -327,6 +350,7 @@ inline cudaError_t fmm_sort(FmmWorkspace& w, const double* soa, int64_t ld, int6
 // lvl (cell index range of every level) and the leaf list (w.leaves, w.nleaves).  hpre / Lc: fmm_cell_splits.
 inline cudaError_t fmm_tree(FmmWorkspace& w, int64_t n, int ncrit, const FmmRoot& rt, std::vector<int>& lvl, cudaStream_t st,
                             uint64_t& launches, std::string& err, const int* hpre = nullptr, int Lc = 0) {
+    fmm_tic(w, 0, st);
     // the cell arrays start from an estimate and the build restarts if they are too small; the estimate follows the CURRENT
     // particle count (a field that grew from a small first call must not rely on doublings alone)
     FMM_TRY(fmm_reserve_cells(w, std::max<int64_t>(8192, 6 * n / std::max(ncrit, 1)), err));
@@ -344,7 +368,7 @@ inline cudaError_t fmm_tree(FmmWorkspace& w, int64_t n, int ncrit, const FmmRoot
         while (true) {
             const int c0 = lvl[lvl.size() - 2], c1 = lvl.back();
             const int nc = c1 - c0;
-            fmm_split_count_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.nchild, hpre, Lc);
+            fmm_split_count_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.nchild, hpre, Lc, w.rec);
             FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, w.nchild, w.child_off, nc, st));
             int last_off = 0, last_n = 0;
             FMM_TRY(cudaMemcpyAsync(&last_off, w.child_off + nc - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -356,7 +380,7 @@ inline cudaError_t fmm_tree(FmmWorkspace& w, int64_t n, int ncrit, const FmmRoot
                 overflow = true;
                 break;
             }
-            fmm_split_emit_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.child_off, ncells, hpre, Lc);
+            fmm_split_emit_kernel<<<(nc + 127) / 128, 128, 0, st>>>(w.cells, c0, c1, w.keys, ncrit, w.child_off, ncells, hpre, Lc, w.rec);
             ++launches;
             if (nnew == 0) break;
             ncells += nnew;
@@ -384,6 +408,7 @@ inline cudaError_t fmm_tree(FmmWorkspace& w, int64_t n, int ncrit, const FmmRoot
     w.nleaves = lp + lf;
     w.leaf_lo = 0;
     w.leaf_hi = w.nleaves;
+    fmm_toc(w, 0, st);
     return cudaSuccess;
 }
 
@@ -404,6 +429,7 @@ inline void fmm_smax(FmmWorkspace& w, FmmCell* cells, int ncells, const std::vec
 // SOURCE leaf outside [0, ntarget) (remote leaves), indexed by first particle; own leaves are filled in here.
 inline cudaError_t fmm_lists(FmmWorkspace& w, const FmmCell* cells, int ntarget, double theta, double nzs_factor, const int* mine,
                              const uint64_t* seeds, int nseeds, int nparts, cudaStream_t st, uint64_t& launches, std::string& err) {
+    fmm_tic(w, 1, st);
     if (!w.front_a) {
         w.cap_pairs = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 192LL * ntarget / nparts), 1500000000LL);
         w.cap_p2p = (unsigned int)std::min<int64_t>(std::max<int64_t>(1 << 20, 96LL * ntarget / nparts), 1500000000LL);
@@ -459,6 +485,7 @@ inline cudaError_t fmm_lists(FmmWorkspace& w, const FmmCell* cells, int ntarget,
     if (w.n_p2p > 0) fmm_p2p_runs_kernel<<<(w.n_p2p + 255) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, w.count_at, w.runs);
     launches += 4;
     FMM_TRY(cudaGetLastError());
+    fmm_toc(w, 1, st);
     return cudaSuccess;
 }
 
@@ -518,24 +545,34 @@ inline cudaError_t fmm_regather(FmmWorkspace& w, const double* soa, int64_t ld, 
 // the far field is the singular kernel, so it does not depend on sigma): skip P2M/M2M/M2L/L2L and only redo L2P + near field.
 template <int P>
 inline cudaError_t fmm_evaluate_p(FmmWorkspace& w, int kernel, int block, const double* gh_table, const std::vector<int>& lvl,
-                                  cudaStream_t st, uint64_t& launches, bool far_valid, bool skip_upward) {
+                                  cudaStream_t st, uint64_t& launches, bool far_valid, bool skip_upward, int stage) {
     cudaError_t e;
-    if (!far_valid) {
-        if (!skip_upward && (e = FmmPasses<P>::upward(w, lvl, st, launches)) != cudaSuccess) return e;
+    if (!far_valid && stage != 2) {
+        if (!skip_upward) {
+            fmm_tic(w, 2, st);
+            if ((e = FmmPasses<P>::upward(w, lvl, st, launches)) != cudaSuccess) return e;
+            fmm_toc(w, 2, st);
+        }
+        fmm_tic(w, 3, st);
         if ((e = FmmPasses<P>::downward(w, lvl, st, launches)) != cudaSuccess) return e;
+        fmm_toc(w, 3, st);
     }
-    return FmmPasses<P>::leaves_uj(w, kernel, block, gh_table, st, launches);
+    if (stage == 1) return cudaSuccess;
+    fmm_tic(w, 4, st);
+    e = FmmPasses<P>::leaves_uj(w, kernel, block, gh_table, st, launches);
+    fmm_toc(w, 4, st);
+    return e;
 }
 
 inline cudaError_t fmm_evaluate(FmmWorkspace& w, int p, int kernel, int block, const double* gh_table,
                                 const std::vector<int>& lvl, cudaStream_t st, uint64_t& launches, bool far_valid = false,
-                                bool skip_upward = false) {
+                                bool skip_upward = false, int stage = 0) {
     switch (p) {
-    case 2: return fmm_evaluate_p<2>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
-    case 3: return fmm_evaluate_p<3>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
-    case 4: return fmm_evaluate_p<4>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
-    case 5: return fmm_evaluate_p<5>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
-    case 6: return fmm_evaluate_p<6>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward);
+    case 2: return fmm_evaluate_p<2>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward, stage);
+    case 3: return fmm_evaluate_p<3>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward, stage);
+    case 4: return fmm_evaluate_p<4>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward, stage);
+    case 5: return fmm_evaluate_p<5>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward, stage);
+    case 6: return fmm_evaluate_p<6>(w, kernel, block, gh_table, lvl, st, launches, far_valid, skip_upward, stage);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -549,6 +586,7 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
                                           LEAF_WARPS * (size_t)2 * LEAF_BATCH * REC_REALS);
     int grid = 0;
     cudaError_t eg = cudaSuccess;
+    fmm_tic(w, 5, st);
 #define FMM_ESTR_CASE(K)                                                                                                   \
     cudaFuncSetAttribute(fmm_leaf_estr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
     if ((eg = fmm_leaf_grid(w, fmm_leaf_estr_kernel<K>, 32 * LEAF_WARPS, smem, (nl + LEAF_WARPS - 1) / LEAF_WARPS, st, grid)) != cudaSuccess) return eg; \
@@ -562,6 +600,7 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
     }
 #undef FMM_ESTR_CASE
     ++launches;
+    fmm_toc(w, 5, st);
     return cudaGetLastError();
 }
 

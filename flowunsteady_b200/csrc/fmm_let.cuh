@@ -526,7 +526,9 @@ inline cudaError_t let_build(FmmWorkspace& w, FmmLet& t, const double* rows, int
         let_top_smax_kernel<<<(w.ncells + 127) / 128, 128, 0, st>>>(w.cells, w.ncells, w.keys, t.Lc, t.binmax);
         ++launches;
     }
+    fmm_tic(w, 2, st);
     cudaError_t e2 = let_upward(w, p, t.lvl, st, launches);
+    fmm_toc(w, 2, st);
     if (e2 != cudaSuccess) { err = std::string("LET upward pass: ") + cudaGetErrorString(e2); return e2; }
     return cudaSuccess;
 }
@@ -593,10 +595,13 @@ inline cudaError_t let_attach_records(FmmWorkspace& w, FmmLet& t, const double* 
 }
 
 // phase 7: U, J of the owner's particles; out: n_own rows of 12 (U, J) in the order the rows arrived.
+// stage 0: everything; stage 1: interaction lists + far field (traversal, M2L, L2L — needs the skeletons and multipoles only,
+// so the caller can keep the source records in flight meanwhile); stage 2: L2P + near field + output rows.
 inline cudaError_t let_evaluate(FmmWorkspace& w, FmmLet& t, double theta, double nzs_factor, int kernel, int block,
-                                const double* gh_table, double* out, bool reuse, cudaStream_t st, uint64_t& launches, std::string& err) {
+                                const double* gh_table, double* out, bool reuse, int stage, cudaStream_t st, uint64_t& launches,
+                                std::string& err) {
     if (t.n_own <= 0) return cudaSuccess;
-    if (!reuse) {
+    if (stage != 2 && !reuse) {
         std::vector<uint64_t> seeds;
         seeds.push_back(0);                                      // (own root, own root)
         for (int q = 0; q < t.nparts; ++q)                       // (own root, root of rank q's tree); empty ranks have no tree
@@ -611,10 +616,11 @@ inline cudaError_t let_evaluate(FmmWorkspace& w, FmmLet& t, double theta, double
     }
     w.cells_eval = t.cells_all;
     w.M_eval = t.M_all;
-    cudaError_t e1 = fmm_evaluate(w, t.P, kernel, block, gh_table, t.lvl, st, launches, reuse, /*skip_upward=*/true);
+    cudaError_t e1 = fmm_evaluate(w, t.P, kernel, block, gh_table, t.lvl, st, launches, reuse, /*skip_upward=*/true, stage);
     w.cells_eval = nullptr;
     w.M_eval = nullptr;
     if (e1 != cudaSuccess) { err = std::string("LET evaluate: ") + cudaGetErrorString(e1); return e1; }
+    if (stage == 1) return cudaSuccess;
     t.far_valid = true;
     let_out_rows_kernel<<<(unsigned)((t.n_own + 255) / 256), 256, 0, st>>>(w.sU, 3, w.sJ, 9, w.lds, t.n_own, w.perm, out);
     ++launches;

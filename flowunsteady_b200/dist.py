@@ -263,21 +263,34 @@ class ShardedField:
                 lap("4 all-gather skeletons + multipoles, attach")
             srec = self._buf("srec", L["slot_n"] * 10)
 
-            def exchange_records():
+            def exchange_records(overlap=None):
+                """all-gather of the owners' source records (UJ or E_str flavour) behind the own ones; `overlap`: device work
+                that needs the skeletons only, enqueued while the records are in flight"""
                 srec[:n_own * 10] = self._dev_view(rec_ptr, n_own * 10)
-                rec_all = c.all_gather(srec, out=self._buf("rec_all", G * L["slot_n"] * 10))
+                rec_all = self._buf("rec_all", G * L["slot_n"] * 10)
+                work = None
+                if G == 1:
+                    rec_all = srec
+                elif overlap is not None:
+                    work = c.all_gather_into_async(rec_all, srec)     # (a blocking gather with the in-process collectives)
+                else:
+                    c.all_gather(srec, out=rec_all)
+                if overlap is not None:
+                    overlap()
+                if work is not None:
+                    work.wait()
                 b.let_attach_records(rec_all.data_ptr(), L["slot_n"], L["np"])
                 return rec_all
 
-            keep = exchange_records()
-            lap("5 all-gather source records, attach")
             out = self._buf("out", max(n_own, 1) * 12).view(-1, 12)
-            b.let_evaluate(out.data_ptr(), reuse)
+            keep = exchange_records(overlap=lambda: b.let_evaluate(out.data_ptr(), reuse, 1))   # traversal, M2L, L2L meanwhile
+            lap("5 all-gather source records || lists, M2L, L2L")
+            b.let_evaluate(out.data_ptr(), reuse, 2)
             if not reuse and self.let_balance and G > 1:
                 # the interaction work this evaluation counted per Morton bin, summed over the ranks: the next cut equalises it
                 c.all_reduce_(self._dev_view(b.let_work(), 8 ** self.let_level, "<i8", torch.int64), "sum")
                 self._let_work_ready = True
-            lap("6 traversal, M2L, L2L, L2P + near field")
+            lap("6 L2P + near field")
             res = c.all_to_all_rows(out[:n_own], L["recv"], L["send"], out=self._buf("res", max(n_home, 1) * 12).view(-1, 12))
             b.let_finish(res.data_ptr(), 0, reset)
             lap("7 inverse all-to-all of U, J + scatter")

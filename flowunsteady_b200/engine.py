@@ -290,8 +290,8 @@ class Engine:
         b = (C.c_int64 * len(nparticles))(*[int(v) for v in nparticles])
         self._check(self._L.vpmb200_let_attach_records(self._h, C.c_void_p(rec_ptr), int(slot_n), b))
 
-    def let_evaluate(self, out_ptr: int, reuse: bool = False):
-        self._check(self._L.vpmb200_let_evaluate(self._h, C.c_void_p(out_ptr), int(reuse)))
+    def let_evaluate(self, out_ptr: int, reuse: bool = False, stage: int = 0):
+        self._check(self._L.vpmb200_let_evaluate(self._h, C.c_void_p(out_ptr), int(reuse), int(stage)))
 
     def let_estr_records(self):
         self._check(self._L.vpmb200_let_estr_records(self._h))
@@ -321,6 +321,12 @@ class Engine:
         d = dict(zip(("target_blocks", "source_tiles", "far_pairs", "all_pairs"), [int(v) for v in a]))
         d["tile_far_fraction"] = d["far_pairs"] / d["all_pairs"] if d["all_pairs"] else 0.0
         return d
+
+    def fmm_times(self) -> dict:
+        """Device ms of the sections of the last UJ_fmm evaluation (vpmb200_fmm_times)."""
+        a = (C.c_double * 6)()
+        self._check(self._L.vpmb200_fmm_times(self._h, a))
+        return dict(zip(("tree", "lists", "upward", "m2l_l2l", "l2p_near", "estr_near"), [round(float(v), 3) for v in a]))
 
     @property
     def launch_count(self) -> int:

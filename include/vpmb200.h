@@ -249,6 +249,10 @@ int32_t vpmb200_fmm_stats(vpmb200_handle h, int64_t* stats);
  * farther apart than the tile's T_FAR sigma_max (K1 runs its branch-free singular loop on them, K2 skips them),
  * stats[3] = all (block, tile) pairs.  Uses the same ordering (direct_sort) and boxes as vpmb200_uj. */
 int32_t vpmb200_direct_tile_stats(vpmb200_handle h, int64_t* stats);
+/* Device time (ms, CUDA events on the handle's stream) of the sections of the LAST UJ_fmm evaluation: ms6 = { sort + tree build,
+ * interaction lists (traversal sweeps with their read-backs + list sorts), upward pass, M2L + L2L, L2P + near field, E_str near
+ * field }.  Diagnostics (load balance across ranks, bench.py). */
+int32_t vpmb200_fmm_times(vpmb200_handle h, double* ms6);
 /* Number of CUDA kernels this handle has enqueued since creation (bench.py reports the per-step delta). */
 int32_t vpmb200_launch_count(vpmb200_handle h, uint64_t* count);
 /* Block the host until all enqueued work on the handle has finished. */
@@ -302,7 +306,9 @@ int32_t vpmb200_let_ptrs(vpmb200_handle h, void** ptrs3);           /* own cells
 int32_t vpmb200_let_attach_tree(vpmb200_handle h, const void* cells_recv, const double* M_recv, int64_t slot_cells,
                                 const int64_t* ncells, const int64_t* nparticles);
 int32_t vpmb200_let_attach_records(vpmb200_handle h, const double* rec_recv, int64_t slot_n, const int64_t* nparticles);
-int32_t vpmb200_let_evaluate(vpmb200_handle h, double* out_rows, int32_t reuse);   /* n_own rows of U(3), J(9), arrival order */
+/* n_own rows of U(3), J(9) in arrival order.  stage 0: everything.  stage 1: interaction lists + far field only (needs
+ * attach_tree, not the records — the record exchange can overlap it); stage 2: L2P + near field + the output rows. */
+int32_t vpmb200_let_evaluate(vpmb200_handle h, double* out_rows, int32_t reuse, int32_t stage);
 int32_t vpmb200_let_estr_records(vpmb200_handle h);                 /* own records -> E_str flavour (needs evaluate's J)    */
 int32_t vpmb200_let_estr_evaluate(vpmb200_handle h, double* out_rows);             /* n_own rows of E_str(3)                  */
 /* Home side: res_rows in the packed order.  what = 0: U, J rows (reset != 0 overwrites and zeroes PSE, else accumulates);
