@@ -358,6 +358,9 @@ class ParticleField:
     # ---- scheme translation ------------------------------------------------------------------------------------
     def _schemes(self, uj_id: int, integration_id: Optional[int] = None):
         sfs = self.SFS
+        if getattr(self.fmm, "eps_tol", None) is not None:
+            raise NotImplementedError("vpm.FMM(eps_tol=...) (error-controlled acceptance) is not available in the GPU engine; "
+                                      "use theta / p")
         kw = dict(kernel=self.kernel.id, f=self.formulation.f, g=self.formulation.g, transposed=int(self.transposed),
                   relaxation=self.relaxation.id, rlxf=self.relaxation.rlxf, sfs=sfs.id, uj=uj_id,
                   fmm_p=self.fmm.p, fmm_ncrit=self.fmm.ncrit, fmm_theta=self.fmm.theta,
@@ -931,7 +934,7 @@ def finalize_verbose(time_beg, line1, vprintln, run_id, v_lvl: int = 0):
     vprintln(f"ELAPSED TIME: {hrs} hours {mins} minutes {secs} seconds", v_lvl)
 
 
-def run_vpm_(pfield, dt: float, nsteps: int, runtime_function=None, static_particles_function=None, nsteps_relax: int = 1,
+def run_vpm_(pfield, dt: float, nsteps: int, runtime_function=None, static_particles_function=None, nsteps_relax: Optional[int] = None,
              save_path=None, run_name: str = "pfield", nsteps_save: int = 1, verbose: bool = True, v_lvl: int = 0,
              create_savepath: bool = True, prompt: bool = True, save_time: bool = True):
     """vpm.run_vpm!(pfield, dt, nsteps; ...): FLOWVPM's own driver loop (FLOWUnsteady inlines it, simulation.jl:300-447).
@@ -946,14 +949,18 @@ def run_vpm_(pfield, dt: float, nsteps: int, runtime_function=None, static_parti
     for i in range(nsteps + 1):
         if i % max(1, nsteps // 10) == 0:
             vprintln(f"Time step {i} out of {nsteps}\tParticles: {get_np(pfield)}", v_lvl + 1)
-        relax = (getattr(pfield.relaxation, "id", 0) != 0 and nsteps_relax >= 1 and i > 0 and i % nsteps_relax == 0)
+        # relax cadence: the relaxation scheme's own nsteps_relax (simulation.jl:346-348); the keyword overrides it
+        every = getattr(pfield.relaxation, "nsteps_relax", 1) if nsteps_relax is None else nsteps_relax
+        relax = (getattr(pfield.relaxation, "id", 0) != 0 and every >= 1 and i > 0 and i % every == 0)
         org_np = get_np(pfield)
         if i != 0:
+            remove = None
             if static_particles_function is not None:
-                static_particles_function(pfield, pfield.t, dt)
+                remove = static_particles_function(pfield, pfield.t, dt)
             nextstep(pfield, dt, relax=relax)
-            for pi in range(get_np(pfield), org_np, -1):     # statics were appended last (simulation.jl:361-365)
-                remove_particle(pfield, pi - 1)
+            if remove is None or remove:                     # simulation.jl:361: statics go unless the function returned false
+                for pi in range(get_np(pfield), org_np, -1): # they were appended last (simulation.jl:362-365)
+                    remove_particle(pfield, pi - 1)
         breakflag = bool(runtime_function(pfield, pfield.t, dt)) if runtime_function is not None else False
         if save_path is not None and (i % nsteps_save == 0 or i == nsteps or breakflag):
             save(pfield, run_name, path=save_path, add_num=True, overwrite_time=pfield.t if save_time else float(pfield.nt))
