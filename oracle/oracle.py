@@ -39,8 +39,8 @@ class Schemes(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc + OpenMP)."""
-    src = os.path.join(_HERE, "vpm_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("vpm_oracle.c", "fmm_oracle.c", "vpm_oracle.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-B", "-C", _HERE, "libvpm_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -76,6 +76,9 @@ def lib():
         L.vpmo_zeta_direct.argtypes = [C.c_int32, C.c_int64, _dp, _dp, _dp, C.c_int64, _dp, _dp]
         L.vpmo_corespreading_reset.argtypes = [_dp, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, _dp]
         L.vpmo_corespreading_reset.restype = C.c_int32
+        L.vpmo_fmm_uj.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int64, _dp, _dp, _dp, _dp, _dp,
+                                  C.POINTER(C.c_int64)]
+        L.vpmo_fmm_uj.restype = C.c_int32
         L.vpmo_num_threads.restype = C.c_int32
         L.vpmo_set_num_threads.argtypes = [C.c_int32]
         _lib = L
@@ -190,6 +193,18 @@ def corespreading_reset(P, kernel, sgm0, beta=1.5, itmax=15, tol=1e-3):
     res = np.zeros(3)
     it = lib().vpmo_corespreading_reset(P, P.shape[0], _kid(kernel), sgm0, beta, itmax, tol, res)
     return it, res
+
+
+def fmm_uj(kernel, x, g, sig, p=4, ncrit=50, theta=0.4, leaf_sigmas=0.0):
+    """The reference's FMM restated (fmm_oracle.c): U (n,3), J (n,9) at every particle; also returns tree statistics."""
+    x, g, sig = _c(x), _c(g), _c(sig)
+    n = x.shape[0]
+    Uo, Jo = np.zeros((n, 3)), np.zeros((n, 9))
+    st = (C.c_int64 * 4)()
+    rc = lib().vpmo_fmm_uj(_kid(kernel), int(p), int(ncrit), float(theta), float(leaf_sigmas), n, x, g, sig, Uo, Jo, st)
+    if rc != 0:
+        raise ValueError("vpmo_fmm_uj: bad arguments")
+    return Uo, Jo, dict(zip(("cells", "leaves", "m2l_pairs", "p2p_pairs"), [int(v) for v in st]))
 
 
 def num_threads() -> int:

@@ -158,7 +158,7 @@ double vpmo_zeta(int32_t kernel, double r) {
 void vpmo_uj_direct(int32_t kernel, int64_t ns, const double *xs, const double *gs, const double *sig,
                     int64_t nt, const double *xt, double *U, double *J, int32_t accum) {
     if (accum == 0) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nt >= 256)   /* (the FMM oracle calls this per leaf pair) */
         for (int64_t i = 0; i < nt; ++i) {
             double u[3] = {U[3 * i], U[3 * i + 1], U[3 * i + 2]};
             double jac[9];
@@ -170,7 +170,7 @@ void vpmo_uj_direct(int32_t kernel, int64_t ns, const double *xs, const double *
             for (int k = 0; k < 9; ++k) J[9 * i + k] = jac[k];
         }
     } else {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nt >= 256)   /* (the FMM oracle calls this per leaf pair) */
         for (int64_t i = 0; i < nt; ++i) {
             long double u[3] = {U[3 * i], U[3 * i + 1], U[3 * i + 2]};
             long double jac[9];

@@ -153,6 +153,11 @@ void vpmo_update_particle(double *p, const vpmo_schemes *s, double a, double b, 
 int32_t vpmo_num_threads(void);
 void vpmo_set_num_threads(int32_t n);
 
+/* fmm_oracle.c: the reference's FMM restated (ExaFMM-style solid harmonics of degree < p, dual tree traversal with
+ * (R_i + R_j) < theta |c_i - c_j|, near field = vpmo_uj_direct).  U (n x 3), J (n x 9) at every particle from every particle. */
+int32_t vpmo_fmm_uj(int32_t kernel, int32_t p, int32_t ncrit, double theta, double leaf_sigmas, int64_t n, const double *x,
+                    const double *g, const double *sig, double *U, double *J, int64_t *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,43 @@ def test_reference_defaults_error_vs_direct():
     assert rel_l2(F[:, 39:42], D[:, 39:42]) < 5e-2      # E_str: near field only, as Estr_fmm
 
 
+@pytest.mark.parametrize("field", ["rings", "rotor", "random"])
+def test_cuda_fmm_vs_reference_style_fmm_oracle(field):
+    """Row a3 of the scope table: the CUDA FMM against the CPU restatement of the REFERENCE's method (oracle/fmm_oracle.c:
+    ExaFMM-style solid harmonics of degree < p for multipoles and locals, same octree, same acceptance, same traversal) at
+    equal (p, ncrit, theta), both measured against the direct sum on the same field.
+      * pure truncation (singular kernel everywhere): the CUDA expansions (Cartesian Taylor, multipoles to order p - 1, locals to
+        order p + 1) carry the same multipole information and two more local orders, so their error must not exceed the
+        oracle's (x 1.2 slack for the different tree of the sparse-leaf refinement);
+      * reference defaults (gaussianerf near field, singular far field, nonzero_sigma = false): BOTH methods show the same
+        regularisation error — the singular far field is used inside the regularised range wherever the acceptance holds —
+        so the CUDA error equals the oracle's to 25 %: the 1e-2 .. 1e-1 level in J at the defaults is a property of the
+        reference's method, not of this implementation."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200 import fields
+    from oracle import oracle as o
+    x, g, s = {"rings": lambda: fields.vortex_rings(30_000), "rotor": lambda: fields.rotor_wake(20_000),
+               "random": lambda: fields.random_field(20_000)}[field]()
+    g = fields.floor_gamma(g)
+    P = fb.new_particles(x, g, s)
+    for kernel in ("singular", "gaussianerf"):
+        D, _ = _eval(P, kernel=kernel, uj="direct")
+        Ud, Jd = D[:, 9:12], D[:, 15:24]
+        for p in (3, 4, 5):
+            F, st = _eval(P, kernel=kernel, uj="fmm", fmm_p=p, fmm_ncrit=50, fmm_theta=0.4)
+            Uo, Jo, so = o.fmm_uj(kernel, x, g, s, p=p, ncrit=50, theta=0.4, leaf_sigmas=4.0)
+            assert abs(st["cells"] - so["cells"]) <= 0.02 * so["cells"] + 2            # the same octree
+            eg = (rel_l2(F[:, 9:12], Ud), rel_l2(F[:, 15:24], Jd))
+            eo = (rel_l2(Uo, Ud), rel_l2(Jo, Jd))
+            if kernel == "singular":
+                assert eg[0] <= 1.2 * eo[0] and eg[1] <= 1.2 * eo[1], (field, p, eg, eo)
+                assert eo[0] < 0.1 and eg[0] < 0.1
+            else:
+                assert 0.75 * eo[0] <= eg[0] <= 1.25 * eo[0] and 0.75 * eo[1] <= eg[1] <= 1.25 * eo[1], (field, p, eg, eo)
+                # and the two approximations agree with each other better than either agrees with the direct sum
+                assert rel_l2(F[:, 9:12], Uo) < eo[0] and rel_l2(F[:, 15:24], Jo) < eo[1], (field, p)
+
+
 def test_error_decreases_with_order_and_theta():
     P = _field(20_000, seed=8)
     D, _ = _eval(P, uj="direct")
