@@ -110,3 +110,46 @@ def test_xdmf_wrapper(tmp_path):
     assert geo.text == "w.3.h5:X" and geo.get("Dimensions") == "37 3" and geo.get("Format") == "HDF"
     attrs = {a.get("Name"): a for a in grid.findall("Attribute")}
     assert set(attrs) == {"Gamma", "sigma", "circulation", "vol", "static", "i"} and attrs["Gamma"].get("Type") == "Vector"
+
+
+def test_file_opens_the_way_libhdf5_opens_it(tmp_path):
+    """the hand-written container read through an independent from-spec reader that follows libhdf5's open
+    path (tests/h5spec.py: superblock checks, root group, NAME lookup by bisecting B-tree keys and the symbol-table node,
+    object-header and datatype validation) — every dataset of a saved particle field must be found by name and decode to the
+    saved values; and the reader's checks are live: breaking one rule at a time makes it refuse the file."""
+    from flowunsteady_b200 import h5min
+    from tests import h5spec
+    rng = np.random.default_rng(0)
+    n = 777
+    data = {"X": rng.random((n, 3)), "Gamma": rng.standard_normal((n, 3)), "sigma": rng.random(n), "circulation": rng.random(n),
+            "vol": rng.random(n), "static": (rng.random(n) < 0.1).astype(np.int64), "i": np.arange(1, n + 1, dtype=np.int64),
+            "np": np.int64(n), "nt": np.int64(12), "t": np.float64(0.125)}
+    path = str(tmp_path / "pfield.12.h5")
+    h5min.write(path, data)
+    f = h5spec.File(path)
+    for name, ref in data.items():
+        got = f.dataset(name)
+        assert got.shape == np.shape(ref) and np.array_equal(got, np.asarray(ref)), name
+    with pytest.raises(KeyError):
+        f.lookup("no_such_dataset")
+    raw = bytearray(open(path, "rb").read())
+
+    def broken(mutate, rule_fragment):
+        b = bytearray(raw)
+        mutate(b)
+        q = str(tmp_path / "broken.h5")
+        open(q, "wb").write(b)
+        with pytest.raises(h5spec.H5SpecError) as ei:
+            g = h5spec.File(q)
+            for name in data:
+                g.dataset(name)
+        assert rule_fragment in str(ei.value), str(ei.value)
+
+    broken(lambda b: b.__setitem__(slice(40, 48), (len(raw) + 8).to_bytes(8, "little")), "end-of-file address")
+    broken(lambda b: b.__setitem__(8, 2), "superblock version")
+    snod = raw.index(b"SNOD")
+    e0, e1 = bytes(raw[snod + 8:snod + 48]), bytes(raw[snod + 48:snod + 88])
+    broken(lambda b: b.__setitem__(slice(snod + 8, snod + 88), e1 + e0), "sorted by name")       # libhdf5's bisection would miss
+    tree = raw.index(b"TREE")
+    broken(lambda b: b.__setitem__(slice(tree + 40, tree + 48), (0).to_bytes(8, "little")), "keys strictly increasing")
+    broken(lambda b: b.__delitem__(slice(len(raw) - 8, len(raw))), "end-of-file address")          # truncated file
