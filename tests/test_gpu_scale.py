@@ -83,9 +83,12 @@ def test_rotor70k_nextstep_dynamic_sfs_full_parity():
     assert relmax(Pg[:, 15:24], Po[:, 15:24]) < 1e-11
     # Through the dynamic procedure the test-filter minus domain-filter difference (alpha = 0.999) amplifies the 1e-12 of
     # U/J/E_str by 1/(1 - alpha) = 1e3 in BOTH implementations; the max norm then picks the worst of 70,000 particles
-    # (measured 1.3e-9 on Gamma; the 2,000-particle cases of test_gpu_step.py stay under 1e-9).  Budget: 5 x 1e-12 x 1e3.
+    # (measured: Gamma 1.3e-9, sigma 3.5e-13; the 2,000-particle cases of test_gpu_step.py stay under 1e-9).  Budget for the
+    # integrated state: 5 x 1e-12 x 1e3.  The coefficient C itself is a RATIO of two such differences, <Gamma.L> / <Gamma.m>,
+    # and where the denominator is small it amplifies once more (measured 1.2e-8 at the worst of the 70,000 particles, relative
+    # to max C = 1); it enters Gamma only multiplied by dt E_str, which is why Gamma holds 1.3e-9.  Budget: 1e-7.
     errs = {name: relmax(Pg[:, sl], Po[:, sl]) for name, sl in (("Gamma", slice(3, 6)), ("sigma", slice(6, 7)), ("C", slice(36, 39)))}
-    assert max(errs.values()) < 5e-9, errs
+    assert errs["Gamma"] < 5e-9 and errs["sigma"] < 5e-9 and errs["C"] < 1e-7, errs
     assert np.abs(Po[:, 36]).max() > 0                        # the coefficient is active on this field
 
 
