@@ -99,6 +99,7 @@ SYMBOLS = {
     "vpmb200_let_keys": (C.c_int32, [_H, _dp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "vpmb200_let_partition": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "vpmb200_let_work": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
+    "vpmb200_let_cut": (C.c_int32, [C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     "vpmb200_let_pack": (C.c_int32, [_H, C.c_void_p]),
     "vpmb200_let_build": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]),
     "vpmb200_let_ptrs": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),

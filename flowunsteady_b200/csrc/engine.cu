@@ -91,6 +91,12 @@ inline unsigned blocks_for(int64_t n, int bt) { return (unsigned)((n + bt - 1) /
 int32_t ensure_probe(vpmb200_engine* e, int64_t m);
 inline int32_t ensure_probe_scratch(vpmb200_engine* e) { return ensure_probe(e, 1024); }
 
+// vpm.FMM(nonzero_sigma): 0 = false (singular far field wherever the acceptance holds), 1 = true with 5 core sizes of clearance
+// between the closest points of two cells, k >= 2 = true with k core sizes (g differs from 1 by 3e-2 at 3, 1e-3 at 4, 2e-5 at 5)
+double nzs_clearance(const vpmb200_schemes& s) {
+    return s.fmm_nonzero_sigma <= 0 ? 0.0 : (s.fmm_nonzero_sigma == 1 ? 5.0 : (double)s.fmm_nonzero_sigma);
+}
+
 double zeta0_of(int kernel) {
     switch (kernel) {
     case K_GAUSSIANERF: return CONST1;
@@ -430,7 +436,7 @@ int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
         CU_TRY(e, fmm_regather(w, e->state, e->ld, e->np, e->stream, e->launches));
     } else {
         if (fmm_reserve(e->fmm, e->np, s.fmm_ncrit, FmmOps<6>::NM, FmmOps<6>::NL, err) != cudaSuccess) return fail(e, VPMB200_ECUDA, err);
-        cudaError_t st = fmm_build(w, e->state, e->ld, e->np, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream, e->launches, err);
+        cudaError_t st = fmm_build(w, e->state, e->ld, e->np, s.fmm_ncrit, s.fmm_theta, nzs_clearance(s), e->fmm_lvl, e->stream, e->launches, err);
         if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
     }
     const int block = e->fmm_table_copies;   // geometry selector of the near-field kernels (fmm_host.cuh: leaves_uj)
@@ -521,7 +527,7 @@ int32_t do_fmm_global(vpmb200_engine* e, double* G, int64_t ldg, int64_t ntot, i
     const int block = e->fmm_table_copies;
     const unsigned nb = blocks_for(ntot, PK_BT);
     if (pass == 0) {
-        cudaError_t st = fmm_build(w, G, ldg, ntot, s.fmm_ncrit, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, e->fmm_lvl, e->stream,
+        cudaError_t st = fmm_build(w, G, ldg, ntot, s.fmm_ncrit, s.fmm_theta, nzs_clearance(s), e->fmm_lvl, e->stream,
                                    e->launches, err, part, nparts);
         if (st != cudaSuccess) return fail(e, st == cudaErrorMemoryAllocation ? VPMB200_ECAPACITY : VPMB200_ECUDA, err);
         CU_TRY(e, cudaMemsetAsync(w.sU, 0, sizeof(double) * 3 * w.lds, e->stream));
@@ -1441,6 +1447,15 @@ int32_t vpmb200_let_partition(vpmb200_handle e, int32_t nparts, int32_t part, in
     return VPMB200_OK;
 }
 
+int32_t vpmb200_let_cut(const int32_t* hist, const int64_t* work, int32_t Lc, int32_t ncrit, int32_t nparts, uint64_t* splitters) {
+    if (!hist || !splitters || Lc < 1 || Lc > LET_MAX_LC || ncrit < 1 || nparts < 1 || nparts > 1024) return VPMB200_EINVAL;
+    static_assert(sizeof(long long) == sizeof(int64_t), "work counts are 64-bit");
+    std::vector<uint64_t> sp;
+    let_cut(hist, reinterpret_cast<const long long*>(work), Lc, ncrit, nparts, sp);
+    for (int k = 0; k <= nparts; ++k) splitters[k] = sp[k];
+    return VPMB200_OK;
+}
+
 int32_t vpmb200_let_work(vpmb200_handle e, void** work_dev) {
     CHECK_HANDLE(e);
     if (!work_dev) return fail(e, VPMB200_EINVAL, "work_dev is NULL");
@@ -1469,7 +1484,7 @@ int32_t vpmb200_let_build(vpmb200_handle e, const double* rows, int64_t n_own, i
     int32_t rc = check_fmm_settings(e);
     if (rc) return rc;
     const vpmb200_schemes& s = e->sch;
-    LET_TRY(e, let_build(e->fmm, e->let, rows, n_own, n_all, s.fmm_ncrit, s.fmm_nonzero_sigma ? 5.0 : 0.0, s.fmm_p, reuse != 0,
+    LET_TRY(e, let_build(e->fmm, e->let, rows, n_own, n_all, s.fmm_ncrit, nzs_clearance(s), s.fmm_p, reuse != 0,
                          e->stream, e->launches, err));
     if (info4) {
         info4[0] = e->let.ncells_own;
@@ -1516,7 +1531,7 @@ int32_t vpmb200_let_evaluate(vpmb200_handle e, double* out_rows, int32_t reuse, 
     const vpmb200_schemes& s = e->sch;
     if (reuse && (s.fmm_nonzero_sigma || !e->let.far_valid)) return fail(e, VPMB200_EINVAL, "let_evaluate: nothing to reuse");
     if (!reuse && stage != 2 && e->let.work) CU_TRY(e, cudaMemsetAsync(e->let.work, 0, sizeof(long long) * e->let.bins, e->stream));
-    LET_TRY(e, let_evaluate(e->fmm, e->let, s.fmm_theta, s.fmm_nonzero_sigma ? 5.0 : 0.0, s.kernel, e->fmm_table_copies, e->gh_table,
+    LET_TRY(e, let_evaluate(e->fmm, e->let, s.fmm_theta, nzs_clearance(s), s.kernel, e->fmm_table_copies, e->gh_table,
                             out_rows, reuse != 0, stage, e->stream, e->launches, err));
     return VPMB200_OK;
 }

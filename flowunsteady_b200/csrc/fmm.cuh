@@ -354,10 +354,16 @@ __global__ void fmm_traverse_kernel(const FmmCell* __restrict__ cells, const uin
     const double dx = ci.cx - cj.cx, dy = ci.cy - cj.cy, dz = ci.cz - cj.cz;
     const double d2 = dx * dx + dy * dy + dz * dz;
     const double rs = ci.R + cj.R;
-    // well separated (ExaFMM's multipole acceptance criterion); with nonzero_sigma the closest possible pair of points
-    // must also be nzs_factor core sizes apart, so the singular far field is never used where g(r/sigma) != 1
+    // well separated (ExaFMM's multipole acceptance criterion); with nonzero_sigma the closest possible pair of points of the
+    // two cells — the exact gap between the two cubes, not a bounding-sphere estimate, which is 3.7x too pessimistic for
+    // neighbours-but-one — must also be nzs_factor core sizes of the SOURCE cell apart, so the singular far field is never used
+    // where g(r/sigma) != 1
     bool well = rs * rs < theta * theta * d2;
-    if (well && nzs_factor > 0.0) well = sqrt(d2) - 1.7320508075688772 * rs > nzs_factor * cj.smax;
+    if (well && nzs_factor > 0.0) {
+        const double gx = fmax(fabs(dx) - rs, 0.0), gy = fmax(fabs(dy) - rs, 0.0), gz = fmax(fabs(dz) - rs, 0.0);
+        const double lim = nzs_factor * cj.smax;
+        well = gx * gx + gy * gy + gz * gz > lim * lim;
+    }
     if (well) {
         push_pair(m2l, &cnt->m2l, cap_m2l, &cnt->overflow, pi, pj);
     } else if (ci.nchild == 0 && cj.nchild == 0) {

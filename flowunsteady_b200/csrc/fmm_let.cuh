@@ -372,50 +372,44 @@ inline void let_units(const std::vector<std::vector<int>>& cnt, int Lc, int ncri
     for (int o = 0; o < 8; ++o) let_units(cnt, Lc, ncrit, level + 1, (q << 3) | (uint64_t)o, units);
 }
 
-// phase 3 (after the caller all-reduced t.hist in place): splitters, send counts, prefix sums for the forced top splits
-inline cudaError_t let_partition(FmmLet& t, int nparts, int part, int ncrit, bool use_work, int64_t* send_counts, cudaStream_t st,
-                                 uint64_t& launches, std::string& err) {
-    if (nparts > 1024) { err = "LET: more than 1024 ranks"; return cudaErrorInvalidValue; }
-    const int bins = t.bins, Lc = t.Lc;
+// The cut of the Morton curve — pure host arithmetic on the all-reduced histogram (and, optionally, the all-reduced work counts)
+// of the level-Lc bins, so every rank derives the SAME splitters; exported as vpmb200_let_cut for the CPU tests.
+// splitters: nparts + 1 key bounds (rank k owns keys in [splitters[k], splitters[k + 1])).
+inline void let_cut(const int* hist, const long long* work, int Lc, int ncrit, int nparts, std::vector<uint64_t>& splitters,
+                    std::vector<int>* prefix_out = nullptr) {
+    const int bins = 1 << (3 * Lc);
     std::vector<std::vector<int>> cnt(Lc + 1);
-    cnt[Lc].resize(bins);
-    FMM_TRY(cudaMemcpyAsync(cnt[Lc].data(), t.hist, sizeof(int) * bins, cudaMemcpyDeviceToHost, st));
-    FMM_TRY(cudaStreamSynchronize(st));
+    cnt[Lc].assign(hist, hist + bins);
     for (int l = Lc - 1; l >= 0; --l) {
         cnt[l].assign((size_t)1 << (3 * l), 0);
         for (size_t q = 0; q < cnt[l + 1].size(); ++q) cnt[l][q >> 3] += cnt[l + 1][q];
     }
     const int64_t ntot = cnt[0][0];
-    std::vector<int> pre(bins + 1, 0);
-    for (int b = 0; b < bins; ++b) pre[b + 1] = pre[b] + cnt[Lc][b];
-    FMM_TRY(cudaMemcpyAsync(t.hpre, pre.data(), sizeof(int) * (bins + 1), cudaMemcpyHostToDevice, st));
+    if (prefix_out) {
+        prefix_out->assign(bins + 1, 0);
+        for (int b = 0; b < bins; ++b) (*prefix_out)[b + 1] = (*prefix_out)[b] + cnt[Lc][b];
+    }
     std::vector<std::pair<uint64_t, int64_t>> units;
     if (ntot > 0) let_units(cnt, Lc, ncrit, 0, 0, units);
-    // Weight of a unit: the interaction work counted in its bins during the previous evaluation (t.work, all-reduced by the
-    // caller) blended with its particle count — equal particle counts are not equal work (the near-field cost follows leaf
-    // occupancy: the ranks that own the densely packed parts of a wake had 2.5x the work of the others on the 5M-ring field,
-    // and every collective waits for the slowest rank).  Without counted work (first evaluation) the cut is by count.
+    // Weight of a unit: the interaction work counted in its bins during the previous evaluation (all-reduced by the caller)
+    // blended with its particle count — equal particle counts are not equal work (the near-field cost follows leaf occupancy).
+    // Without counted work (first evaluation) the cut is by count.
     std::vector<double> wgt(units.size());
     double wtot = 0.0;
     {
-        std::vector<long long> hw;
         double per_particle = 0.0;
         std::vector<double> wpre;
-        if (use_work && t.work && ntot > 0) {
-            hw.resize(bins);
-            FMM_TRY(cudaMemcpyAsync(hw.data(), t.work, sizeof(long long) * bins, cudaMemcpyDeviceToHost, st));
-            FMM_TRY(cudaStreamSynchronize(st));
+        if (work && ntot > 0) {
             wpre.assign(bins + 1, 0.0);
-            for (int bq = 0; bq < bins; ++bq) wpre[bq + 1] = wpre[bq] + (double)hw[bq];
+            for (int bq = 0; bq < bins; ++bq) wpre[bq + 1] = wpre[bq] + (double)work[bq];
             per_particle = wpre[bins] / (double)ntot;
         }
         for (size_t u = 0; u < units.size(); ++u) {
             double w = (double)units[u].second;
             if (per_particle > 0.0) {
-                // bins covered by the unit: [first key >> shift, + 8^(Lc - level)); the level follows from the next unit / the key
+                // bins from the unit's first bin up to the next unit's first bin (the bins in between hold no particles)
                 const uint64_t b0 = units[u].first >> (3 * (FMM_MAXLEVEL - Lc));
                 const uint64_t b1 = u + 1 < units.size() ? units[u + 1].first >> (3 * (FMM_MAXLEVEL - Lc)) : (uint64_t)bins;
-                // (units are consecutive in Morton order, so the bins up to the next unit's first bin hold no other particles)
                 w = (wpre[b1] - wpre[b0]) + 0.25 * per_particle * (double)units[u].second;
             }
             wgt[u] = w;
@@ -423,20 +417,38 @@ inline cudaError_t let_partition(FmmLet& t, int nparts, int part, int ncrit, boo
         }
     }
     // rank k takes the units whose cumulative weight (at the unit's START) falls in [k, k + 1) * wtot / nparts
-    t.splitters.assign(nparts + 1, ~0ull >> 1);
-    t.splitters[0] = 0;
+    splitters.assign(nparts + 1, ~0ull >> 1);
+    splitters[0] = 0;
     {
         double cum = 0.0;
         int k = 1;
         for (size_t u = 0; u < units.size(); ++u) {
-            while (k < nparts && cum >= wtot * k / nparts) t.splitters[k++] = units[u].first;
+            while (k < nparts && cum >= wtot * k / nparts) splitters[k++] = units[u].first;
             cum += wgt[u];
         }
         // ranks left without a unit get empty ranges at the end of the curve
     }
-    t.splitters[nparts] = 1ull << 63;
+    splitters[nparts] = 1ull << 63;
     for (int k = 1; k < nparts; ++k)
-        if (t.splitters[k] == (~0ull >> 1)) t.splitters[k] = 1ull << 63;
+        if (splitters[k] == (~0ull >> 1)) splitters[k] = 1ull << 63;
+}
+
+// phase 3 (after the caller all-reduced t.hist in place): splitters, send counts, prefix sums for the forced top splits
+inline cudaError_t let_partition(FmmLet& t, int nparts, int part, int ncrit, bool use_work, int64_t* send_counts, cudaStream_t st,
+                                 uint64_t& launches, std::string& err) {
+    if (nparts > 1024) { err = "LET: more than 1024 ranks"; return cudaErrorInvalidValue; }
+    const int bins = t.bins, Lc = t.Lc;
+    std::vector<int> hh(bins);
+    FMM_TRY(cudaMemcpyAsync(hh.data(), t.hist, sizeof(int) * bins, cudaMemcpyDeviceToHost, st));
+    std::vector<long long> hw;
+    if (use_work && t.work) {
+        hw.resize(bins);
+        FMM_TRY(cudaMemcpyAsync(hw.data(), t.work, sizeof(long long) * bins, cudaMemcpyDeviceToHost, st));
+    }
+    FMM_TRY(cudaStreamSynchronize(st));
+    std::vector<int> pre;
+    let_cut(hh.data(), hw.empty() ? nullptr : hw.data(), Lc, ncrit, nparts, t.splitters, &pre);
+    FMM_TRY(cudaMemcpyAsync(t.hpre, pre.data(), sizeof(int) * (bins + 1), cudaMemcpyHostToDevice, st));
     t.nparts = nparts;
     t.part = part;
     // send counts: where the splitters fall in the sorted home keys

@@ -117,7 +117,8 @@ typedef struct {
     int32_t fmm_p;          /* vpm_fmm = vpm.FMM(; p=4, ncrit=50, theta=0.4, nonzero_sigma) simulation.jl:43 */
     int32_t fmm_ncrit;
     double fmm_theta;
-    int32_t fmm_nonzero_sigma;
+    int32_t fmm_nonzero_sigma; /* 0 = false; 1 = true (far field only beyond 5 core sizes of clearance between two cells'
+                                  closest points); k >= 2 = true with k core sizes                                */
 } vpmb200_schemes;
 
 typedef struct vpmb200_engine* vpmb200_handle;
@@ -295,6 +296,11 @@ int32_t vpmb200_let_keys(vpmb200_handle h, const double* lohi6_global, int32_t L
  * the int64 [8^Lc] device array vpmb200_let_work returns; the caller all-reduces it (SUM, in place) after the evaluation and
  * the NEXT partition weighs every unit by it (every rank must pass the same flag). */
 int32_t vpmb200_let_work(vpmb200_handle h, void** work_dev);
+/* The cut itself, host arithmetic only (no device, no handle; what vpmb200_let_partition applies to the all-reduced arrays):
+ * hist = particle count of every level-Lc Morton bin (int32 [8^Lc]), work = the counted work per bin or NULL (cut by count);
+ * splitters[0 .. nparts] receives the key bounds, rank k owning Morton keys in [splitters[k], splitters[k + 1]).  A bound never
+ * falls inside a cell of the global tree's top that holds <= ncrit particles (that cell is a leaf with one owner). */
+int32_t vpmb200_let_cut(const int32_t* hist, const int64_t* work, int32_t Lc, int32_t ncrit, int32_t nparts, uint64_t* splitters);
 int32_t vpmb200_let_partition(vpmb200_handle h, int32_t nparts, int32_t part, int32_t use_work, int64_t* send_counts);
 int32_t vpmb200_let_pack(vpmb200_handle h, double* rows);           /* np rows of (x, y, z, Gamma, sigma), Morton order    */
 /* Owner side: sort the n_own received rows, build this rank's part of the global octree, upward pass.  n_all = particles of

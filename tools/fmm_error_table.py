@@ -4,7 +4,8 @@
 For every field: 2048 sampled particles; relative L2 error of U and J of
   total        p = 4, ncrit = 50, theta = 0.4, nonzero_sigma = false  vs direct gaussianerf   (the reference's defaults)
   truncation   the same expansions with the SINGULAR kernel everywhere vs direct singular      (pure expansion error)
-  regularised  nonzero_sigma = true vs direct gaussianerf                                      (no singular far field inside 5 sigma)
+  regularised  nonzero_sigma = true vs direct gaussianerf     (no singular far field inside 5 / 4 / 3 sigma of clearance between
+               the closest points of two cells: vpmb200_schemes.fmm_nonzero_sigma = 1 / 4 / 3)
 and the time of one evaluation in each mode.  total - truncation is what using the singular far field inside the regularised
 range costs: a property of the reference's scheme (oracle/fmm_oracle.c reproduces it, tests/test_gpu_fmm.py).
 
@@ -44,7 +45,9 @@ for name, gen in CASES:
             truth[kernel] = e.uj_probe(x[idx], want_J=True)
     for mode, kw, kernel in (("total (reference defaults)", dict(fmm_nonzero_sigma=0), "gaussianerf"),
                              ("truncation only (singular kernel)", dict(fmm_nonzero_sigma=0), "singular"),
-                             ("nonzero_sigma = true", dict(fmm_nonzero_sigma=1), "gaussianerf")):
+                             ("nonzero_sigma = true (5 sigma clearance)", dict(fmm_nonzero_sigma=1), "gaussianerf"),
+                             ("nonzero_sigma = true, 4 sigma clearance", dict(fmm_nonzero_sigma=4), "gaussianerf"),
+                             ("nonzero_sigma = true, 3 sigma clearance", dict(fmm_nonzero_sigma=3), "gaussianerf")):
         with fb.Engine(n, schemes=fb.default_schemes(uj="fmm", kernel=kernel, fmm_p=4, fmm_ncrit=50, fmm_theta=0.4, **kw)) as e:
             e.upload(P)
             e.uj(); e.synchronize()
