@@ -13,8 +13,9 @@
 //   * per-particle stages (SFS coefficient, update, relaxation) are shard-local;
 //   * add_particle appends to the least-loaded shard, remove_particle / remove_where reproduce the reference's resulting
 //     GLOBAL order through the map, vpmb200_multi_rebalance moves the tail of the fullest shard to the emptiest one.
-// UJ_fmm on a multi handle is not wired yet (the local-essential-tree phases exist, vpmb200_let_*, and are orchestrated by
-// flowunsteady_b200/dist.py across processes): it returns VPMB200_ENOTSUP.
+//   * UJ_fmm: the local-essential-tree phases of fmm_let.cuh (vpmb200_let_*) with the exchanges done by peer copies and small
+//     host-side reductions — the sequence flowunsteady_b200/dist.py runs across processes with NCCL, here under one thread
+//     (phases separated by stream synchronisation; no far-field reuse between DynamicSFS's two filter evaluations yet).
 
 struct vpmb200_multi {
     int G = 0;
@@ -30,6 +31,10 @@ struct vpmb200_multi {
     std::vector<cudaEvent_t> ev_pack, ev_done;
     bool have_done = false;
     std::vector<double> stage;               // host staging for non-contiguous transfers
+    // UJ_fmm with a local essential tree under one host thread: per-device exchange buffers (grow-only)
+    struct LetBuf { void* p = nullptr; size_t bytes = 0; };
+    std::vector<LetBuf> lb_send, lb_recv, lb_cells, lb_M, lb_rec, lb_out, lb_res;
+    bool let_work_ready = false;
     vpmb200_schemes sch;
     double t = 0.0;
     int64_t nt = 0;
@@ -139,10 +144,191 @@ int32_t multi_pairwise(vpmb200_multi* m, Pack pack, Apply apply) {
     return VPMB200_OK;
 }
 
+// ---- UJ_fmm with a local essential tree, one host thread: the phases of fmm_let.cuh with the exchanges done by peer copies.
+//      Same sequence as flowunsteady_b200/dist.py (_uj_fmm_let); phases are separated by stream synchronisation.
+int32_t let_grow(vpmb200_multi* m, std::vector<vpmb200_multi::LetBuf>& v, int k, size_t bytes) {
+    if ((int)v.size() < m->G) v.resize(m->G);
+    if (bytes <= v[k].bytes && v[k].p) return VPMB200_OK;
+    M_CU(m, cudaSetDevice(m->dev[k]));
+    if (v[k].p) cudaFree(v[k].p);
+    v[k].p = nullptr;
+    v[k].bytes = 0;
+    const size_t cap = bytes + bytes / 8 + 4096;
+    M_CU(m, cudaMalloc(&v[k].p, cap));
+    v[k].bytes = cap;
+    return VPMB200_OK;
+}
+
+int32_t multi_sync_all(vpmb200_multi* m) {
+    for (int k = 0; k < m->G; ++k) M_ENG(m, k, vpmb200_synchronize(m->eng[k]));
+    return VPMB200_OK;
+}
+
+// every device's `bins` values of type T combined on the host (sum or max) and written back to every device
+template <typename T, typename Op>
+int32_t multi_allreduce(vpmb200_multi* m, const std::vector<T*>& dev_ptrs, int count, Op op) {
+    std::vector<T> acc(count), tmp(count);
+    for (int k = 0; k < m->G; ++k) {
+        M_CU(m, cudaSetDevice(m->dev[k]));
+        M_CU(m, cudaMemcpy(k == 0 ? acc.data() : tmp.data(), dev_ptrs[k], sizeof(T) * count, cudaMemcpyDeviceToHost));
+        if (k > 0)
+            for (int i = 0; i < count; ++i) acc[i] = op(acc[i], tmp[i]);
+    }
+    for (int k = 0; k < m->G; ++k) {
+        M_CU(m, cudaSetDevice(m->dev[k]));
+        M_CU(m, cudaMemcpy(dev_ptrs[k], acc.data(), sizeof(T) * count, cudaMemcpyHostToDevice));
+    }
+    return VPMB200_OK;
+}
+
+// rows of `ncol` doubles: block (src k -> dst q) of src's buffer goes behind the blocks of the lower source ranks in dst's buffer
+int32_t multi_alltoall_rows(vpmb200_multi* m, std::vector<vpmb200_multi::LetBuf>& src, std::vector<vpmb200_multi::LetBuf>& dst,
+                            const std::vector<std::vector<int64_t>>& counts /* [src][dst] */, int ncol, bool transpose) {
+    // transpose = false: src k sends counts[k][q] rows to q;  true (the way back): src q sends counts[k][q] rows to k
+    const int G = m->G;
+    for (int to = 0; to < G; ++to) {
+        int64_t need = 0;
+        for (int from = 0; from < G; ++from) need += transpose ? counts[to][from] : counts[from][to];
+        int32_t rc = let_grow(m, dst, to, sizeof(double) * (size_t)std::max<int64_t>(need, 1) * ncol);
+        if (rc) return rc;
+    }
+    for (int to = 0; to < G; ++to) {
+        M_CU(m, cudaSetDevice(m->dev[to]));
+        int64_t doff = 0;
+        for (int from = 0; from < G; ++from) {
+            const int64_t n = transpose ? counts[to][from] : counts[from][to];
+            int64_t soff = 0;
+            for (int q = 0; q < to; ++q) soff += transpose ? counts[q][from] : counts[from][q];
+            if (n > 0)
+                M_CU(m, cudaMemcpyPeerAsync(static_cast<double*>(dst[to].p) + doff * ncol, m->dev[to],
+                                            static_cast<const double*>(src[from].p) + soff * ncol, m->dev[from],
+                                            sizeof(double) * (size_t)n * ncol, m->eng[to]->stream));
+            doff += n;
+        }
+    }
+    return multi_sync_all(m);
+}
+
+int32_t multi_uj_fmm(vpmb200_multi* m, int reset, int reset_sfs, int sfs) {
+    if (sfs && !reset) return mfail(m, VPMB200_ENOTSUP, "sharded UJ_fmm with sfs needs reset (what every SFS scheme calls)");
+    const int G = m->G, Lc = 5, bins = 1 << (3 * Lc);
+    // 1 bounds
+    double lohi[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
+    for (int k = 0; k < G; ++k) {
+        double b[6];
+        M_ENG(m, k, vpmb200_let_bounds(m->eng[k], b));
+        for (int c = 0; c < 3; ++c) { lohi[c] = std::min(lohi[c], b[c]); lohi[3 + c] = std::max(lohi[3 + c], b[3 + c]); }
+    }
+    if (!(lohi[0] <= lohi[3])) return VPMB200_OK;   // no particle anywhere
+    // 2 keys + histogram, summed over the devices
+    std::vector<int*> hist(G);
+    std::vector<double*> bmax(G);
+    std::vector<long long*> work(G);
+    bool nzs = false;
+    for (int k = 0; k < G; ++k) {
+        void *h = nullptr, *b = nullptr, *w = nullptr;
+        M_ENG(m, k, vpmb200_let_keys(m->eng[k], lohi, Lc, &h, &b));
+        M_ENG(m, k, vpmb200_let_work(m->eng[k], &w));
+        hist[k] = static_cast<int*>(h);
+        bmax[k] = static_cast<double*>(b);
+        work[k] = static_cast<long long*>(w);
+        nzs = b != nullptr;
+    }
+    int32_t rc = multi_sync_all(m);
+    if (rc) return rc;
+    if ((rc = multi_allreduce<int>(m, hist, bins, [](int a, int b) { return a + b; }))) return rc;
+    if (nzs && (rc = multi_allreduce<double>(m, bmax, bins, [](double a, double b) { return std::max(a, b); }))) return rc;
+    // 3 partition (the work counts of the previous evaluation were summed right after it)
+    std::vector<std::vector<int64_t>> counts(G, std::vector<int64_t>(G, 0));   // [home k][owner q]
+    for (int k = 0; k < G; ++k) M_ENG(m, k, vpmb200_let_partition(m->eng[k], G, k, m->let_work_ready ? 1 : 0, counts[k].data()));
+    std::vector<int64_t> n_own(G, 0);
+    int64_t n_all = 0;
+    for (int k = 0; k < G; ++k)
+        for (int q = 0; q < G; ++q) { n_own[q] += counts[k][q]; n_all += counts[k][q]; }
+    // 4 particle rows to their owners
+    for (int k = 0; k < G; ++k) {
+        if ((rc = let_grow(m, m->lb_send, k, sizeof(double) * (size_t)std::max<int64_t>(m->eng[k]->np, 1) * LET_ROW))) return rc;
+        M_ENG(m, k, vpmb200_let_pack(m->eng[k], static_cast<double*>(m->lb_send[k].p)));
+    }
+    if ((rc = multi_sync_all(m))) return rc;
+    if ((rc = multi_alltoall_rows(m, m->lb_send, m->lb_recv, counts, LET_ROW, false))) return rc;
+    // 5 owner trees + upward pass
+    std::vector<int64_t> ncells(G, 0);
+    int64_t nm3 = 0;
+    for (int q = 0; q < G; ++q) {
+        int64_t info[4];
+        M_ENG(m, q, vpmb200_let_build(m->eng[q], static_cast<const double*>(m->lb_recv[q].p), n_own[q], n_all, 0, info));
+        ncells[q] = info[0];
+        nm3 = info[2];
+    }
+    if ((rc = multi_sync_all(m))) return rc;
+    // 6 skeletons, multipoles, records of every rank gathered on every device (peer copies), appended behind the own ones
+    const int64_t slot_c = std::max<int64_t>(*std::max_element(ncells.begin(), ncells.end()), 1);
+    const int64_t slot_n = std::max<int64_t>(*std::max_element(n_own.begin(), n_own.end()), 1);
+    const size_t cb = (size_t)vpmb200_let_cell_bytes();
+    auto gather_records = [&]() -> int32_t {
+        for (int q = 0; q < G; ++q) {
+            int32_t r2 = let_grow(m, m->lb_rec, q, sizeof(double) * (size_t)G * slot_n * REC_REALS);
+            if (r2) return r2;
+            M_CU(m, cudaSetDevice(m->dev[q]));
+            for (int k = 0; k < G; ++k) {
+                if (k == q || n_own[k] == 0) continue;
+                void* p3[3];
+                vpmb200_let_ptrs(m->eng[k], p3);
+                M_CU(m, cudaMemcpyPeerAsync(static_cast<double*>(m->lb_rec[q].p) + (size_t)k * slot_n * REC_REALS, m->dev[q], p3[2], m->dev[k],
+                                            sizeof(double) * (size_t)n_own[k] * REC_REALS, m->eng[q]->stream));
+            }
+            M_ENG(m, q, vpmb200_let_attach_records(m->eng[q], static_cast<const double*>(m->lb_rec[q].p), slot_n, n_own.data()));
+        }
+        return multi_sync_all(m);
+    };
+    for (int q = 0; q < G; ++q) {
+        if ((rc = let_grow(m, m->lb_cells, q, cb * (size_t)G * slot_c))) return rc;
+        if ((rc = let_grow(m, m->lb_M, q, sizeof(double) * (size_t)G * slot_c * nm3))) return rc;
+        M_CU(m, cudaSetDevice(m->dev[q]));
+        for (int k = 0; k < G; ++k) {
+            if (k == q || ncells[k] == 0) continue;
+            void* p3[3];
+            vpmb200_let_ptrs(m->eng[k], p3);
+            M_CU(m, cudaMemcpyPeerAsync(static_cast<char*>(m->lb_cells[q].p) + (size_t)k * slot_c * cb, m->dev[q], p3[0], m->dev[k],
+                                        cb * (size_t)ncells[k], m->eng[q]->stream));
+            M_CU(m, cudaMemcpyPeerAsync(static_cast<double*>(m->lb_M[q].p) + (size_t)k * slot_c * nm3, m->dev[q], p3[1], m->dev[k],
+                                        sizeof(double) * (size_t)ncells[k] * nm3, m->eng[q]->stream));
+        }
+        M_ENG(m, q, vpmb200_let_attach_tree(m->eng[q], m->lb_cells[q].p, static_cast<const double*>(m->lb_M[q].p), slot_c, ncells.data(),
+                                            n_own.data()));
+    }
+    if ((rc = multi_sync_all(m))) return rc;
+    if ((rc = gather_records())) return rc;
+    // 7 evaluate, 8 results home
+    for (int q = 0; q < G; ++q) {
+        if ((rc = let_grow(m, m->lb_out, q, sizeof(double) * (size_t)std::max<int64_t>(n_own[q], 1) * 12))) return rc;
+        M_ENG(m, q, vpmb200_let_evaluate(m->eng[q], static_cast<double*>(m->lb_out[q].p), 0, 0));
+    }
+    if ((rc = multi_sync_all(m))) return rc;
+    {   // the interaction work counted per Morton bin, summed: the next cut equalises it
+        if ((rc = multi_allreduce<long long>(m, work, bins, [](long long a, long long b) { return a + b; }))) return rc;
+        m->let_work_ready = true;
+    }
+    if ((rc = multi_alltoall_rows(m, m->lb_out, m->lb_res, counts, 12, true))) return rc;
+    for (int k = 0; k < G; ++k) {
+        M_ENG(m, k, vpmb200_let_finish(m->eng[k], static_cast<const double*>(m->lb_res[k].p), 0, reset));
+        if (reset_sfs) M_ENG(m, k, vpmb200_reset_particles_sfs(m->eng[k]));
+    }
+    if (sfs) {
+        for (int q = 0; q < G; ++q) M_ENG(m, q, vpmb200_let_estr_records(m->eng[q]));
+        if ((rc = multi_sync_all(m))) return rc;
+        if ((rc = gather_records())) return rc;
+        for (int q = 0; q < G; ++q) M_ENG(m, q, vpmb200_let_estr_evaluate(m->eng[q], static_cast<double*>(m->lb_out[q].p)));
+        if ((rc = multi_sync_all(m))) return rc;
+        if ((rc = multi_alltoall_rows(m, m->lb_out, m->lb_res, counts, 3, true))) return rc;
+        for (int k = 0; k < G; ++k) M_ENG(m, k, vpmb200_let_finish(m->eng[k], static_cast<const double*>(m->lb_res[k].p), 1, 0));
+    }
+    return multi_sync_all(m);
+}
+
 int32_t multi_uj(vpmb200_multi* m, int reset, int reset_sfs, int sfs) {
-    if (m->sch.uj == VPMB200_UJ_FMM)
-        return mfail(m, VPMB200_ENOTSUP, "UJ_fmm on a multi-GPU handle is not wired yet: use vpm_UJ = UJ_direct here, or the "
-                                         "local-essential-tree driver in flowunsteady_b200/dist.py");
+    if (m->sch.uj == VPMB200_UJ_FMM) return multi_uj_fmm(m, reset, reset_sfs, sfs);
     for (int k = 0; k < m->G; ++k) {
         if (reset) M_ENG(m, k, vpmb200_reset_particles(m->eng[k]));
         if (reset_sfs) M_ENG(m, k, vpmb200_reset_particles_sfs(m->eng[k]));
@@ -235,6 +421,8 @@ int32_t vpmb200_multi_destroy(vpmb200_multi_handle m) {
     }
     for (int k = 0; k < (int)m->eng.size(); ++k) {
         cudaSetDevice(m->dev[k]);
+        for (auto* v : {&m->lb_send, &m->lb_recv, &m->lb_cells, &m->lb_M, &m->lb_rec, &m->lb_out, &m->lb_res})
+            if (k < (int)v->size() && (*v)[k].p) cudaFree((*v)[k].p);
         if (k < (int)m->tiles_own.size()) cudaFree(m->tiles_own[k]);
         if (k < (int)m->tiles_peer.size()) cudaFree(m->tiles_peer[k]);
         if (k < (int)m->ev_pack.size() && m->ev_pack[k]) cudaEventDestroy(m->ev_pack[k]);

@@ -343,8 +343,8 @@ int32_t vpmb200_stage(vpmb200_handle h, int32_t stage, double a, double b, doubl
  * the GLOBAL particle order (the order of the host's matrix, on which vpm.remove_particle's swap-with-last is defined) is kept
  * as an index map on the host.  Direct U/J (+ E_str): source tiles are exchanged device-to-device (cudaMemcpyPeerAsync over
  * NVLink / NVSwitch, ordered by CUDA events; no NCCL, no host staging) and every device's pair kernels run concurrently;
- * per-particle stages are shard-local.  vpm_UJ = UJ_fmm returns VPMB200_ENOTSUP on a multi handle (the local-essential-tree
- * phases vpmb200_let_* are driven across processes by flowunsteady_b200/dist.py).  devices = NULL means 0 .. ngpus-1; the
+ * per-particle stages are shard-local.  vpm_UJ = UJ_fmm runs the local-essential-tree phases (vpmb200_let_*) with the exchanges
+ * done by peer copies (the sequence flowunsteady_b200/dist.py runs across processes with NCCL).  devices = NULL means 0 .. ngpus-1; the
  * same ordinal may appear more than once (several shards on one GPU: how the tests run on a one-GPU box). */
 typedef struct vpmb200_multi* vpmb200_multi_handle;
 int32_t vpmb200_multi_create(int64_t max_particles, int32_t nfields, int32_t float_bits, int32_t ngpus, const int32_t* devices,

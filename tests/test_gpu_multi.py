@@ -51,6 +51,35 @@ def test_multi_steps_match_one_gpu(ngpus, kw):
     assert np.array_equal(got[:, 42], ref[:, 42])
 
 
+@pytest.mark.parametrize("ngpus", [2, 5])
+@pytest.mark.parametrize("kw", [dict(uj="fmm", sfs="constant", clippings=1), dict(uj="fmm", fmm_nonzero_sigma=1),
+                                dict(uj="fmm", integration="rungekutta3", relaxation="pedrizzetti", sfs="dynamic", alpha=0.999,
+                                     force_positive=1, clippings=1)])
+def test_multi_fmm_local_essential_tree_matches_one_gpu(ngpus, kw):
+    """vpm_UJ = UJ_fmm on the multi handle: the local-essential-tree phases with peer copies between them (multi.inl:
+    multi_uj_fmm) against ONE engine — U, J, E_str of an evaluation to 1e-12, two whole steps to the dynamic procedure's
+    budget."""
+    import flowunsteady_b200 as fb
+    P = _field(9000, seed=12)
+    dyn = kw.get("sfs") == "dynamic"
+    outs = []
+    for make in (lambda: fb.Engine(P.shape[0], schemes=fb.default_schemes(**kw)),
+                 lambda: fb.MultiEngine(P.shape[0], ngpus, _devices(ngpus), schemes=fb.default_schemes(**kw))):
+        with make() as e:
+            e.upload(P)
+            if dyn:
+                for _ in range(2):
+                    e.nextstep(2e-3, (1.0, -0.5, 0.25), relax=True)
+            else:
+                e.uj(True, True, True)
+                e.uj(False, False, False)          # accumulate on top
+            outs.append(e.download(np.zeros_like(P)))
+    ref, got = outs
+    for name, sl, tol in (("X", slice(0, 3), 1e-11), ("U", slice(9, 12), 1e-11 if dyn else 1e-12), ("J", slice(15, 24), 1e-11 if dyn else 1e-12),
+                          ("SFS", slice(39, 42), 1e-9 if dyn else 1e-11), ("Gamma", slice(3, 6), 5e-9), ("sigma", slice(6, 7), 5e-9)):
+        assert relmax(got[:, sl], ref[:, sl]) < tol, name
+
+
 def test_multi_mutation_follows_the_reference_order():
     """add_particle / remove_particle / wake treatment on a sharded field leave the host-visible order exactly as the same
     calls on ONE engine do (the reference's swap-with-last and removal-loop semantics), whatever shard a particle lives on;
@@ -146,11 +175,10 @@ def test_multi_errors():
         with pytest.raises(fb.EngineError) as ei:
             me.upload(np.zeros((101, 43)))
         assert ei.value.code == -4
-        me.set_schemes(fb.default_schemes(uj="fmm"))
         me.upload(_field(64))
         with pytest.raises(fb.EngineError) as ei:
-            me.uj()
-        assert ei.value.code == -5                                  # VPMB200_ENOTSUP, stated loudly
+            me.set_schemes(fb.default_schemes(viscous="corespreading", nu=1e-5, cs_sgm0=0.1))
+        assert ei.value.code == -5                                  # VPMB200_ENOTSUP, stated loudly (RBF re-fit is single-GPU)
         with pytest.raises(fb.EngineError):
             me.remove_particle(64)
     with pytest.raises(fb.EngineError):
