@@ -88,6 +88,7 @@ SYMBOLS = {
     "vpmb200_multi_remove_particle": (C.c_int32, [_H, C.c_int64]),
     "vpmb200_multi_remove_where": (C.c_int32, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]),
     "vpmb200_multi_rebalance": (C.c_int32, [_H, C.c_double, C.POINTER(C.c_int64)]),
+    "vpmb200_multi_set_statics": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "vpmb200_multi_uj": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_int32]),
     "vpmb200_multi_sfs": (C.c_int32, [_H, C.c_double, C.c_double]),
     "vpmb200_multi_nextstep": (C.c_int32, [_H, C.c_double, _dp, C.c_int32]),

@@ -35,6 +35,9 @@ struct vpmb200_multi {
     struct LetBuf { void* p = nullptr; size_t bytes = 0; };
     std::vector<LetBuf> lb_send, lb_recv, lb_cells, lb_M, lb_rec, lb_out, lb_res;
     bool let_work_ready = false;
+    // static-particle fast path on the sharded field (vpmb200_multi_set_statics): the step's statics are ordinary appended particles (they sit at the END
+    // of the global order, so dropping them is a pop) that nextstep removes again; valid while nt == static_gen
+    int64_t nstatic = 0, static_gen = -1;
     vpmb200_schemes sch;
     double t = 0.0;
     int64_t nt = 0;
@@ -411,6 +414,10 @@ int32_t multi_transfer(vpmb200_multi* m, double* particles, int64_t ld, uint32_t
 
 extern "C" {
 
+static int32_t multi_add_impl(vpmb200_multi* m, const double* cols, int64_t ld, int64_t n);
+static int32_t multi_remove_impl(vpmb200_multi* m, int64_t i);
+static int32_t multi_drop_statics(vpmb200_multi* m);
+
 const char* vpmb200_multi_last_error(vpmb200_multi_handle m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
 
 int32_t vpmb200_multi_destroy(vpmb200_multi_handle m) {
@@ -516,13 +523,13 @@ int32_t vpmb200_multi_get_time(vpmb200_multi_handle m, double* t, int64_t* nt) {
 
 int32_t vpmb200_multi_get_np(vpmb200_multi_handle m, int64_t* np) {
     if (!m || !np) return VPMB200_EINVAL;
-    *np = m->np;
+    *np = m->np - m->nstatic;          // a parked static set is not part of the host's field
     return VPMB200_OK;
 }
 
 int32_t vpmb200_multi_shard_sizes(vpmb200_multi_handle m, int64_t* n_per_gpu) {
     if (!m || !n_per_gpu) return VPMB200_EINVAL;
-    for (int k = 0; k < m->G; ++k) n_per_gpu[k] = (int64_t)m->gid[k].size();
+    for (int k = 0; k < m->G; ++k) n_per_gpu[k] = (int64_t)m->gid[k].size();   // (includes a parked static set)
     return VPMB200_OK;
 }
 
@@ -531,6 +538,7 @@ int32_t vpmb200_multi_shard_sizes(vpmb200_multi_handle m, int64_t* n_per_gpu) {
 int32_t vpmb200_multi_upload(vpmb200_multi_handle m, const double* particles, int64_t ld, int64_t np, uint32_t field_mask) {
     if (!m) return VPMB200_EINVAL;
     if (np < 0 || (np > 0 && !particles) || ld < NFIELDS) return mfail(m, VPMB200_EINVAL, "upload: bad arguments");
+    { int32_t rcs = multi_drop_statics(m); if (rcs) return rcs; }
     if (np > m->maxp) return mfail(m, VPMB200_ECAPACITY, "np exceeds max_particles");
     if (np != m->np || (field_mask & VPMB200_FM_ALL) == VPMB200_FM_ALL) {
         int64_t lo = 0;
@@ -548,6 +556,7 @@ int32_t vpmb200_multi_upload(vpmb200_multi_handle m, const double* particles, in
 
 int32_t vpmb200_multi_download(vpmb200_multi_handle m, double* particles, int64_t ld, int64_t np, uint32_t field_mask) {
     if (!m) return VPMB200_EINVAL;
+    { int32_t rcs = multi_drop_statics(m); if (rcs) return rcs; }
     if (np != m->np) return mfail(m, VPMB200_EINVAL, "download: np must equal the field's particle count on a multi-GPU handle");
     if (np == 0) return VPMB200_OK;
     if (!particles || ld < NFIELDS) return mfail(m, VPMB200_EINVAL, "download: bad arguments");
@@ -558,6 +567,12 @@ int32_t vpmb200_multi_download(vpmb200_multi_handle m, double* particles, int64_
 int32_t vpmb200_multi_add_particles(vpmb200_multi_handle m, const double* cols, int64_t ld, int64_t n) {
     if (!m) return VPMB200_EINVAL;
     if (n < 0 || (n > 0 && !cols)) return mfail(m, VPMB200_EINVAL, "add_particles: bad arguments");
+    int32_t rcs = multi_drop_statics(m);          // any mutation invalidates a parked static set (as on the single handle)
+    if (rcs) return rcs;
+    return multi_add_impl(m, cols, ld, n);
+}
+
+static int32_t multi_add_impl(vpmb200_multi* m, const double* cols, int64_t ld, int64_t n) {
     if (m->np + n > m->maxp) return mfail(m, VPMB200_ECAPACITY, "adding particles would exceed max_particles");
     int64_t done = 0;
     while (done < n) {
@@ -582,6 +597,12 @@ int32_t vpmb200_multi_add_particles(vpmb200_multi_handle m, const double* cols, 
 // vpm.remove_particle(pfield, i) on the GLOBAL order: the particle with the last global index takes index i
 int32_t vpmb200_multi_remove_particle(vpmb200_multi_handle m, int64_t i) {
     if (!m) return VPMB200_EINVAL;
+    int32_t rcs = multi_drop_statics(m);
+    if (rcs) return rcs;
+    return multi_remove_impl(m, i);
+}
+
+static int32_t multi_remove_impl(vpmb200_multi* m, int64_t i) {
     if (i < 0 || i >= m->np) return mfail(m, VPMB200_EINVAL, "particle index out of range");
     const int ka = m->owner[(size_t)i];
     const int64_t la = m->local[(size_t)i];
@@ -610,6 +631,7 @@ int32_t vpmb200_multi_remove_particle(vpmb200_multi_handle m, int64_t i) {
 int32_t vpmb200_multi_remove_where(vpmb200_multi_handle m, int32_t criterion, const double* params, int64_t* removed) {
     if (!m) return VPMB200_EINVAL;
     if (!params || criterion < 1 || criterion > 4) return mfail(m, VPMB200_EINVAL, "remove_where: bad arguments");
+    { int32_t rcs = multi_drop_statics(m); if (rcs) return rcs; }
     if (removed) *removed = 0;
     if (m->np == 0) return VPMB200_OK;
     static const int nparams[5] = {0, 2, 2, 9, 4};
@@ -663,6 +685,7 @@ int32_t vpmb200_multi_remove_where(vpmb200_multi_handle m, int32_t criterion, co
 int32_t vpmb200_multi_rebalance(vpmb200_multi_handle m, double tolerance, int64_t* moved_out) {
     if (!m) return VPMB200_EINVAL;
     if (moved_out) *moved_out = 0;
+    { int32_t rcs = multi_drop_statics(m); if (rcs) return rcs; }
     if (m->G < 2) return VPMB200_OK;
     int64_t moved_total = 0;
     for (int iter = 0; iter < 4 * m->G; ++iter) {
@@ -706,6 +729,7 @@ int32_t vpmb200_multi_rebalance(vpmb200_multi_handle m, double tolerance, int64_
 
 int32_t vpmb200_multi_uj(vpmb200_multi_handle m, int32_t reset, int32_t reset_sfs, int32_t sfs) {
     if (!m) return VPMB200_EINVAL;
+    if (m->nstatic > 0 && m->static_gen != m->nt) { int32_t rcs = multi_drop_statics(m); if (rcs) return rcs; }
     return multi_uj(m, reset, reset_sfs, sfs);
 }
 
@@ -714,10 +738,41 @@ int32_t vpmb200_multi_sfs(vpmb200_multi_handle m, double a, double b) {
     return multi_sfs(m, a, b);
 }
 
+// drop the parked statics: they are the last `nstatic` global indices (nothing may be appended behind them while they are parked)
+static int32_t multi_drop_statics(vpmb200_multi* m) {
+    while (m->nstatic > 0) {
+        int32_t rc = multi_remove_impl(m, m->np - 1);
+        if (rc) return rc;
+        m->nstatic--;
+    }
+    m->static_gen = -1;
+    return VPMB200_OK;
+}
+
+// vpmb200_set_statics on a sharded field (simulation.jl:355-365): the columns join the field (least-loaded shard, static flag
+// forced) for the step whose counter equals `generation`; vpmb200_multi_nextstep removes them again.
+int32_t vpmb200_multi_set_statics(vpmb200_multi_handle m, const double* cols, int64_t ld, int64_t n, int64_t generation) {
+    if (!m) return VPMB200_EINVAL;
+    if (n < 0 || (n > 0 && !cols) || ld < NFIELDS) return mfail(m, VPMB200_EINVAL, "set_statics: bad arguments");
+    int32_t rc = multi_drop_statics(m);
+    if (rc) return rc;
+    if (n == 0 || generation != m->nt) return VPMB200_OK;       // a set for another step is never used
+    std::vector<double> tmp((size_t)n * NFIELDS);
+    for (int64_t i = 0; i < n; ++i) {
+        std::memcpy(&tmp[(size_t)i * NFIELDS], cols + i * ld, sizeof(double) * NFIELDS);
+        tmp[(size_t)i * NFIELDS + F_STATIC] = 1.0;
+    }
+    if ((rc = multi_add_impl(m, tmp.data(), NFIELDS, n))) return rc;
+    m->nstatic = n;
+    m->static_gen = generation;
+    return VPMB200_OK;
+}
+
 int32_t vpmb200_multi_nextstep(vpmb200_multi_handle m, double dt, const double* Uinf, int32_t relax) {
     if (!m) return VPMB200_EINVAL;
     if (!Uinf) return mfail(m, VPMB200_EINVAL, "Uinf is NULL");
     int32_t rc;
+    if (m->nstatic > 0 && m->static_gen != m->nt && (rc = multi_drop_statics(m))) return rc;   // stale set
     if (m->np > 0) {
         if (m->sch.integration == VPMB200_INTEGRATION_EULER) {
             if ((rc = multi_sfs(m, 1.0, 1.0))) return rc;
@@ -735,6 +790,7 @@ int32_t vpmb200_multi_nextstep(vpmb200_multi_handle m, double dt, const double* 
             }
         }
     }
+    if ((rc = multi_drop_statics(m))) return rc;   // the step consumed them (the reference removes them after nextstep)
     m->t += dt;
     m->nt += 1;
     for (int k = 0; k < m->G; ++k) vpmb200_set_time(m->eng[k], m->t, m->nt);
@@ -747,6 +803,7 @@ int32_t vpmb200_multi_uj_probe(vpmb200_multi_handle m, const double* X, int64_t 
     if (!m) return VPMB200_EINVAL;
     if (np_probe < 0 || (np_probe > 0 && (!X || !U))) return mfail(m, VPMB200_EINVAL, "uj_probe: bad arguments");
     if (np_probe == 0) return VPMB200_OK;
+    if (m->nstatic > 0 && m->static_gen != m->nt) { int32_t rcs = multi_drop_statics(m); if (rcs) return rcs; }
     std::vector<double> u((size_t)np_probe * 3), j(J ? (size_t)np_probe * 9 : 0);
     std::fill(U, U + np_probe * 3, 0.0);
     if (J) std::fill(J, J + np_probe * 9, 0.0);

@@ -448,6 +448,12 @@ class MultiEngine:
         self._check(self._L.vpmb200_multi_remove_where(self._h, int(criterion), p.ctypes.data, C.byref(r)))
         return r.value
 
+    def set_statics(self, cols: np.ndarray, generation: int | None = None):
+        P = _as_matrix(np.atleast_2d(cols)) if len(cols) else np.zeros((0, NFIELDS))
+        gen = self.get_time()[1] if generation is None else int(generation)
+        self._check(self._L.vpmb200_multi_set_statics(self._h, P.ctypes.data if P.shape[0] else None,
+                                                      P.strides[0] // 8 if P.shape[0] else NFIELDS, P.shape[0], gen))
+
     def rebalance(self, tolerance: float = 0.05) -> int:
         moved = C.c_int64()
         self._check(self._L.vpmb200_multi_rebalance(self._h, float(tolerance), C.byref(moved)))

@@ -368,6 +368,10 @@ int32_t vpmb200_multi_remove_particle(vpmb200_multi_handle h, int64_t i);
 int32_t vpmb200_multi_remove_where(vpmb200_multi_handle h, int32_t criterion, const double* params, int64_t* removed);
 /* Periodic rebalance: tails of the fullest shards move to the emptiest (device to device) until max - min <= tolerance x mean. */
 int32_t vpmb200_multi_rebalance(vpmb200_multi_handle h, double tolerance, int64_t* moved);
+/* vpmb200_set_statics on the sharded field: the step's static columns join the field (as its LAST global indices, on the
+ * least-loaded shard, static flag forced) while the step counter equals `generation`; vpmb200_multi_nextstep removes them
+ * again, any other mutation / transfer drops them first, vpmb200_multi_get_np does not count them. */
+int32_t vpmb200_multi_set_statics(vpmb200_multi_handle h, const double* cols, int64_t ld, int64_t n, int64_t generation);
 int32_t vpmb200_multi_uj(vpmb200_multi_handle h, int32_t reset, int32_t reset_sfs, int32_t sfs);
 int32_t vpmb200_multi_sfs(vpmb200_multi_handle h, double a, double b);
 int32_t vpmb200_multi_nextstep(vpmb200_multi_handle h, double dt, const double* Uinf, int32_t relax);
