@@ -484,6 +484,18 @@ def run_ours(args):
                 ms_none = timed(step, 1)
                 eng.set_schemes(sch)
                 direct2["step_sfs_none"] = {"ms_per_step": ms_none, "interactions_per_s": 4 * float(n) * float(n) / (ms_none * 1e-3)}
+            # the O(N) kernels are HBM-bound: the RK3 substep update moves 45 doubles per particle (31 read, 14
+            # written: Gamma, SFS, C, static, X, U, J, sigma and the 7 q-storage rows); a = 1, b = 0, dt = 0 leaves the state as it is
+            hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s of B200_PROFILING.md (no MEASURED_PEAKS.json)"
+            try:
+                mp_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                hbm_peak, hbm_src = float(mp_["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            except Exception:
+                pass
+            upd_ms = timed(lambda: eng.stage(E.STAGE_UPDATE, 1.0, 0.0, 0.0, Uinf), 50) / 50
+            gbs = 45 * 8 * float(n) / (upd_ms * 1e-3) / 1e9
+            direct2["update_kernel"] = {"ms": upd_ms, "bytes_per_particle": 360, "achieved_gbs": gbs, "peak_gbs": hbm_peak,
+                                        "frac": gbs / hbm_peak, "peak_source": hbm_src, "bound": "hbm"}
             # regularised branch alone: the same generator at 200k particles with sigma blown up so that EVERY pair is inside
             # T_FAR (no tile takes the far loop), and the rotor-hover stand-in (BASELINE configs[1]) at 200k as it is
             from flowunsteady_b200 import fields as F

@@ -77,9 +77,9 @@ def test_uj_large_sampled():
     Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x[idx], accum=1)
     assert relmax(U[idx], Uo) < TOL64
     assert relmax(J[idx], Jo) < TOL64
-    # divergence-free velocity: tr J = 0 to round-off at every particle (size-independent property)
-    tr = J[:, 0] + J[:, 4] + J[:, 8]
-    assert np.abs(tr).max() < 1e-11 * np.abs(J).max()
+    # (tr J = 0 holds by construction in K1 — J33 is closed as -(J11 + J22), uj_direct.cuh acc_close_trace — so it is no
+    #  evidence; what pins J33 is its comparison with the oracle's independently summed J33 above.)
+    assert relmax(J[idx, 8:9], Jo[:, 8:9]) < 1e-11                 # J33 alone: relative to ITS max norm, not the whole tensor's
 
 
 def test_uj_accumulate_and_reset_flags():
@@ -191,7 +191,8 @@ def test_probe_set_uses_split_geometry():
 
 def test_full_size_1m_sampled_parity_and_properties():
     """BASELINE configs[2] at its full size (N = 1,000,000 vortex rings, direct FP64): 2048 sampled targets against the
-    long-double oracle over all 10^6 sources, tr J = 0 at every particle, and bitwise reproducibility of a second run."""
+    long-double oracle over all 10^6 sources (J33 also on its own: K1 closes the trace by construction, so only the oracle's
+    independently summed J33 is evidence for it), and bitwise reproducibility of a second run."""
     import flowunsteady_b200 as fb
     from flowunsteady_b200 import engine as E, fields
     from oracle import oracle as o
@@ -208,5 +209,4 @@ def test_full_size_1m_sampled_parity_and_properties():
     Uo, Jo = o.uj_direct("gaussianerf", x, g, s, x[idx], accum=1)
     assert relmax(a[idx, E.U:E.U + 3], Uo) < TOL64
     assert relmax(a[idx, E.J:E.J + 9], Jo) < TOL64
-    Jm = a[:, E.J:E.J + 9]
-    assert np.abs(Jm[:, 0] + Jm[:, 4] + Jm[:, 8]).max() < 1e-11 * np.abs(Jm).max()
+    assert relmax(a[idx, E.J + 8:E.J + 9], Jo[:, 8:9]) < 1e-11
