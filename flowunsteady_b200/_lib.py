@@ -106,6 +106,10 @@ SYMBOLS = {
     "vpmb200_let_ptrs": (C.c_int32, [_H, C.POINTER(C.c_void_p)]),
     "vpmb200_let_attach_tree": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "vpmb200_let_attach_records": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "vpmb200_let_attach_skeleton": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "vpmb200_let_halo_plan": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "vpmb200_let_halo_serve": (C.c_int32, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vpmb200_let_halo_set": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
     "vpmb200_let_evaluate": (C.c_int32, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "vpmb200_let_estr_records": (C.c_int32, [_H]),
     "vpmb200_let_estr_evaluate": (C.c_int32, [_H, C.c_void_p]),

@@ -415,6 +415,8 @@ int32_t estr_local_from_sorted(vpmb200_engine* e, const double* rec, int64_t nti
 // pfield.UJ(pfield; ...) through the GPU FMM (fmm.cuh): U, J [and the near-field E_str] of every particle
 int32_t do_uj_fmm(vpmb200_engine* e, int reset, int reset_sfs, int sfs) {
     e->shard_sorted_np = -1;
+    e->fmm.halo = FmmHalo();   // (a local-essential-tree evaluation may have left halo buffers attached)
+    e->let.halo_mode = false;
     const int hint = e->fmm_hint;
     const bool far_was_valid = e->fmm_far_valid;
     e->fmm_hint = 0;
@@ -516,6 +518,8 @@ int32_t check_fmm_settings(vpmb200_engine* e) {
 // results combine with one all-reduce.  pass 0: tree + U, J.   pass 1: near-field E_str from the (reduced) J rows.
 int32_t do_fmm_global(vpmb200_engine* e, double* G, int64_t ldg, int64_t ntot, int part, int nparts, int pass) {
     e->shard_sorted_np = -1;
+    e->fmm.halo = FmmHalo();
+    e->let.halo_mode = false;
     const vpmb200_schemes& s = e->sch;
     int32_t rc = check_fmm_settings(e);
     if (rc) return rc;
@@ -1514,6 +1518,49 @@ int32_t vpmb200_let_attach_tree(vpmb200_handle e, const void* cells_recv, const 
     return VPMB200_OK;
 }
 
+int32_t vpmb200_let_attach_skeleton(vpmb200_handle e, const void* cells_recv, int64_t slot_cells, const int64_t* ncells,
+                                    const int64_t* nparticles, const int64_t* nleaves) {
+    CHECK_HANDLE(e);
+    if (!ncells || !nparticles || !nleaves || slot_cells < 0) return fail(e, VPMB200_EINVAL, "let_attach_skeleton: bad arguments");
+    CU_TRY(e, cudaSetDevice(e->device));
+    LET_TRY(e, let_attach_skeleton(e->fmm, e->let, static_cast<const FmmCell*>(cells_recv), slot_cells, ncells, nparticles, nleaves,
+                                   e->stream, e->launches, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_halo_plan(vpmb200_handle e, int64_t* counts3, void** req_cells_dev, void** req_leaf_dev) {
+    CHECK_HANDLE(e);
+    if (!counts3) return fail(e, VPMB200_EINVAL, "counts3 is NULL");
+    CU_TRY(e, cudaSetDevice(e->device));
+    LET_TRY(e, let_halo_plan(e->fmm, e->let, counts3, e->stream, e->launches, err));
+    if (req_cells_dev) *req_cells_dev = e->let.req_cells;
+    if (req_leaf_dev) *req_leaf_dev = e->let.req_leaf;
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_halo_serve(vpmb200_handle e, const void* req_cells, int64_t ncell, const void* req_leaf, int64_t nleaf,
+                               double* M_out, double* rec_out) {
+    CHECK_HANDLE(e);
+    if (ncell < 0 || nleaf < 0 || (ncell > 0 && M_out && !req_cells) || (nleaf > 0 && rec_out && !req_leaf))
+        return fail(e, VPMB200_EINVAL, "let_halo_serve: bad arguments");
+    CU_TRY(e, cudaSetDevice(e->device));
+    LET_TRY(e, let_halo_serve(e->fmm, e->let, static_cast<const int*>(req_cells), ncell, static_cast<const int2*>(req_leaf), nleaf,
+                              M_out, rec_out, e->stream, e->launches, err));
+    return VPMB200_OK;
+}
+
+int32_t vpmb200_let_halo_set(vpmb200_handle e, const double* M2, const double* rec2) {
+    CHECK_HANDLE(e);
+    if (!e->let.halo_mode) return fail(e, VPMB200_EINVAL, "let_halo_set needs let_attach_skeleton first");
+    FmmHalo& h = e->fmm.halo;
+    h.rec_split = (int)e->let.n_own;
+    h.cell_split = e->let.ncells_own;
+    h.mslot = e->let.mslot;
+    if (M2) h.M2 = M2;
+    if (rec2) h.rec2 = rec2;
+    return VPMB200_OK;
+}
+
 int32_t vpmb200_let_attach_records(vpmb200_handle e, const double* rec_recv, int64_t slot_n, const int64_t* nparticles) {
     CHECK_HANDLE(e);
     if (!nparticles || slot_n < 0) return fail(e, VPMB200_EINVAL, "let_attach_records: bad arguments");
@@ -1525,12 +1572,13 @@ int32_t vpmb200_let_attach_records(vpmb200_handle e, const double* rec_recv, int
 
 int32_t vpmb200_let_evaluate(vpmb200_handle e, double* out_rows, int32_t reuse, int32_t stage) {
     CHECK_HANDLE(e);
-    if (stage < 0 || stage > 2) return fail(e, VPMB200_EINVAL, "let_evaluate: stage must be 0, 1 or 2");
+    if (!(stage >= 0 && stage <= 2) && stage != 5 && stage != 6)
+        return fail(e, VPMB200_EINVAL, "let_evaluate: stage must be 0, 1, 2, 5 or 6");
     if (e->let.n_own > 0 && !out_rows && stage != 1) return fail(e, VPMB200_EINVAL, "out_rows is NULL");
     CU_TRY(e, cudaSetDevice(e->device));
     const vpmb200_schemes& s = e->sch;
     if (reuse && (s.fmm_nonzero_sigma || !e->let.far_valid)) return fail(e, VPMB200_EINVAL, "let_evaluate: nothing to reuse");
-    if (!reuse && stage != 2 && e->let.work) CU_TRY(e, cudaMemsetAsync(e->let.work, 0, sizeof(long long) * e->let.bins, e->stream));
+    if (!reuse && stage != 2 && stage != 6 && e->let.work) CU_TRY(e, cudaMemsetAsync(e->let.work, 0, sizeof(long long) * e->let.bins, e->stream));
     LET_TRY(e, let_evaluate(e->fmm, e->let, s.fmm_theta, nzs_clearance(s), s.kernel, e->fmm_table_copies, e->gh_table,
                             out_rows, reuse != 0, stage, e->stream, e->launches, err));
     return VPMB200_OK;

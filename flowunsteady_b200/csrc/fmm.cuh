@@ -34,6 +34,17 @@ struct FmmCell {
     double pad_;
 };
 
+// Local essential tree, demand-driven (fmm_let.cuh): sources beyond the rank's own block live in separate RECEIVED buffers.
+// Near field: a run whose first record index is >= rec_split reads rec2[index - rec_split]; M2L: a source cell id >= cell_split
+// reads the multipole M2[mslot[id]].  The defaults switch both off (single GPU, all-gather LET).
+struct FmmHalo {
+    int rec_split = 0x7fffffff;
+    const double* rec2 = nullptr;
+    int cell_split = 0x7fffffff;
+    const double* M2 = nullptr;
+    const int* mslot = nullptr;
+};
+
 // ---- bounding box -----------------------------------------------------------------------------------------------
 __global__ void fmm_bounds_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                                   int64_t n, double* __restrict__ out /* gridDim.x * 6 */) {
@@ -395,7 +406,7 @@ __global__ void fmm_list_offsets_kernel(const uint64_t* __restrict__ keys, unsig
 template <int P>
 __global__ void __launch_bounds__(32)
 fmm_m2l_kernel(const FmmCell* __restrict__ cells, int ncells, const uint64_t* __restrict__ keys,
-               const unsigned int* __restrict__ off, const double* __restrict__ M, double* __restrict__ L) {
+               const unsigned int* __restrict__ off, const double* __restrict__ M, double* __restrict__ L, FmmHalo halo) {
     using Ops = FmmOps<P>;
     extern __shared__ double sacc[];  // [3 * NL][32]  (coefficient-major: conflict-free per-lane columns)
     const int c = blockIdx.x;
@@ -412,7 +423,8 @@ fmm_m2l_kernel(const FmmCell* __restrict__ cells, int ncells, const uint64_t* __
 #pragma unroll 1
         for (int comp = 0; comp < 3; ++comp) {
             double m[Ops::NM];
-            const double* src = M + ((size_t)j * 3 + comp) * Ops::NM;
+            const double* src = j >= halo.cell_split ? halo.M2 + ((size_t)halo.mslot[j] * 3 + comp) * Ops::NM
+                                                     : M + ((size_t)j * 3 + comp) * Ops::NM;
 #pragma unroll
             for (int a = 0; a < Ops::NM; ++a) m[a] = src[a];
             Ops::template m2l<32>(D, m, sacc + comp * Ops::NL * 32 + lane);   // this lane's private column
@@ -506,12 +518,15 @@ struct RunReader {
 // (k, off) is the cursor: `off` records of run k are already consumed.  Returns the number of records in flight.
 template <int BATCH = LEAF_BATCH>
 __device__ __forceinline__ int stage_batch_async(RunReader& rr, unsigned int& k, unsigned int b1, int& off,
-                                                 const double* __restrict__ rec, double* __restrict__ slice, int lane) {
+                                                 const double* __restrict__ rec, double* __restrict__ slice, int lane,
+                                                 const FmmHalo& halo) {
     int n = 0;
     while (k < b1 && n < BATCH) {
         const int2 r = rr.get(k, lane);
         const int take = min(r.y - off, BATCH - n);
-        const double2* g2 = reinterpret_cast<const double2*>(rec + (size_t)(r.x + off) * REC_REALS);
+        const double* base = r.x >= halo.rec_split ? halo.rec2 + (size_t)(r.x - halo.rec_split + off) * REC_REALS
+                                                   : rec + (size_t)(r.x + off) * REC_REALS;
+        const double2* g2 = reinterpret_cast<const double2*>(base);
         double2* s2 = reinterpret_cast<double2*>(slice + (size_t)n * REC_REALS);
         for (int q = lane; q < take * (REC_REALS / 2); q += 32) cp_async16(s2 + q, g2 + q);
         n += take;
@@ -623,7 +638,7 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
                    const int2* __restrict__ runs, const unsigned int* __restrict__ p2p_off, const double* __restrict__ rec,
                    const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                    const double* __restrict__ L, const double* __restrict__ gh_table, double* __restrict__ sU,
-                   double* __restrict__ sJ, int64_t lds) {
+                   double* __restrict__ sJ, int64_t lds, FmmHalo halo) {
     using Ops = FmmOps<P>;
     constexpr int BATCH = LeafGeom<REP>::BATCH;
     // shared: [G table x REP (gaussianerf)] then per warp { [3 * NL padded even] local expansion, 2 x [BATCH * 10] records }
@@ -685,13 +700,13 @@ fmm_leaf_uj_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ le
         unsigned int k = b0;
         int off = 0, pb = 0;
         __syncwarp();
-        int n_next = stage_batch_async<BATCH>(rr, k, b1, off, rec, buf0, lane);
+        int n_next = stage_batch_async<BATCH>(rr, k, b1, off, rec, buf0, lane, halo);
         while (true) {
             cp_async_wait_all();
             __syncwarp();
             int ns = n_next;
             if (ns == 0) break;
-            n_next = stage_batch_async<BATCH>(rr, k, b1, off, rec, pb ? buf0 : buf1, lane);
+            n_next = stage_batch_async<BATCH>(rr, k, b1, off, rec, pb ? buf0 : buf1, lane, halo);
             ns = pad_batch<false>(pb ? buf1 : buf0, ns, 2 * S, lane);
             const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0) + way * (REC_REALS / 2);
             for (int s = 0; s < ns; s += 2 * S) {
@@ -758,7 +773,7 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
                      const int2* __restrict__ runs, const unsigned int* __restrict__ p2p_off, const double* __restrict__ rec,
                      const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                      const double* __restrict__ sJ, int64_t lds, int transposed, const double* __restrict__ z_table,
-                     double* __restrict__ sE) {
+                     double* __restrict__ sE, FmmHalo halo) {
     extern __shared__ __align__(16) double smem[];   // [Z table (gaussianerf)] then per warp 2 x [LEAF_BATCH * 10] records
     constexpr int TABD = KERNEL == K_GAUSSIANERF ? ((VPM_GZ_NINT + 1) & ~1) : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -790,13 +805,13 @@ fmm_leaf_estr_kernel(const FmmCell* __restrict__ cells, const int* __restrict__ 
         unsigned int k = b0;
         int off = 0, pb = 0;
         __syncwarp();
-        int n_next = stage_batch_async(rr, k, b1, off, rec, buf0, lane);
+        int n_next = stage_batch_async(rr, k, b1, off, rec, buf0, lane, halo);
         while (true) {
             cp_async_wait_all();
             __syncwarp();
             int ns = n_next;
             if (ns == 0) break;
-            n_next = stage_batch_async(rr, k, b1, off, rec, pb ? buf0 : buf1, lane);
+            n_next = stage_batch_async(rr, k, b1, off, rec, pb ? buf0 : buf1, lane, halo);
             ns = pad_batch<true>(pb ? buf1 : buf0, ns, 2 * S, lane);
             const double2* r2p = reinterpret_cast<const double2*>(pb ? buf1 : buf0) + way * (REC_REALS / 2);
             for (int s = 0; s < ns; s += 2 * S) {

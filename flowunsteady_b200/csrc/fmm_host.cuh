@@ -40,6 +40,8 @@ struct FmmWorkspace {
     // combined arrays ([own | other ranks']) instead of w.cells / w.M; targets are always the own cells [0, ncells)
     const FmmCell* cells_eval = nullptr;
     const double* M_eval = nullptr;
+    FmmHalo halo;                   // demand-driven LET: received multipoles / records (defaults: off)
+    int64_t count_at_cap = 0;       // entries of count_at (the halo mode indexes it beyond the particle count)
     // device time of the sections of the LAST evaluation (CUDA events on the engine's stream; vpmb200_fmm_times):
     // 0 sort + tree, 1 lists (traversal sweeps incl. their host read-backs, sorts), 2 upward, 3 M2L + L2L, 4 L2P + near field,
     // 5 E_str near field
@@ -168,6 +170,7 @@ inline cudaError_t fmm_reserve_particles(FmmWorkspace& w, int64_t n, std::string
     FMM_TRY(cudaMalloc(&w.sJ, sizeof(double) * 9 * w.lds));
     FMM_TRY(cudaMalloc(&w.sE, sizeof(double) * 3 * w.lds));
     FMM_TRY(cudaMalloc(&w.count_at, sizeof(int) * cap_n));
+    w.count_at_cap = cap_n;
     if (!w.counters) FMM_TRY(cudaMalloc(&w.counters, sizeof(FmmCounters)));
     if (!w.bounds) FMM_TRY(cudaMalloc(&w.bounds, sizeof(double) * 6 * 256));
     w.cap_n = cap_n;
@@ -235,7 +238,7 @@ struct FmmPasses {
             return e;
         const FmmCell* cells = w.cells_eval ? w.cells_eval : w.cells;
         const double* M = w.M_eval ? w.M_eval : w.M;
-        fmm_m2l_kernel<P><<<w.ncells, 32, smem, st>>>(cells, w.ncells, w.m2l_sorted, w.m2l_off, M, w.L);
+        fmm_m2l_kernel<P><<<w.ncells, 32, smem, st>>>(cells, w.ncells, w.m2l_sorted, w.m2l_off, M, w.L, w.halo);
         ++launches;
         for (int l = 1; l + 1 < (int)lvl.size(); ++l) {
             const int c0 = lvl[l], c1 = lvl[l + 1];
@@ -263,7 +266,7 @@ struct FmmPasses {
         int grid = 0;
         if ((e = fmm_leaf_grid(w, kfn, 32 * WARPS, smem, (nl + WARPS - 1) / WARPS, st, grid)) != cudaSuccess) return e;
         kfn<<<grid, 32 * WARPS, smem, st>>>(
-            w.cells_eval ? w.cells_eval : w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds);
+            w.cells_eval ? w.cells_eval : w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.L, gh_table, w.sU, w.sJ, w.lds, w.halo);
         ++launches;
         return cudaGetLastError();
     }
@@ -591,7 +594,7 @@ inline cudaError_t fmm_estr(FmmWorkspace& w, int kernel, int block, int transpos
     cudaFuncSetAttribute(fmm_leaf_estr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
     if ((eg = fmm_leaf_grid(w, fmm_leaf_estr_kernel<K>, 32 * LEAF_WARPS, smem, (nl + LEAF_WARPS - 1) / LEAF_WARPS, st, grid)) != cudaSuccess) return eg; \
     fmm_leaf_estr_kernel<K><<<grid, 32 * LEAF_WARPS, smem, st>>>(                                                          \
-        w.cells_eval ? w.cells_eval : w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE)
+        w.cells_eval ? w.cells_eval : w.cells, w.leaves + w.leaf_lo, nl, &w.counters->next, w.runs, w.p2p_off, w.rec, w.sx, w.sy, w.sz, w.sJ, w.lds, transposed, z_table, w.sE, w.halo)
     switch (kernel) {
     case K_GAUSSIANERF: FMM_ESTR_CASE(K_GAUSSIANERF); break;
     case K_WINCKELMANS: FMM_ESTR_CASE(K_WINCKELMANS); break;

@@ -65,10 +65,24 @@ struct FmmLet {
     std::vector<int64_t> ncells_of;    // cells of every rank's tree
     bool far_valid = false;            // L of the last evaluation still valid (DynamicSFS second evaluation)
     int P = 0;
+    // demand-driven halo ("let_halo"): only the skeletons are gathered; multipoles and records of the cells / leaves the
+    // traversal actually touches are requested from their owners
+    bool halo_mode = false;
+    int nleaves_remote = 0;            // leaves of the other ranks' trees (their ordinals index rleaf / pneed / poff)
+    std::vector<int> leaf_off;         // first ordinal of every rank's leaves (own rank: 0, unused)
+    std::vector<int64_t> nleaves_of;
+    int2* rleaf = nullptr;             // remote leaf ordinal -> (first record in the OWNER's order, count)
+    int *mneed = nullptr, *mslot = nullptr, *pneed = nullptr, *pslot = nullptr, *pcnt = nullptr, *poff = nullptr;
+    int* req_cells = nullptr;          // needed remote cells as owner-local ids, grouped by owner
+    int2* req_leaf = nullptr;          // needed remote leaves as (first record, count) in the owner's order, grouped by owner
+    int64_t cap_hc = 0, cap_hl = 0;    // capacities of the per-cell / per-remote-leaf arrays
+    int* serve_off = nullptr;          // owner side: record offset of every requested leaf
+    int64_t cap_serve = 0;
 };
 
 inline void let_free(FmmLet& t) {
-    void* ptrs[] = {t.hkeys, t.hkeys_alt, t.hperm, t.hperm_alt, t.hist, t.hpre, t.binmax, t.split_idx, t.cells_all, t.M_all, t.work};
+    void* ptrs[] = {t.hkeys, t.hkeys_alt, t.hperm, t.hperm_alt, t.hist, t.hpre, t.binmax, t.split_idx, t.cells_all, t.M_all, t.work,
+                    t.rleaf, t.mneed, t.mslot, t.pneed, t.pslot, t.pcnt, t.poff, t.req_cells, t.req_leaf, t.serve_off};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     t = FmmLet();
@@ -257,6 +271,90 @@ __global__ void let_finish_kernel(const double* __restrict__ res, int ncol, int6
         double* d = soa + (size_t)(rowB + k) * ld + p;
         *d = accumulate ? *d + r[nA + k] : r[nA + k];
     }
+}
+
+// ---- demand-driven halo ------------------------------------------------------------------------------------------------
+// owner side, before the skeleton leaves: every leaf carries its ordinal among the tree's leaves (in the unused pad_ field)
+__global__ void let_stamp_leaves_kernel(FmmCell* __restrict__ cells, int ncells, const int* __restrict__ leaf_pos) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells) cells[c].pad_ = cells[c].nchild == 0 ? (double)leaf_pos[c] : -1.0;
+}
+
+// another rank's SKELETON behind the own cells: indices move as in let_attach_cells_kernel, but a leaf's particle range is not
+// here — its `start` becomes n_own + (global ordinal of the remote leaf), the id the traversal pushes into the P2P list;
+// rleaf keeps where the records sit on the owner, count_at (indexed by that id) the count
+__global__ void let_attach_skeleton_kernel(const FmmCell* __restrict__ src, int nc, FmmCell* __restrict__ dst, int cell_off,
+                                           int leaf_off, int n_own, int2* __restrict__ rleaf, int* __restrict__ count_at) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    FmmCell v = src[c];
+    if (v.parent >= 0) v.parent += cell_off;
+    if (v.child0 >= 0) v.child0 += cell_off;
+    if (v.nchild == 0) {
+        const int o = leaf_off + (int)v.pad_;
+        rleaf[o] = make_int2(v.start, v.count);
+        count_at[n_own + o] = v.count;
+        v.start = n_own + o;
+    } else {
+        v.start = n_own;
+    }
+    dst[c] = v;
+}
+
+__global__ void let_mark_m2l_kernel(const uint64_t* __restrict__ keys, unsigned int n, int cell_split, int* __restrict__ mneed) {
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int j = (int)(keys[k] & 0xffffffffu);
+    if (j >= cell_split) mneed[j] = 1;
+}
+__global__ void let_mark_p2p_kernel(const uint64_t* __restrict__ keys, unsigned int n, int n_own, const int2* __restrict__ rleaf,
+                                    int* __restrict__ pneed, int* __restrict__ pcnt) {
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int s = (int)(keys[k] & 0xffffffffu);
+    if (s >= n_own) {
+        pneed[s - n_own] = 1;
+        pcnt[s - n_own] = rleaf[s - n_own].y;
+    }
+}
+// needed cells of one owner's block -> owner-local ids at their compact slots
+__global__ void let_compact_cells_kernel(const int* __restrict__ mneed, const int* __restrict__ mslot, int c0, int c1,
+                                         int* __restrict__ req_cells) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < c1 && mneed[c]) req_cells[mslot[c]] = c - c0;
+}
+__global__ void let_compact_leaves_kernel(const int* __restrict__ pneed, const int* __restrict__ pslot, const int2* __restrict__ rleaf,
+                                          int n, int2* __restrict__ req_leaf) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < n && pneed[o]) req_leaf[pslot[o]] = rleaf[o];
+}
+// P2P runs of remote leaves: (n_own + offset of the leaf's records inside the received halo buffer, count)
+__global__ void let_halo_runs_kernel(const uint64_t* __restrict__ keys, unsigned int n, int n_own, const int2* __restrict__ rleaf,
+                                     const int* __restrict__ poff, int2* __restrict__ runs) {
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int s = (int)(keys[k] & 0xffffffffu);
+    if (s >= n_own) runs[k] = make_int2(n_own + poff[s - n_own], rleaf[s - n_own].y);
+}
+// owner side: requested multipoles, and the records of the requested leaves back to back (one warp per leaf)
+__global__ void let_serve_M_kernel(const int* __restrict__ ids, int n, int nm3, const double* __restrict__ M, double* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * nm3) return;
+    const int i = (int)(t / nm3), a = (int)(t % nm3);
+    out[t] = M[(size_t)ids[i] * nm3 + a];
+}
+__global__ void let_serve_counts_kernel(const int2* __restrict__ leaves, int n, int* __restrict__ cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt[i] = leaves[i].y;
+}
+__global__ void let_serve_rec_kernel(const int2* __restrict__ leaves, const int* __restrict__ off, int n, const double* __restrict__ rec,
+                                     double* __restrict__ out) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int2 l = leaves[i];
+    const double* src = rec + (size_t)l.x * REC_REALS;
+    double* dst = out + (size_t)off[i] * REC_REALS;
+    for (int q = threadIdx.x & 31; q < l.y * REC_REALS; q += 32) dst[q] = src[q];
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -538,6 +636,8 @@ inline cudaError_t let_build(FmmWorkspace& w, FmmLet& t, const double* rows, int
         let_top_smax_kernel<<<(w.ncells + 127) / 128, 128, 0, st>>>(w.cells, w.ncells, w.keys, t.Lc, t.binmax);
         ++launches;
     }
+    let_stamp_leaves_kernel<<<(w.ncells + 255) / 256, 256, 0, st>>>(w.cells, w.ncells, w.leaf_pos);   // (for the halo mode)
+    ++launches;
     fmm_tic(w, 2, st);
     cudaError_t e2 = let_upward(w, p, t.lvl, st, launches);
     fmm_toc(w, 2, st);
@@ -590,6 +690,8 @@ inline cudaError_t let_attach_tree(FmmWorkspace& w, FmmLet& t, const FmmCell* ce
         poff += nparticles[q];
     }
     t.ncells_all = coff;
+    t.halo_mode = false;
+    w.halo = FmmHalo();
     FMM_TRY(cudaGetLastError());
     return cudaSuccess;
 }
@@ -613,7 +715,7 @@ inline cudaError_t let_evaluate(FmmWorkspace& w, FmmLet& t, double theta, double
                                 const double* gh_table, double* out, bool reuse, int stage, cudaStream_t st, uint64_t& launches,
                                 std::string& err) {
     if (t.n_own <= 0) return cudaSuccess;
-    if (stage != 2 && !reuse) {
+    if (stage != 2 && stage != 6 && !reuse) {
         std::vector<uint64_t> seeds;
         seeds.push_back(0);                                      // (own root, own root)
         for (int q = 0; q < t.nparts; ++q)                       // (own root, root of rank q's tree); empty ranks have no tree
@@ -626,13 +728,15 @@ inline cudaError_t let_evaluate(FmmWorkspace& w, FmmLet& t, double theta, double
             ++launches;
         }
     }
+    if (stage == 5) return cudaSuccess;                          // lists only (the halo is planned from them)
     w.cells_eval = t.cells_all;
-    w.M_eval = t.M_all;
-    cudaError_t e1 = fmm_evaluate(w, t.P, kernel, block, gh_table, t.lvl, st, launches, reuse, /*skip_upward=*/true, stage);
+    w.M_eval = t.halo_mode ? w.M : t.M_all;                      // halo mode: own multipoles in place, the others' in w.halo.M2
+    cudaError_t e1 = fmm_evaluate(w, t.P, kernel, block, gh_table, t.lvl, st, launches, reuse, /*skip_upward=*/true,
+                                  stage == 6 ? 1 : stage);
     w.cells_eval = nullptr;
     w.M_eval = nullptr;
     if (e1 != cudaSuccess) { err = std::string("LET evaluate: ") + cudaGetErrorString(e1); return e1; }
-    if (stage == 1) return cudaSuccess;
+    if (stage == 1 || stage == 6) return cudaSuccess;
     t.far_valid = true;
     let_out_rows_kernel<<<(unsigned)((t.n_own + 255) / 256), 256, 0, st>>>(w.sU, 3, w.sJ, 9, w.lds, t.n_own, w.perm, out);
     ++launches;
@@ -659,6 +763,166 @@ inline cudaError_t let_estr_evaluate(FmmWorkspace& w, FmmLet& t, int kernel, int
     if (e1 != cudaSuccess) { err = std::string("LET E_str: ") + cudaGetErrorString(e1); return e1; }
     let_out_rows_kernel<<<(unsigned)((t.n_own + 255) / 256), 256, 0, st>>>(w.sE, 3, w.sE, 0, w.lds, t.n_own, w.perm, out);
     ++launches;
+    FMM_TRY(cudaGetLastError());
+    return cudaSuccess;
+}
+
+// ---- demand-driven halo: host side ---------------------------------------------------------------------------------------
+template <typename T>
+inline cudaError_t let_grow_arr(T*& p, int64_t& cap, int64_t need, std::string& err) {
+    if (need <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const int64_t c = need + need / 4 + 1024;
+    FMM_TRY(cudaMalloc(&p, sizeof(T) * c));
+    cap = c;
+    return cudaSuccess;
+}
+
+// phase 6a (halo mode): the other ranks' SKELETONS only.  cells_recv: all-gathered, rank q's block at q * slot_cells.
+inline cudaError_t let_attach_skeleton(FmmWorkspace& w, FmmLet& t, const FmmCell* cells_recv, int64_t slot_cells, const int64_t* ncells,
+                                       const int64_t* nparticles, const int64_t* nleaves, cudaStream_t st, uint64_t& launches,
+                                       std::string& err) {
+    const int G = t.nparts;
+    int64_t total = 0, nl = 0;
+    for (int q = 0; q < G; ++q) {
+        total += ncells[q];
+        if (q != t.part) nl += nleaves[q];
+    }
+    if (ncells[t.part] != t.ncells_own || nparticles[t.part] != t.n_own) { err = "LET: own block sizes do not match"; return cudaErrorInvalidValue; }
+    if (total > t.cap_cells_all || !t.cells_all) {
+        if (t.cells_all) cudaFree(t.cells_all);
+        t.cells_all = nullptr;
+        t.cap_cells_all = 0;
+        const int64_t cap = total + total / 4 + 64;
+        FMM_TRY(cudaMalloc(&t.cells_all, sizeof(FmmCell) * cap));
+        t.cap_cells_all = cap;
+    }
+    {   // per-cell and per-remote-leaf bookkeeping (+1: the scans read one element past the end for the totals)
+        int64_t c1 = t.cap_hc, c2 = t.cap_hc, c3 = t.cap_hc;
+        FMM_TRY(let_grow_arr(t.mneed, c1, total + 1, err));
+        FMM_TRY(let_grow_arr(t.mslot, c2, total + 1, err));
+        FMM_TRY(let_grow_arr(t.req_cells, c3, total + 1, err));
+        t.cap_hc = std::min(c1, std::min(c2, c3));
+        int64_t l1 = t.cap_hl, l2 = t.cap_hl, l3 = t.cap_hl, l4 = t.cap_hl, l5 = t.cap_hl, l6 = t.cap_hl;
+        FMM_TRY(let_grow_arr(t.rleaf, l1, nl + 1, err));
+        FMM_TRY(let_grow_arr(t.pneed, l2, nl + 1, err));
+        FMM_TRY(let_grow_arr(t.pslot, l3, nl + 1, err));
+        FMM_TRY(let_grow_arr(t.pcnt, l4, nl + 1, err));
+        FMM_TRY(let_grow_arr(t.poff, l5, nl + 1, err));
+        FMM_TRY(let_grow_arr(t.req_leaf, l6, nl + 1, err));
+        t.cap_hl = std::min(std::min(l1, l2), std::min(std::min(l3, l4), std::min(l5, l6)));
+    }
+    if (t.n_own + nl > w.count_at_cap) {   // count_at is indexed by n_own + remote leaf ordinal in this mode
+        if (w.count_at) cudaFree(w.count_at);
+        w.count_at = nullptr;
+        w.count_at_cap = 0;
+        const int64_t cap = t.n_own + nl + (t.n_own + nl) / 4 + 1024;
+        FMM_TRY(cudaMalloc(&w.count_at, sizeof(int) * cap));
+        w.count_at_cap = cap;
+    }
+    t.cell_off.assign(G, 0);
+    t.part_off.assign(G, 0);
+    t.leaf_off.assign(G, 0);
+    t.ncells_of.assign(ncells, ncells + G);
+    t.nleaves_of.assign(nleaves, nleaves + G);
+    if (t.ncells_own > 0) FMM_TRY(cudaMemcpyAsync(t.cells_all, w.cells, sizeof(FmmCell) * t.ncells_own, cudaMemcpyDeviceToDevice, st));
+    int coff = t.ncells_own, loff = 0;
+    for (int q = 0; q < G; ++q) {
+        if (q == t.part) continue;
+        t.cell_off[q] = coff;
+        t.leaf_off[q] = loff;
+        const int nc = (int)ncells[q];
+        if (nc > 0) {
+            let_attach_skeleton_kernel<<<(nc + 255) / 256, 256, 0, st>>>(cells_recv + (size_t)q * slot_cells, nc, t.cells_all + coff, coff, loff,
+                                                                       (int)t.n_own, t.rleaf, w.count_at);
+            ++launches;
+        }
+        coff += nc;
+        loff += (int)nleaves[q];
+    }
+    t.ncells_all = coff;
+    t.nleaves_remote = loff;
+    t.halo_mode = true;
+    w.halo = FmmHalo();
+    FMM_TRY(cudaGetLastError());
+    return cudaSuccess;
+}
+
+// After the interaction lists exist (let_evaluate stage 5): which remote multipoles and which remote leaves' records does this
+// rank need?  counts3[3 q + 0 / 1 / 2] = cells / leaves / records requested from rank q (zeros for the rank itself); the request
+// arrays t.req_cells / t.req_leaf are grouped by owner in rank order; the P2P runs of remote leaves are rewritten to point into
+// the halo record buffer (in request order).
+inline cudaError_t let_halo_plan(FmmWorkspace& w, FmmLet& t, int64_t* counts3, cudaStream_t st, uint64_t& launches, std::string& err) {
+    const int G = t.nparts;
+    for (int q = 0; q < 3 * G; ++q) counts3[q] = 0;
+    if (!t.halo_mode) { err = "LET: halo plan without a skeleton attach"; return cudaErrorInvalidValue; }
+    const int nc = t.ncells_all, nl = t.nleaves_remote;
+    FMM_TRY(cudaMemsetAsync(t.mneed, 0, sizeof(int) * (nc + 1), st));
+    FMM_TRY(cudaMemsetAsync(t.pneed, 0, sizeof(int) * (nl + 1), st));
+    FMM_TRY(cudaMemsetAsync(t.pcnt, 0, sizeof(int) * (nl + 1), st));
+    if (t.n_own > 0) {
+        if (w.n_m2l > 0) let_mark_m2l_kernel<<<(w.n_m2l + 255) / 256, 256, 0, st>>>(w.m2l_sorted, w.n_m2l, t.ncells_own, t.mneed);
+        if (w.n_p2p > 0) let_mark_p2p_kernel<<<(w.n_p2p + 255) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, (int)t.n_own, t.rleaf, t.pneed, t.pcnt);
+        launches += 2;
+    }
+    FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, t.mneed, t.mslot, nc + 1, st));
+    FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, t.pneed, t.pslot, nl + 1, st));
+    FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, t.pcnt, t.poff, nl + 1, st));
+    launches += 3;
+    // per-owner totals: differences of the scans at the block boundaries
+    std::vector<int> hb(6 * G, 0);
+    for (int q = 0; q < G; ++q) {
+        if (q == t.part) continue;
+        const int c0 = t.cell_off[q], c1 = c0 + (int)t.ncells_of[q], l0 = t.leaf_off[q], l1 = l0 + (int)t.nleaves_of[q];
+        FMM_TRY(cudaMemcpyAsync(&hb[6 * q + 0], t.mslot + c0, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaMemcpyAsync(&hb[6 * q + 1], t.mslot + c1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaMemcpyAsync(&hb[6 * q + 2], t.pslot + l0, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaMemcpyAsync(&hb[6 * q + 3], t.pslot + l1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaMemcpyAsync(&hb[6 * q + 4], t.poff + l0, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FMM_TRY(cudaMemcpyAsync(&hb[6 * q + 5], t.poff + l1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (t.ncells_of[q] > 0) {
+            let_compact_cells_kernel<<<((int)t.ncells_of[q] + 255) / 256, 256, 0, st>>>(t.mneed, t.mslot, c0, c1, t.req_cells);
+            ++launches;
+        }
+    }
+    if (nl > 0) {
+        let_compact_leaves_kernel<<<(nl + 255) / 256, 256, 0, st>>>(t.pneed, t.pslot, t.rleaf, nl, t.req_leaf);
+        ++launches;
+    }
+    if (t.n_own > 0 && w.n_p2p > 0) {
+        let_halo_runs_kernel<<<(w.n_p2p + 255) / 256, 256, 0, st>>>(w.p2p_sorted, w.n_p2p, (int)t.n_own, t.rleaf, t.poff, w.runs);
+        ++launches;
+    }
+    FMM_TRY(cudaStreamSynchronize(st));
+    for (int q = 0; q < G; ++q) {
+        counts3[3 * q + 0] = hb[6 * q + 1] - hb[6 * q + 0];
+        counts3[3 * q + 1] = hb[6 * q + 3] - hb[6 * q + 2];
+        counts3[3 * q + 2] = hb[6 * q + 5] - hb[6 * q + 4];
+    }
+    FMM_TRY(cudaGetLastError());
+    return cudaSuccess;
+}
+
+// Owner side: the multipoles of the requested cells (ids local to this rank's tree; M_out may be NULL when only records are
+// re-served) and the records of the requested leaves, back to back in request order.
+inline cudaError_t let_halo_serve(FmmWorkspace& w, FmmLet& t, const int* req_cells, int64_t ncell, const int2* req_leaf, int64_t nleaf,
+                                  double* M_out, double* rec_out, cudaStream_t st, uint64_t& launches, std::string& err) {
+    const int nm3 = 3 * let_nm(t.P);
+    if (M_out && ncell > 0) {
+        const int64_t tot = ncell * nm3;
+        let_serve_M_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(req_cells, (int)ncell, nm3, w.M, M_out);
+        ++launches;
+    }
+    if (rec_out && nleaf > 0) {
+        FMM_TRY(let_grow_arr(t.serve_off, t.cap_serve, 2 * (nleaf + 1), err));
+        int* cnt = t.serve_off + (nleaf + 1);
+        let_serve_counts_kernel<<<(unsigned)((nleaf + 255) / 256), 256, 0, st>>>(req_leaf, (int)nleaf, cnt);
+        FMM_CUB(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, t.serve_off, (int)nleaf, st));
+        let_serve_rec_kernel<<<(unsigned)((nleaf + 3) / 4), 128, 0, st>>>(req_leaf, t.serve_off, (int)nleaf, w.rec, rec_out);
+        launches += 3;
+    }
     FMM_TRY(cudaGetLastError());
     return cudaSuccess;
 }

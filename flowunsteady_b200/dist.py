@@ -104,7 +104,10 @@ class ShardedField:
              pack_estr_records, uj_from_records, estr_from_records, stage, get_schemes, set_time, get_time, stream, let_*).
     device:  torch device the exchange buffers live on ("cuda:N" for Engine).
     coll:    collectives object (default: TorchCollectives(group)).
-    fmm:     "let" (local essential tree) or "replicated" (round-1 scheme) for vpm_UJ = UJ_fmm.
+    fmm:     "let" (local essential tree, every rank receives all skeletons, multipoles and records), "let_halo" (same tree
+             and same results, but only the skeletons are all-gathered: multipoles and source records travel on demand,
+             owner -> the ranks whose traversal listed them; per-rank memory ~ own share + halo) or "replicated" (round-1
+             scheme) for vpm_UJ = UJ_fmm.
     """
 
     def __init__(self, backend, max_local: int, device, group=None, coll=None, fmm: str = "let", let_level: int = LET_LEVEL):
@@ -243,9 +246,12 @@ class ShardedField:
             rows = c.all_to_all_rows(send[:n_home], L["send"], L["recv"], out=self._buf("rows", max(n_own, 1) * 7).view(-1, 7))
             L["rows"] = rows                                         # the engine reads it until the evaluation ends
             lap("2 pack + all-to-all of particle rows")
-            info = b.let_build(rows.data_ptr(), n_own, L["n_all"], reuse)
+            halo = self.fmm_mode == "let_halo"
+            info = b.let_build(rows.data_ptr(), n_own, n_own if halo else L["n_all"], reuse)
             cells_ptr, M_ptr, rec_ptr = b.let_ptrs()
             lap("3 owner sort, tree, upward pass")
+            if halo:
+                return self._let_halo_evaluate(L, info, cells_ptr, n_own, n_home, reuse, reset, reset_sfs, sfs, hint, sch, lap)
             if not reuse:
                 ncells_own, _, nm3, _ = info
                 sizes = c.all_gather_ints([n_own, ncells_own], dev)
@@ -307,6 +313,75 @@ class ShardedField:
             L["far_valid"] = bool(hint == 1 and not sch.fmm_nonzero_sigma)
             del keep
 
+    def _let_halo_evaluate(self, L, info, cells_ptr, n_own, n_home, reuse, reset, reset_sfs, sfs, hint, sch, lap):
+        """Phases 4-8 of the LET evaluation with a demand-driven halo (vpmb200.h: vpmb200_let_attach_skeleton ...): the
+        skeletons are all-gathered, the traversal runs, and every rank then REQUESTS the multipoles of the remote cells on
+        its M2L list and the records of the remote leaves on its P2P list from their owners (two all-to-alls of ids, two of
+        payload).  Called inside the stream context of _uj_fmm_let."""
+        b, c, dev, G, r = self.b, self.coll, self.device, self.world, self.rank
+        ncells_own, nleaves, nm3, _ = info
+        out = self._buf("out", max(n_own, 1) * 12).view(-1, 12)
+        if not reuse:
+            sizes = c.all_gather_ints([n_own, ncells_own, nleaves if n_own > 0 else 0], dev)
+            L["np"], L["nc"], L["nl"] = ([s[k] for s in sizes] for k in range(3))
+            L["slot_c"] = max(max(L["nc"]), 1)
+            cb = b.let_cell_bytes()
+            sc = self._buf("sc", L["slot_c"] * cb, torch.uint8)
+            sc[:ncells_own * cb] = self._dev_view(cells_ptr, ncells_own * cb, "|u1", torch.uint8)
+            cells_all = c.all_gather(sc, out=self._buf("cells_all", G * L["slot_c"] * cb, torch.uint8))
+            b.let_attach_skeleton(cells_all.data_ptr(), L["slot_c"], L["nc"], L["np"], L["nl"])
+            lap("4 all-gather skeletons, attach")
+            b.let_evaluate(out.data_ptr(), False, 5)                  # interaction lists
+            want, pc, pl = b.let_halo_plan(G)                         # want[3 q + (0, 1, 2)]: cells, leaves, records from rank q
+            allw = c.all_gather_ints(want, dev)                       # allw[q][3 k + j]: what rank q wants from rank k
+            give = [allw[q][3 * r:3 * r + 3] for q in range(G)]       # what rank q wants from this rank
+            wc, wl = [want[3 * q] for q in range(G)], [want[3 * q + 1] for q in range(G)]
+            ids_c = self._dev_view(pc, max(sum(wc), 1), "<i4", torch.int32)[:sum(wc)].view(-1, 1)
+            ids_l = self._dev_view(pl, 2 * max(sum(wl), 1), "<i4", torch.int32)[:2 * sum(wl)].view(-1, 2)
+            gc, gl = [g[0] for g in give], [g[1] for g in give]
+            L["ask_c"] = c.all_to_all_rows(ids_c, wc, gc, out=self._buf("ask_c", max(sum(gc), 1), torch.int32).view(-1, 1))
+            L["ask_l"] = c.all_to_all_rows(ids_l, wl, gl, out=self._buf("ask_l", 2 * max(sum(gl), 1), torch.int32).view(-1, 2))
+            L["want"], L["give"] = want, give
+            lap("5 lists, halo plan, all-to-all of the requests")
+        want, give = L["want"], L["give"]
+        gc, gl, gr = ([g[k] for g in give] for k in range(3))
+        wc, wr = [want[3 * q] for q in range(G)], [want[3 * q + 2] for q in range(G)]
+
+        def serve(with_multipoles: bool):
+            """owner side: gather what the others listed; then the payload all-to-all(s); then point the kernels at the halo"""
+            M_out = self._buf("halo_M_out", max(sum(gc), 1) * nm3).view(-1, nm3) if with_multipoles else None
+            rec_out = self._buf("halo_rec_out", max(sum(gr), 1) * 10).view(-1, 10)
+            b.let_halo_serve(L["ask_c"].data_ptr(), sum(gc) if with_multipoles else 0, L["ask_l"].data_ptr(), sum(gl),
+                             M_out.data_ptr() if with_multipoles else 0, rec_out.data_ptr())
+            if with_multipoles:
+                L["M2"] = c.all_to_all_rows(M_out[:sum(gc)], gc, wc, out=self._buf("halo_M", max(sum(wc), 1) * nm3).view(-1, nm3))
+            L["rec2"] = c.all_to_all_rows(rec_out[:sum(gr)], gr, wr, out=self._buf("halo_rec", max(sum(wr), 1) * 10).view(-1, 10))
+            b.let_halo_set(L["M2"].data_ptr(), L["rec2"].data_ptr())
+            L["halo_bytes"] = 8 * (sum(wc) * nm3 + sum(wr) * 10)
+
+        serve(not reuse)
+        lap("6 halo: serve, all-to-all of multipoles + records")
+        b.let_evaluate(out.data_ptr(), reuse, 6)                      # M2L + L2L
+        b.let_evaluate(out.data_ptr(), reuse, 2)                      # L2P + near field + output rows
+        if not reuse and self.let_balance and G > 1:
+            c.all_reduce_(self._dev_view(b.let_work(), 8 ** self.let_level, "<i8", torch.int64), "sum")
+            self._let_work_ready = True
+        lap("7 M2L, L2L, L2P + near field")
+        res = c.all_to_all_rows(out[:n_own], L["recv"], L["send"], out=self._buf("res", max(n_home, 1) * 12).view(-1, 12))
+        b.let_finish(res.data_ptr(), 0, reset)
+        lap("8 inverse all-to-all of U, J + scatter")
+        if reset_sfs:
+            b.reset_particles_sfs()
+        if sfs:
+            b.let_estr_records()
+            serve(False)
+            outE = self._buf("outE", max(n_own, 1) * 3).view(-1, 3)
+            b.let_estr_evaluate(outE.data_ptr())
+            resE = c.all_to_all_rows(outE[:n_own], L["recv"], L["send"], out=self._buf("resE", max(n_home, 1) * 3).view(-1, 3))
+            b.let_finish(resE.data_ptr(), 1, False)
+            lap("9 E_str: records, halo, near field, return")
+        L["far_valid"] = bool(hint == 1 and not sch.fmm_nonzero_sigma)
+
     # ---- UJ_fmm over the sharded field: replicated tree, leaves split over the ranks (round-1 scheme) ----------------
     def _uj_fmm(self, reset: bool, reset_sfs: bool, sfs: bool):
         """All ranks gather (X, Gamma, sigma) of every particle (56 B each), build the SAME tree, evaluate 1/world of the
@@ -359,7 +434,7 @@ class ShardedField:
     def uj(self, reset: bool = True, reset_sfs: bool = False, sfs: bool = False):
         b = self.b
         if b.get_schemes().uj == _E.UJ_IDS["fmm"]:
-            if self.fmm_mode == "let":
+            if self.fmm_mode in ("let", "let_halo"):
                 return self._uj_fmm_let(reset, reset_sfs, sfs)
             return self._uj_fmm(reset, reset_sfs, sfs)
         if reset:

@@ -286,6 +286,27 @@ class Engine:
         a, b = (C.c_int64 * g)(*[int(v) for v in ncells]), (C.c_int64 * g)(*[int(v) for v in nparticles])
         self._check(self._L.vpmb200_let_attach_tree(self._h, C.c_void_p(cells_ptr), C.c_void_p(M_ptr), int(slot_cells), a, b))
 
+    def let_attach_skeleton(self, cells_ptr: int, slot_cells: int, ncells, nparticles, nleaves):
+        g = len(ncells)
+        a, b, c = ((C.c_int64 * g)(*[int(v) for v in x]) for x in (ncells, nparticles, nleaves))
+        self._check(self._L.vpmb200_let_attach_skeleton(self._h, C.c_void_p(cells_ptr), int(slot_cells), a, b, c))
+
+    def let_halo_plan(self, nparts: int):
+        """-> (counts3 [3 * nparts], device pointer of the requested cell ids, of the requested (start, count) leaf pairs)"""
+        cnt = (C.c_int64 * (3 * nparts))()
+        pc, pl = C.c_void_p(), C.c_void_p()
+        self._check(self._L.vpmb200_let_halo_plan(self._h, cnt, C.byref(pc), C.byref(pl)))
+        return [int(v) for v in cnt], pc.value or 0, pl.value or 0
+
+    def let_halo_serve(self, req_cells_ptr: int, ncell: int, req_leaf_ptr: int, nleaf: int, M_out_ptr: int, rec_out_ptr: int):
+        self._check(self._L.vpmb200_let_halo_serve(self._h, C.c_void_p(req_cells_ptr), int(ncell), C.c_void_p(req_leaf_ptr), int(nleaf),
+                                                   C.c_void_p(M_out_ptr) if M_out_ptr else None,
+                                                   C.c_void_p(rec_out_ptr) if rec_out_ptr else None))
+
+    def let_halo_set(self, M2_ptr: int, rec2_ptr: int):
+        self._check(self._L.vpmb200_let_halo_set(self._h, C.c_void_p(M2_ptr) if M2_ptr else None,
+                                                 C.c_void_p(rec2_ptr) if rec2_ptr else None))
+
     def let_attach_records(self, rec_ptr: int, slot_n: int, nparticles):
         b = (C.c_int64 * len(nparticles))(*[int(v) for v in nparticles])
         self._check(self._L.vpmb200_let_attach_records(self._h, C.c_void_p(rec_ptr), int(slot_n), b))

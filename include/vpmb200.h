@@ -312,8 +312,22 @@ int32_t vpmb200_let_ptrs(vpmb200_handle h, void** ptrs3);           /* own cells
 int32_t vpmb200_let_attach_tree(vpmb200_handle h, const void* cells_recv, const double* M_recv, int64_t slot_cells,
                                 const int64_t* ncells, const int64_t* nparticles);
 int32_t vpmb200_let_attach_records(vpmb200_handle h, const double* rec_recv, int64_t slot_n, const int64_t* nparticles);
+/* Demand-driven halo (the memory-lean variant: a rank never holds another rank's multipoles or records unless its own
+ * traversal needs them).  Only the SKELETONS are all-gathered -> attach_skeleton (nleaves = leaves of every rank's tree,
+ * info4[1] of let_build) -> let_evaluate(stage 5: interaction lists) -> halo_plan: counts3[3 q + 0 / 1 / 2] = cells / leaves /
+ * records this rank requests from rank q, *req_cells_dev = int32 owner-local cell ids, *req_leaf_dev = int32 pairs (first
+ * record, count) in the owner's order, both grouped by owner -> [all-to-all of the requests] -> halo_serve on the owner
+ * (requested multipoles, requested leaves' records back to back; M_out = NULL re-serves records only) -> [all-to-all of the
+ * replies] -> halo_set(received multipoles, received records) -> let_evaluate(stage 6: M2L + L2L) -> let_evaluate(stage 2). */
+int32_t vpmb200_let_attach_skeleton(vpmb200_handle h, const void* cells_recv, int64_t slot_cells, const int64_t* ncells,
+                                    const int64_t* nparticles, const int64_t* nleaves);
+int32_t vpmb200_let_halo_plan(vpmb200_handle h, int64_t* counts3, void** req_cells_dev, void** req_leaf_dev);
+int32_t vpmb200_let_halo_serve(vpmb200_handle h, const void* req_cells, int64_t ncell, const void* req_leaf, int64_t nleaf,
+                               double* M_out, double* rec_out);
+int32_t vpmb200_let_halo_set(vpmb200_handle h, const double* M2, const double* rec2);
 /* n_own rows of U(3), J(9) in arrival order.  stage 0: everything.  stage 1: interaction lists + far field only (needs
- * attach_tree, not the records — the record exchange can overlap it); stage 2: L2P + near field + the output rows. */
+ * attach_tree, not the records — the record exchange can overlap it); stage 2: L2P + near field + the output rows;
+ * stage 5: interaction lists only; stage 6: M2L + L2L only (the halo variant plans its requests between the two). */
 int32_t vpmb200_let_evaluate(vpmb200_handle h, double* out_rows, int32_t reuse, int32_t stage);
 int32_t vpmb200_let_estr_records(vpmb200_handle h);                 /* own records -> E_str flavour (needs evaluate's J)    */
 int32_t vpmb200_let_estr_evaluate(vpmb200_handle h, double* out_rows);             /* n_own rows of E_str(3)                  */

@@ -41,7 +41,7 @@ def _single(P, kw, action):
         return eng.download(np.zeros_like(P))
 
 
-def _sharded(P, kw, world, action, bounds=None, let_level=5):
+def _sharded(P, kw, world, action, bounds=None, let_level=5, mode="let"):
     """`action(field_or_engine)` on a ShardedField of `world` engines sharing cuda:0."""
     import flowunsteady_b200 as fb
     from flowunsteady_b200.dist import ShardedField, partition
@@ -54,7 +54,7 @@ def _sharded(P, kw, world, action, bounds=None, let_level=5):
         lo, hi = parts[rank]
         eng = fb.Engine(max(hi - lo, 1) + 8, device=0, schemes=fb.default_schemes(**kw))
         eng.upload(P[lo:hi].copy())
-        sf = ShardedField(eng, max_local=max(hi - lo, 1) + 8, device="cuda:0", coll=coll, fmm="let", let_level=let_level)
+        sf = ShardedField(eng, max_local=max(hi - lo, 1) + 8, device="cuda:0", coll=coll, fmm=mode, let_level=let_level)
         action(sf)
         eng.synchronize()
         out = eng.download(np.zeros((hi - lo, 43)))
@@ -64,6 +64,12 @@ def _sharded(P, kw, world, action, bounds=None, let_level=5):
     return np.concatenate(run_ranks(world, body))
 
 
+@pytest.fixture(params=["let", "let_halo"])
+def let_mode(request):
+    """all-gathered essential tree / demand-driven halo (dist.py: ShardedField(fmm=...)): same tree, same lists, same results"""
+    return request.param
+
+
 def _assert_same(got, ref, names, tol):
     for name in names:
         err = relmax(got[:, GROUPS[name]], ref[:, GROUPS[name]])
@@ -71,46 +77,46 @@ def _assert_same(got, ref, names, tol):
 
 
 @pytest.mark.parametrize("world,kind,n", [(2, "cloud", 3001), (3, "cloud", 20000), (8, "rings", 60000), (4, "rotor", 40000)])
-def test_let_uj_estr_matches_one_gpu(world, kind, n):
+def test_let_uj_estr_matches_one_gpu(world, kind, n, let_mode):
     P = _field(n, kind)
     kw = dict(uj="fmm", sfs="constant")
     ref = _single(P, kw, lambda e: e.uj(True, True, True))
-    got = _sharded(P, kw, world, lambda f: f.uj(True, True, True))
+    got = _sharded(P, kw, world, lambda f: f.uj(True, True, True), mode=let_mode)
     _assert_same(got, ref, ["U", "J", "SFS"], 1e-12)
 
 
 @pytest.mark.parametrize("let_level", [1, 2, 4])
-def test_let_histogram_level_does_not_matter(let_level):
+def test_let_histogram_level_does_not_matter(let_level, let_mode):
     P = _field(12000, "cloud", seed=5)
     kw = dict(uj="fmm", fmm_p=3, fmm_theta=0.5, fmm_ncrit=20)
     ref = _single(P, kw, lambda e: e.uj())
-    got = _sharded(P, kw, 4, lambda f: f.uj(), let_level=let_level)
+    got = _sharded(P, kw, 4, lambda f: f.uj(), let_level=let_level, mode=let_mode)
     _assert_same(got, ref, ["U", "J"], 1e-12)
 
 
-def test_let_more_ranks_than_particles_and_empty_home_rank():
+def test_let_more_ranks_than_particles_and_empty_home_rank(let_mode):
     """6 ranks, 40 particles (a single leaf: one owner, five empty owners), one rank holding no home particles at all."""
     P = _field(40, "cloud", seed=9)
     kw = dict(uj="fmm")
     ref = _single(P, kw, lambda e: e.uj())
     bounds = [(0, 10), (10, 10), (10, 25), (25, 30), (30, 39), (39, 40)]
-    got = _sharded(P, kw, 6, lambda f: f.uj(), bounds=bounds)
+    got = _sharded(P, kw, 6, lambda f: f.uj(), bounds=bounds, mode=let_mode)
     _assert_same(got, ref, ["U", "J"], 1e-12)
 
 
-def test_let_nonzero_sigma_matches_one_gpu():
+def test_let_nonzero_sigma_matches_one_gpu(let_mode):
     """nonzero_sigma = true: the acceptance uses every cell's largest core size; for the partial top cells that maximum is
     taken over ALL ranks (per-bin sigma max, all-reduced), so the lists equal the one-GPU lists."""
     P = _field(20000, "cloud", seed=31)
     P[::7, 6] *= 2.5                      # uneven cores so that sigma_max matters
     kw = dict(uj="fmm", fmm_nonzero_sigma=1)
     ref = _single(P, kw, lambda e: e.uj())
-    got = _sharded(P, kw, 4, lambda f: f.uj())
+    got = _sharded(P, kw, 4, lambda f: f.uj(), mode=let_mode)
     _assert_same(got, ref, ["U", "J"], 1e-12)
 
 
 @pytest.mark.parametrize("world", [2, 5])
-def test_let_rk3_dynamic_sfs_steps_match_one_gpu(world):
+def test_let_rk3_dynamic_sfs_steps_match_one_gpu(world, let_mode):
     """Two whole RK3 + DynamicSFS + pedrizzetti steps (far-field reuse between the two filter evaluations on both sides)."""
     P = _field(9000, "cloud", seed=12)
     kw = dict(uj="fmm", integration="rungekutta3", relaxation="pedrizzetti", sfs="dynamic", alpha=0.999, force_positive=1,
@@ -121,13 +127,13 @@ def test_let_rk3_dynamic_sfs_steps_match_one_gpu(world):
             f.nextstep(2e-3, (1.0, -0.5, 0.25), relax=True)
 
     ref = _single(P, kw, steps)
-    got = _sharded(P, kw, world, steps)
+    got = _sharded(P, kw, world, steps, mode=let_mode)
     _assert_same(got, ref, ["X", "U", "J"], 1e-11)
     # through the dynamic procedure: 1e-12 x 1/(1 - alpha) = 1e-9 per evaluation, two steps (measured 1.1e-9 on C)
     _assert_same(got, ref, ["Gamma", "sigma", "C"], 5e-9)
 
 
-def test_let_accumulate_flag():
+def test_let_accumulate_flag(let_mode):
     """reset = false adds the new U, J to the rows the home rank holds."""
     P = _field(5000, "cloud", seed=2)
     kw = dict(uj="fmm")
@@ -137,5 +143,42 @@ def test_let_accumulate_flag():
         f.uj(False, False, False)
 
     ref = _single(P, kw, twice)
-    got = _sharded(P, kw, 3, twice)
+    got = _sharded(P, kw, 3, twice, mode=let_mode)
     _assert_same(got, ref, ["U", "J"], 1e-12)
+
+
+def test_let_halo_moves_less_than_the_all_gather_and_detaches_cleanly():
+    """Demand-driven halo: (1) a rank receives only the multipoles / records its lists name — well under what the all-gather
+    variant receives; (2) a plain one-GPU UJ_fmm on the same engine afterwards does not see the halo buffers."""
+    import flowunsteady_b200 as fb
+    from flowunsteady_b200.dist import ShardedField, partition
+    n, world = 60000, 8
+    P = _field(n, "rings")
+    kw = dict(uj="fmm")
+    parts = partition(n, world)
+
+    def body(rank, coll):
+        import torch
+        torch.cuda.set_device(0)
+        lo, hi = parts[rank]
+        eng = fb.Engine(hi - lo + 8, device=0, schemes=fb.default_schemes(**kw))
+        eng.upload(P[lo:hi].copy())
+        sf = ShardedField(eng, max_local=hi - lo + 8, device="cuda:0", coll=coll, fmm="let_halo")
+        sf.uj()
+        eng.synchronize()
+        L = sf._let
+        nm3 = 3 * (eng.get_schemes().fmm_p * (eng.get_schemes().fmm_p + 1) * (eng.get_schemes().fmm_p + 2)) // 6
+        full = 8 * (sum(L["np"]) - L["np"][rank]) * 10 + 8 * (sum(L["nc"]) - L["nc"][rank]) * nm3
+        got = L["halo_bytes"]
+        eng.uj()                                   # one-GPU evaluation of the home particles alone
+        eng.synchronize()
+        alone = eng.download(np.zeros((hi - lo, 43)))
+        eng.close()
+        return got, full, alone
+
+    res = run_ranks(world, body)
+    for rank, (got, full, alone) in enumerate(res):
+        assert got < 0.8 * full, (rank, got, full)
+        lo, hi = parts[rank]
+        ref = _single(P[lo:hi].copy(), kw, lambda e: e.uj())
+        _assert_same(alone, ref, ["U", "J"], 1e-12)
