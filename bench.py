@@ -87,7 +87,7 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle parity check of the timed state")
     ap.add_argument("--no-balance", action="store_true", help="UJ_fmm LET: cut the Morton curve by particle count, not by measured work")
     ap.add_argument("--let-timing", action="store_true", help="UJ_fmm mode: add a synchronised per-phase breakdown of one step")
-    ap.add_argument("--fmm-mode", default="let", choices=["let", "replicated"],
+    ap.add_argument("--fmm-mode", default="let", choices=["let", "let_halo", "replicated"],
                     help="multi-GPU UJ_fmm: local essential tree (default) or round 1's replicated tree")
     ap.add_argument("--cpu-targets", type=int, default=4096, help="targets of the CPU baseline slab")
     return ap.parse_args()
@@ -382,7 +382,7 @@ def run_ours(args):
         # secondary mode (BASELINE configs[1], [3], [4]): an O(N) method has no pair count; report particle-evaluations/s
         eval_ms = timed(lambda: field.uj(True, True, True), 3) / 3
         phases = None
-        if args.let_timing and args.fmm_mode == "let":   # outside the timed region: the phase timer drains the stream
+        if args.let_timing and args.fmm_mode in ("let", "let_halo"):   # outside the timed region: the phase timer drains the stream
             field.let_timing = {}
             t0 = time.perf_counter()
             step()
@@ -397,6 +397,20 @@ def run_ours(args):
                 dist.all_gather_object(allp, mine)
                 phases["per_rank"] = allp
         field.uj(True, True, True)          # U, J, SFS rows consistent with the current X, Gamma, sigma
+        # device memory in use on every GPU (driver view: engine cudaMalloc + torch exchange buffers + contexts) and, in the halo
+        # mode, the multipole + record bytes each rank RECEIVED for one evaluation against what the all-gather variant receives
+        free_b, total_b = torch.cuda.mem_get_info(local_rank)
+        memrow = {"rank": rank, "device_mem_used_gb": round((total_b - free_b) / 1e9, 3)}
+        Ls = field._let or {}
+        if "halo_bytes" in Ls:
+            nm3 = 3 * (sch.fmm_p * (sch.fmm_p + 1) * (sch.fmm_p + 2)) // 6
+            memrow["halo_received_mb"] = round(Ls["halo_bytes"] / 1e6, 2)
+            memrow["all_gather_would_receive_mb"] = round(8 * ((sum(Ls["np"]) - Ls["np"][rank]) * 10
+                                                               + (sum(Ls["nc"]) - Ls["nc"][rank]) * nm3) / 1e6, 2)
+        memrows = [memrow]
+        if world > 1:
+            memrows = [None] * world
+            dist.all_gather_object(memrows, memrow)
         parity = None if args.no_parity else fmm_parity_check(field, eng, sch, n, world, rank, local_rank)
         if rank == 0:
             cfg = make_config(args, n, world)
@@ -412,9 +426,12 @@ def run_ours(args):
                 "config": cfg,
                 "config_notes": {"parallelism": ("local essential tree: Morton-range ownership, all-to-all of particles, all-gather of "
                                                  "skeletons / multipoles / records, inverse all-to-all of results"
-                                                 if args.fmm_mode == "let" else "replicated tree, leaves split, all-reduce")
+                                                 if args.fmm_mode == "let" else
+                                                 "local essential tree, demand-driven halo: all-gather of skeletons only; multipoles "
+                                                 "and source records requested from their owners (all-to-all)"
+                                                 if args.fmm_mode == "let_halo" else "replicated tree, leaves split, all-reduce")
                                  + f" over {world} GPU(s)"},
-                "parity": parity, "let_phases_ms_rank0_one_step": phases,
+                "parity": parity, "memory_per_rank": memrows, "let_phases_ms_rank0_one_step": phases,
                 "let_balance": "work-weighted cut" if not args.no_balance else "count-based cut",
                 "gpu_launches": int(launches), "clocks": clocks,
                 "fmm_tree_rank0": eng.fmm_stats()}), flush=True)

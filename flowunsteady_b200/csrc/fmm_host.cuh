@@ -177,9 +177,13 @@ inline cudaError_t fmm_reserve_particles(FmmWorkspace& w, int64_t n, std::string
     return cudaSuccess;
 }
 
-// Cell-sized arrays; `cells` is a capacity (the tree build restarts with a larger one if it is exceeded).
+// Cell-sized arrays; `cells` is a capacity (the tree build restarts with a larger one if it is exceeded).  Grows with 12.5 %
+// headroom: the request follows the particle count, and a rank of a sharded field owns a few hundred particles more or fewer
+// from one evaluation to the next — an exact fit paid 12 cudaFree + 12 cudaMalloc (7 ms, and once 180 ms, in the tree phase
+// of a 2 x 2.5M-particle LET step: profiles/r02x_let_step_probe_2gpu.txt) on every upward drift of the owned count.
 inline cudaError_t fmm_reserve_cells(FmmWorkspace& w, int64_t cells, std::string& err) {
     if (cells <= w.cap_cells && w.cells) return cudaSuccess;
+    cells += cells / 8 + 1024;
     void* ptrs[] = {w.cells, w.nchild, w.child_off, w.leaf_flag, w.leaf_pos, w.leaves, w.leaves_alt, w.leaf_keys,
                     w.leaf_keys_alt, w.mine, w.m2l_off, w.p2p_off};
     for (void* p : ptrs)

@@ -1,6 +1,7 @@
 """2-GPU NCCL tests of the sharded field against the single-GPU engine (skipped when < 2 GPUs are visible): the direct path
 (all-gather of source tiles) and UJ_fmm with the local essential tree (all-to-all of particle rows, all-gather of skeletons /
-multipoles / records, inverse all-to-all) and with round 1's replicated tree.  The same LET logic runs on ONE GPU with
+multipoles / records — or, "let_halo", of the skeletons only with multipoles / records on request — inverse all-to-all) and
+with round 1's replicated tree.  The same LET logic runs on ONE GPU with
 in-process collectives in tests/test_gpu_let.py."""
 import os
 import socket
@@ -50,6 +51,8 @@ def _worker(rank, world, port, n, kw, out_dir, fmm_mode="let"):
     (dict(integration="rungekutta3", sfs="dynamic", force_positive=1, clippings=1), "let"),
     (dict(integration="rungekutta3", uj="fmm", fmm_nonzero_sigma=1, sfs="constant", clippings=1), "let"),
     (dict(integration="rungekutta3", uj="fmm", sfs="dynamic", force_positive=1, clippings=1), "let"),
+    (dict(integration="rungekutta3", uj="fmm", fmm_nonzero_sigma=1, sfs="constant", clippings=1), "let_halo"),
+    (dict(integration="rungekutta3", uj="fmm", sfs="dynamic", force_positive=1, clippings=1), "let_halo"),
     (dict(integration="rungekutta3", uj="fmm", fmm_nonzero_sigma=1, sfs="constant", clippings=1), "replicated")])
 def test_two_gpu_matches_one_gpu(kw, fmm_mode, tmp_path):
     if torch.cuda.device_count() < 2:
