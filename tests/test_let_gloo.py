@@ -77,7 +77,7 @@ CASES = {
     "uj_estr_all_near": dict(n=333, op="uj", schemes=dict(sfs="constant"), far=None, truth="oracle"),
     # with a far field (the multipole channel carries data): equal to the same stand-in on ONE rank
     "uj_estr_far": dict(n=250, op="uj", schemes=dict(sfs="constant"), far=2, level=3, truth="one_rank"),
-    "rk3_dynamic_sfs_far": dict(n=150, op="step", far=2, level=3, truth="one_rank",
+    "rk3_dynamic_sfs_far": dict(n=180, op="step", far=2, level=3, truth="one_rank",
                                 schemes=dict(integration="rungekutta3", sfs="dynamic", force_positive=1, clippings=1)),
     "accumulate_far": dict(n=150, op="uj_twice", schemes=dict(), far=2, level=2, truth="one_rank"),
     # three ranks, one of them without home particles; 7 particles on 3 ranks (owners without particles)
