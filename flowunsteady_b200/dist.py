@@ -116,6 +116,8 @@ class ShardedField:
         self.coll = coll if coll is not None else TorchCollectives(group)
         self.world, self.rank = self.coll.world, self.coll.rank
         self.device = torch.device(device)
+        if fmm not in ("let", "let_halo", "replicated"):
+            raise ValueError(f"fmm must be 'let', 'let_halo' or 'replicated', not {fmm!r}")
         self.fmm_mode = fmm if hasattr(backend, "let_bounds") else "replicated"
         self.let_level = int(let_level)
         self.td = int(backend.tile_doubles())
