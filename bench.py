@@ -65,7 +65,9 @@ def make_config(args, n: int, world: int) -> dict:
     return {"workload": f"{FIELD_NAMES[args.field]}, direct P2P FP64, gaussianerf, rVPM, rungekutta3 + pedrizzetti, {sfs}",
             "particles": int(n), "sfs": args.sfs, "uj": args.uj, "field": args.field,
             "evaluations_per_step": EVALS_PER_STEP[args.sfs], "estr_passes_per_step": ESTR_PER_STEP[args.sfs],
-            "gpus": int(world)}
+            "gpus": int(world),
+            # timing rule: inputs larger than L2 between timed iterations (no explicit flush)
+            "l2": f"inputs larger than L2: particle state {344 * int(n) / 1e6:.0f} MB (344 B/particle), rewritten every substep"}
 
 
 # --------------------------------------------------------------------------------------------------------------
